@@ -1,0 +1,96 @@
+"""ctypes binding of libdcb200.so -- the C ABI declared in include/dcb200.h.
+
+There is no fallback: if the shared library is missing or a call fails, this raises.  PyTorch is used by the
+callers only for device memory (``tensor.data_ptr()``), streams and torch.distributed.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libdcb200.so")
+
+F32, BF16 = 0, 1
+ACT_NONE, ACT_SILU, ACT_GELU_TANH, ACT_GEGLU = 0, 1, 2, 3
+ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05 = 0, 1, 2
+MAX_SEGS = 12
+
+c_void_p, c_int, c_i32, c_i64, c_u64, c_float = C.c_void_p, C.c_int, C.c_int32, C.c_int64, C.c_uint64, C.c_float
+
+
+class Seg(C.Structure):
+    _fields_ = [("src", c_void_p), ("C", c_i32), ("H", c_i32), ("W", c_i32), ("c_off", c_i32), ("kc", c_i32),
+                ("dy", c_i32), ("dx", c_i32), ("stride", c_i32), ("_r0", c_i32), ("_r1", c_i32)]
+
+
+class GemmDesc(C.Structure):
+    _fields_ = [("dtype", c_i32), ("engine", c_i32), ("NB", c_i32), ("OH", c_i32), ("OW", c_i32), ("N", c_i32),
+                ("nseg", c_i32), ("_r0", c_i32), ("seg", Seg * MAX_SEGS),
+                ("W", c_void_p), ("bias", c_void_p), ("rowvec", c_void_p), ("rowvec_idx", c_void_p),
+                ("gate", c_void_p), ("residual", c_void_p), ("res_idx", c_void_p), ("out", c_void_p),
+                ("mse_target", c_void_p), ("mse_scale", c_void_p), ("mse_part", c_void_p),
+                ("rowvec_ld", c_i32), ("gate_ld", c_i32), ("rows_per_group", c_i32), ("act", c_i32),
+                ("act_post", c_i32), ("res_ld", c_i32), ("res_mod", c_i32), ("res_dtype", c_i32),
+                ("out_ld", c_i32), ("out_dtype", c_i32), ("mse_div", c_i32), ("mse_ld", c_i32)]
+
+
+_PROTOS = {
+    "dcb_version": (c_int, []),
+    "dcb_last_error": (C.c_char_p, []),
+    "dcb_launch_count": (c_i64, []),
+    "dcb_prologue": (c_int, [c_int, c_int, c_void_p, c_void_p, c_u64, c_i64, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                             c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "dcb_timestep_embed": (c_int, [c_int, c_void_p, c_int, c_int, c_int, c_float, c_float, c_void_p, c_void_p]),
+    "dcb_gemm": (c_int, [C.POINTER(GemmDesc), c_void_p]),
+    "dcb_gemm_mse_layout": (c_int, [C.POINTER(GemmDesc), C.POINTER(c_i32), C.POINTER(c_i32)]),
+    "dcb_mse_finalize": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
+    "dcb_eps_mse": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_i64, c_void_p, c_int, c_void_p]),
+    "dcb_groupnorm_stats": (c_int, [c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                                    c_void_p]),
+    "dcb_groupnorm_apply": (c_int, [c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                                    c_void_p, c_void_p, c_float, c_int, c_void_p, c_void_p]),
+    "dcb_layernorm": (c_int, [c_int, c_void_p, c_i64, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int,
+                              c_int, c_void_p, c_void_p]),
+    "dcb_attention": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float,
+                              c_void_p, c_int, c_void_p]),
+    "dcb_haar_dwt": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
+    "dcb_haar_idwt": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
+    "dcb_upsample2x": (c_int, [c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "dcb_nhwc_to_nchw": (c_int, [c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "dcb_unpatchify": (c_int, [c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "dcb_cast_f32": (c_int, [c_int, c_void_p, c_i64, c_void_p, c_void_p]),
+}
+
+EXPORTS = tuple(_PROTOS)
+_lib = None
+
+
+class DcbError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load libdcb200.so (once).  Fails loudly -- there is no CPU / torch fallback for the hot path."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} not found: build the CUDA extension first (python -m dcb200.build, or "
+                f"__graft_entry__.build()).  dcb200 has no fallback path.")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in _PROTOS.items():
+            fn = getattr(L, name)  # AttributeError here == ABI drift
+            fn.restype, fn.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().dcb_last_error().decode("utf-8", "replace")
+        raise DcbError(f"dcb200 {what} failed (rc={rc}): {msg}")
+
+
+def launch_count() -> int:
+    return int(lib().dcb_launch_count())

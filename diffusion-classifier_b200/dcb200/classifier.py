@@ -1,0 +1,243 @@
+"""DiffusionClassifier -- drop-in for the reference's hot path, diffusion/diffusion_classifier.py:17-161,657-725.
+
+Same constructor (``DiffusionClassifier(backbone, config)``), same attributes (``model, ema, encoder, null_token,
+schedule, pred_param, config``) and the same ``classify(x, text=None, fast=False) -> LongTensor[BS]`` contract,
+including its assertions, its CPU-generator draw of t (:688), its ``errors`` table initialised to +inf (:669)
+and its per-stage ``mean -> topk(largest=False)`` pruning (:718-721).
+
+What changes is how the work is issued (B200-first):
+  * the (image b, timestep j, alive class c) triple loop is folded into the denoiser's batch axis: one launch
+    sequence scores ``U`` (b, j) units x ``n_alive`` classes, sharing z_t / eps across the classes of a unit;
+  * q_sample is a fused prologue kernel that also stages the first layer's operand (dcb_prologue);
+  * the eps-MSE is the epilogue of the last GEMM (predicted noise never reaches HBM);
+  * the class token's cross-attention collapses to a per-class bias table computed once per call;
+  * with torch.distributed initialised and ``config.dcb_shard == 'timestep'`` the (b, j) units are sharded over
+    ranks and the stage's error slab is combined by ONE all-reduce (NCCL over NVLink) before the top-k.
+"""
+from __future__ import annotations
+
+import math
+import os
+
+import torch
+import torch.nn as nn
+
+from . import engine as E
+from .dit import DiT
+from .ema import EMA
+from .unet import UNetCondition2D
+
+
+def log(t, eps=1e-20):
+    return torch.log(t.clamp(min=eps))
+
+
+def shard_range(n_units, rank, world):
+    """Contiguous slice of the stage's flattened (timestep j, image b) units owned by ``rank``."""
+    return (n_units * rank) // world, (n_units * (rank + 1)) // world
+
+
+def combine_stage_errors(errors, slab, classes, start, end, dist=None):
+    """Merge one stage's per-rank error slab [BS, classes, nj] (zeros where a rank owns nothing) into the
+    reference-shaped ``errors`` table: ONE sum all-reduce, then only the (image, alive class) entries are written so
+    pruned classes keep +inf exactly as in diffusion_classifier.py:669,713-721.  Adding zeros is exact, hence labels
+    and sums are bit-identical for every world size."""
+    if dist is not None:
+        dist.all_reduce(slab)
+    alive = torch.zeros(errors.shape[0], errors.shape[1], dtype=torch.bool, device=errors.device)
+    alive.scatter_(1, classes, True)
+    errors[:, :, start:end] = torch.where(alive.unsqueeze(-1), slab, errors[:, :, start:end])
+    return errors
+
+
+class DiffusionClassifier(nn.Module):
+    def __init__(self, backbone: nn.Module, config):
+        super().__init__()
+        self.config = config
+        pred_param = self.config.pred_param
+        assert pred_param in ['v', 'eps'], "Invalid prediction parameterization. Must be 'v' or 'eps'"
+        self.pred_param = pred_param
+        schedule = self.config.schedule
+        assert schedule in ['cosine', 'shifted_cosine'], "Invalid schedule. Must be 'cosine' or 'shifted_cosine'"
+        self.schedule = self.logsnr_schedule_cosine if schedule == 'cosine' else self.logsnr_schedule_cosine_shifted
+        self.noise_d = self.config.noise_d
+        self.image_d = self.config.image_size
+        self.cfg_w = self.config.cfg_w
+        assert isinstance(backbone, nn.Module), "Model must be an instance of torch.nn.Module."
+        self.model = backbone
+        self.ema = EMA(self.model, beta=config.ema_beta, update_after_step=config.ema_warmup,
+                       update_every=config.ema_update_freq)
+        self.encoder_type = self.config.encoder_type
+        if self.encoder_type == 't5':
+            raise NotImplementedError("the t5 text encoder is not on the classification hot path")
+        elif self.encoder_type == 'nn':
+            self.encoder = nn.Embedding(self.config.classes + 1, backbone.config.encoder_hid_dim)
+            self.tokenizer = None
+            self.null_token = self.config.classes
+        elif self.encoder_type == 'DiT':
+            self.tokenizer = None
+            self.encoder = None
+            self.null_token = self.config.classes
+        self.last_errors = None  # [BS, classes, T] fp32 table of the most recent classify() call
+        self._eps_calls = 0
+
+    # ---- schedule (diffusion_classifier.py:119-161), evaluated exactly as the reference does ------------------
+    def logsnr_schedule_cosine(self, t, logsnr_min=-15, logsnr_max=15):
+        logsnr_max = logsnr_max + math.log(self.noise_d / self.image_d)
+        logsnr_min = logsnr_min + math.log(self.noise_d / self.image_d)
+        t_min = math.atan(math.exp(-0.5 * logsnr_max))
+        t_max = math.atan(math.exp(-0.5 * logsnr_min))
+        return -2 * log(torch.tan(t_min + t * (t_max - t_min)))
+
+    def logsnr_schedule_cosine_shifted(self, t):
+        return self.logsnr_schedule_cosine(t) + 2 * math.log(self.noise_d / self.image_d)
+
+    def encode_text_prompt(self, text):
+        if self.encoder_type == 'nn':
+            return self.encoder(text).unsqueeze(1)
+        return text
+
+    # ---- helpers ------------------------------------------------------------------------------------------------
+    def _dist(self):
+        import torch.distributed as dist
+        if getattr(self.config, "dcb_shard", None) == "timestep" and dist.is_available() and dist.is_initialized() \
+                and dist.get_world_size() > 1:
+            return dist, dist.get_rank(), dist.get_world_size()
+        return None, 0, 1
+
+    def _max_samples(self, H, W):
+        v = getattr(self.config, "dcb_max_batch", None)
+        if v:
+            return int(v)
+        return int(os.environ.get("DCB_MAX_BATCH", max(1, min(1024, (1 << 22) // (H * W)))))
+
+    # ---- the hot path ---------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def classify(self, x, text=None, fast=False, t_all=None, eps_all=None):
+        """``t_all`` [T,BS] / ``eps_all`` [T,BS,C,H,W] optionally inject pre-drawn noise (parity runs); by default
+        t comes from the CPU generator exactly as the reference draws it and eps from the in-kernel Philox stream
+        (``config.dcb_eps == 'torch'`` draws eps with torch.randn_like per step like the reference instead)."""
+        cfg = self.config
+        assert self.encoder_type is not None, "Encoder must be provided for classification."
+        assert len(cfg.evaluation_per_stage) == cfg.n_stages, \
+            "Number of evaluations per stage must match the number of stages."
+        assert len(cfg.n_keep_per_stage) == cfg.n_stages, \
+            "Number of classes to keep per stage must match the number of stages."
+        assert cfg.n_keep_per_stage[-1] == 1, "Only one class should be selected at the end of the classification process."
+        assert cfg.n_fast_classes <= cfg.classes and cfg.n_fast_classes >= 2, \
+            "Number of fast classes must be less than or equal to the total number of classes. Must be at least 2."
+        if not x.is_cuda:
+            raise RuntimeError("dcb200.DiffusionClassifier.classify needs CUDA tensors; there is no CPU path")
+
+        per_stage = [0] + list(cfg.evaluation_per_stage)
+        BS, Cimg, H, W = x.shape
+        dev = x.device
+        T = per_stage[-1]
+        errors = torch.full((BS, cfg.classes, T), torch.inf, device=dev)
+        if fast:
+            text = text.view(-1, 1).to(dev)
+            classes = torch.arange(cfg.classes).repeat(BS, 1).to(dev)
+            wrong = classes[(classes == text) == False].view(BS, -1)  # noqa: E712
+            sel = torch.randint(0, wrong.shape[1], (BS, cfg.n_fast_classes - 1)).to(dev)
+            classes = torch.cat((text, torch.gather(wrong, 1, sel)), dim=1)
+        else:
+            classes = torch.arange(cfg.classes).repeat(BS, 1).to(dev)
+
+        net = self.ema.ema_model  # the reference scores with the EMA copy (:700)
+        is_dit = isinstance(net, DiT)
+        if not isinstance(net, (UNetCondition2D, DiT)):
+            raise TypeError("backbone must be a dcb200.UNetCondition2D or dcb200.DiT")
+        ctx = net.make_ctx(dev)
+        pk = net.packed(ctx)
+        xin = x.contiguous().float()
+        v_param = self.pred_param == 'v'
+        table = None
+        if not is_dit:  # collapsed cross-attention bias per class, once per call
+            table = net.cross_attn_table(ctx, pk, E.cast(ctx, self.encoder.weight))
+        patch = net.config.patch_size if is_dit else 1
+        No = (patch * patch * Cimg) if is_dit else Cimg
+        rows = (H // patch) * (W // patch)
+        fused = (ctx.precision == "bf16") and rows % 128 == 0 and not getattr(cfg, "dcb_unfused_mse", False)
+        eps_mode = getattr(cfg, "dcb_eps", None) or "philox"
+        seed = int(torch.initial_seed() & 0x7FFFFFFFFFFFFFFF) + 0x9E3779B9 * self._eps_calls
+        self._eps_calls += 1
+        dist, rank, world = self._dist()
+        max_s = self._max_samples(H, W)
+
+        for i in range(cfg.n_stages):
+            start, end = per_stage[i], per_stage[i + 1]
+            nj = end - start
+            # t for every step of the stage from the CPU generator, in the reference's order (:688)
+            if t_all is None:
+                t_stage = torch.stack([torch.rand(BS) for _ in range(nj)])
+            else:
+                t_stage = t_all[start:end].detach().cpu().float()
+            logsnr = self.schedule(t_stage).to(dev)                 # [nj, BS]
+            alpha = torch.sqrt(torch.sigmoid(logsnr)).reshape(-1).contiguous()
+            sigma = torch.sqrt(torch.sigmoid(-logsnr)).reshape(-1).contiguous()
+            logsnr = logsnr.reshape(-1).float().contiguous()
+            if eps_all is not None:
+                eps_stage = eps_all[start:end].to(dev).float().reshape(nj * BS, Cimg, H, W).contiguous()
+            elif eps_mode == "torch":
+                eps_stage = torch.stack([torch.randn_like(xin) for _ in range(nj)]).reshape(nj * BS, Cimg, H, W)
+            else:
+                eps_stage = None
+            nk = classes.shape[1]
+            n_units = nj * BS
+            lo, hi = shard_range(n_units, rank, world)
+            chunk = max(1, max_s // nk)
+            slab = torch.zeros(BS, cfg.classes, nj, device=dev) if dist is not None else None
+            for u0 in range(lo, hi, chunk):
+                U = min(chunk, hi - u0)
+                units = torch.arange(u0, u0 + U, device=dev)
+                img = (units % BS).to(torch.int32)
+                jrel = units // BS
+                cls = classes[img.long()]                              # [U, nk]
+                cls32 = cls.reshape(-1).to(torch.int32).contiguous()
+                a_in, target = E.prologue(
+                    ctx, 1 if is_dit else 0, xin, U, nk, Cimg, H, W, pk.kpad_in, patch=patch,
+                    eps=None if eps_stage is None else eps_stage[u0:u0 + U], seed=seed, unit_id0=start * BS + u0,
+                    alpha=alpha[u0:u0 + U], sigma=sigma[u0:u0 + U], img=img, want_target=True, v_param=v_param)
+                err = torch.empty(U * nk, device=dev, dtype=torch.float32)
+                mse = dict(target=target, div=nk, ld=No, err=err, fused=fused,
+                           scale=alpha[u0:u0 + U].repeat_interleave(nk).contiguous() if v_param else None)
+                if is_dit:
+                    net.run(ctx, pk, a_in, logsnr[u0:u0 + U], U, nk, cls32, mse=mse)
+                else:
+                    net.run(ctx, pk, a_in, logsnr[u0:u0 + U], U, nk, H, W, table, xattn_idx=cls32, mse=mse)
+                b_idx = img.long().repeat_interleave(nk)
+                j_idx = jrel.repeat_interleave(nk)
+                if slab is None:
+                    errors[b_idx, cls.reshape(-1), start + j_idx] = err      # reference :713-714
+                else:
+                    slab[b_idx, cls.reshape(-1), j_idx] = err
+            if slab is not None:
+                combine_stage_errors(errors, slab, classes, start, end, dist)  # one collective per stage
+            num_keep = cfg.n_keep_per_stage[i]
+            end_of_stage_errors = errors[:, :, :end].mean(dim=2)             # reference :719
+            _, keep_indices = torch.topk(end_of_stage_errors, num_keep, dim=1, largest=False)
+            classes = keep_indices
+        assert classes.shape[1] == 1, "Only one class should be selected at the end of the classification process."
+        self.last_errors = errors
+        return classes[:, 0]
+
+    # ---- callers of the hot path (diffusion_classifier.py:532-578); next-row f1 in SURVEY 8 ---------------------
+    @torch.no_grad()
+    def evaluate(self, val_dataloader, stop_idx=None, metrics=None, classification=False, from_t=1):
+        if not classification:
+            raise NotImplementedError("sampling (DDPM + CFG) is outside the classification hot path (SURVEY 8 f2)")
+        val_samples, batches = [], []
+        dev = next(self.ema.ema_model.parameters()).device
+        for idx, batch in enumerate(val_dataloader):
+            batch = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in batch.items()}
+            x = batch["images"]
+            p = batch["prompt"] if "prompt" in batch.keys() else None
+            sample = self.classify(x, p, fast=bool(self.config.fast_classification))
+            if metrics is not None:
+                for metric in metrics:
+                    metric.update((sample, batch))
+            val_samples.append(sample)
+            batches.append(batch)
+            if stop_idx is not None and idx == stop_idx:
+                break
+        return val_samples, batches, metrics

@@ -1,0 +1,155 @@
+// common.cuh -- shared host/device helpers for libdcb200 (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../../include/dcb200.h"
+
+namespace dcb {
+
+// ---- host side error / launch bookkeeping (api.cu owns the storage) ------------------------------------
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+int num_sms();
+
+#define DCB_REQUIRE(cond, ...)            \
+  do {                                    \
+    if (!(cond)) {                        \
+      dcb::set_error(__VA_ARGS__);        \
+      return DCB_EINVAL;                  \
+    }                                     \
+  } while (0)
+
+#define DCB_CHECK_LAUNCH(name)                                            \
+  do {                                                                    \
+    cudaError_t e__ = cudaGetLastError();                                 \
+    if (e__ != cudaSuccess) {                                             \
+      dcb::set_error("%s launch failed: %s", name, cudaGetErrorString(e__)); \
+      return (int)e__;                                                    \
+    }                                                                     \
+    dcb::count_launch();                                                  \
+  } while (0)
+
+// ---- device helpers --------------------------------------------------------------------------------------
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float gelu_tanh_f(float x) {
+  // torch F.gelu(approximate='tanh'): 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3)))
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  float u = k0 * (x + k1 * x * x * x);
+  return 0.5f * x * (1.0f + tanhf(u));
+}
+__device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.7071067811865476f)); }
+
+__device__ __forceinline__ float apply_act(int act, float v) {
+  if (act == DCB_ACT_SILU) return silu_f(v);
+  if (act == DCB_ACT_GELU_TANH) return gelu_tanh_f(v);
+  return v;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <typename T>
+__device__ __forceinline__ float to_f(T v);
+template <>
+__device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+template <typename T>
+__device__ __forceinline__ T from_f(float v);
+template <>
+__device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float load_as_f(const void* p, int dtype, int64_t i) {
+  return dtype == DCB_BF16 ? __bfloat162float(((const __nv_bfloat16*)p)[i]) : ((const float*)p)[i];
+}
+__device__ __forceinline__ void store_from_f(void* p, int dtype, int64_t i, float v) {
+  if (dtype == DCB_BF16) ((__nv_bfloat16*)p)[i] = __float2bfloat16_rn(v);
+  else ((float*)p)[i] = v;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ void unpack_bf16x8(const uint4& u, float* f) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack_bf16x8(const float* f) {
+  uint4 u;
+  u.x = pack_bf16x2(f[0], f[1]);
+  u.y = pack_bf16x2(f[2], f[3]);
+  u.z = pack_bf16x2(f[4], f[5]);
+  u.w = pack_bf16x2(f[6], f[7]);
+  return u;
+}
+
+// ---- device-side GEMM description shared by the SIMT and tcgen05 engines ---------------------------------
+struct SegDev {
+  const void* src;
+  int C, H, W, c_off, kc, dy, dx, stride;
+};
+
+struct EpiDev {
+  int M, N, n_out;  // n_out = N (or N/2 for GEGLU)
+  int rows_per_sample;  // OH*OW
+  const float* bias;
+  const float* rowvec;
+  const int* rowvec_idx;
+  const float* gate;
+  const void* residual;
+  const int* res_idx;
+  void* out;
+  const float* mse_target;
+  const float* mse_scale;
+  float* mse_part;
+  int rowvec_ld, gate_ld, rows_per_group;
+  int act, act_post;
+  int res_ld, res_mod, res_dtype;
+  int out_ld, out_dtype;
+  int mse_div, mse_ld;
+};
+
+struct GemmDev {
+  int dtype;
+  int NB, OH, OW;
+  int nseg, K;
+  SegDev seg[DCB_MAX_SEGS];
+  const void* W;
+  EpiDev epi;
+};
+
+// scalar epilogue for one accumulator value (column index n is in OUTPUT space; bias handled by caller)
+__device__ __forceinline__ float epi_scalar(const EpiDev& e, int m, int n, float v) {
+  int grp = e.rows_per_group > 0 ? m / e.rows_per_group : 0;
+  if (e.rowvec) v += e.rowvec[(int64_t)(e.rowvec_idx ? e.rowvec_idx[grp] : grp) * e.rowvec_ld + n];
+  v = apply_act(e.act, v);
+  if (e.gate) v *= e.gate[(int64_t)grp * e.gate_ld + n];
+  if (e.residual) {
+    int64_t r = e.res_idx ? e.res_idx[m] : (e.res_mod > 0 ? m % e.res_mod : m);
+    v += load_as_f(e.residual, e.res_dtype, r * e.res_ld + n);
+  }
+  v = apply_act(e.act_post, v);
+  return v;
+}
+
+// host entry points of the engines (gemm_simt.cu / gemm_tc.cu)
+int launch_gemm_simt(const GemmDev& g, cudaStream_t st);
+int launch_gemm_tc(const GemmDev& g, cudaStream_t st);
+int tc_geometry(const GemmDev& g, int* m_tiles, int* n_tiles, int* BN);
+
+}  // namespace dcb

@@ -1,0 +1,594 @@
+// gemm_tc.cu -- tcgen05 / TMEM / TMA implicit-GEMM engine (bf16 in, fp32 accumulate) for sm_100a.
+//
+// One persistent, warp-specialised kernel covers every dense contraction on the denoiser path
+// (diffusers ResnetBlock2D conv1/conv2/conv_shortcut, Down/Upsample2D convs, Transformer2D proj_in/out,
+// attention projections, GEGLU/GELU feed-forwards, DiT patch-embed / QKV / MLP / adaLN linears,
+// conv_out / proj_out_2 with the fused eps-MSE epilogue):
+//
+//   D[m, n] = sum over K-segments  A_seg[pixel(m) + tap_seg, c] * W[n, k]        m = (sample, y, x) output pixel
+//
+//   warp 0      TMA producer: for each K block (64 channels of one segment/tap) one 5-D tiled TMA load pulls the
+//               [128 pixels x 64 ch] activation box straight out of the NHWC tensor -- the box is shifted by the
+//               tap offset and TMA's out-of-bounds zero fill *is* the conv padding; stride-2 convs use a
+//               (2C, W/2, 2, H/2, N) view of the same memory -- plus one 2-D load of the [BN x 64] weight box.
+//               Both land 128B-swizzled, i.e. directly in the canonical K-major UMMA layout.
+//   warp 1      MMA issuer: one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16) x4 per
+//               stage into a TMEM accumulator; tcgen05.commit releases the smem stage / publishes the accumulator.
+//   warps 2-5   epilogue: tcgen05.ld 32x32b.x16 (one TMEM lane = one output pixel per thread), fused
+//               bias / time-embedding row vector / activation / GEGLU / adaLN gate / residual / eps-MSE, bf16 store.
+//   TMEM is double buffered (2 x BN <= 512 columns) so the epilogue of tile i overlaps the mainloop of tile i+1.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include <mutex>
+
+#include "common.cuh"
+
+namespace dcb {
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 64;                         // 64 bf16 = 128 B = one swizzle-128B row
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;     // 16 KB
+constexpr int TC_THREADS = 192;
+constexpr int TC_MAX_STAGES = 8;
+constexpr int TC_SMEM_BUDGET = 200 * 1024;
+
+struct TcSeg {
+  int map;  // which A tensor map
+  int c0;   // channel coordinate (dim 0) of the first K block (includes the x-parity offset for stride 2)
+  int dx, p, dy;
+  int nkb;  // K blocks (of 64) in this segment
+};
+
+struct TcParams {
+  int nseg;
+  TcSeg seg[DCB_MAX_SEGS];
+  int tiles_x, tiles_y, tiles_nb, n_tiles, total_tiles;
+  int bw, bh, bn;  // pixel box of one M tile: bw*bh*bn == 128
+  int OW, OH, NB;
+  int BN, stages, total_kb;
+  uint32_t idesc;
+};
+
+// ---- PTX wrappers ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// Bounded wait: a protocol bug becomes a trap (an error the host sees) instead of a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  uint64_t t0 = 0;
+  for (uint32_t spins = 0;; ++spins) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+    if ((spins & 0x3ff) == 0x3ff) {
+      uint64_t now = globaltimer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ull) {
+        printf("dcb gemm_tc: mbarrier wait timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x,
+               bar, parity);
+        __trap();
+      }
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 lanes x 16 consecutive fp32 columns: thread t of the warp receives lane (base_lane + t)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+// K-major, 128B-swizzled operand tile ([rows][64 bf16], 8-row atoms of 1024 B): SBO = 1024 B, LBO unused (=1),
+// descriptor version 1 (Blackwell), layout type 2 (SWIZZLE_128B).  cf. cute::UMMA::SmemDescriptor.
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// ---- epilogue for 16 consecutive output columns of one row ------------------------------------------------
+// v[] holds acc (+bias already added by caller for GEGLU); n0 is the first OUTPUT column.
+__device__ __forceinline__ void epi_store16(const EpiDev& e, int m, int n0, float* v, float& mse_acc, int sample,
+                                            int pix) {
+  const int grp = e.rows_per_group > 0 ? m / e.rows_per_group : 0;
+  const int nvalid = min(16, e.n_out - n0);
+  if (e.rowvec) {
+    const float* rv = e.rowvec + (int64_t)(e.rowvec_idx ? e.rowvec_idx[grp] : grp) * e.rowvec_ld + n0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (i < nvalid) v[i] += rv[i];
+  }
+  if (e.act == DCB_ACT_SILU || e.act == DCB_ACT_GELU_TANH) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = apply_act(e.act, v[i]);
+  }
+  if (e.gate) {
+    const float* gt = e.gate + (int64_t)grp * e.gate_ld + n0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (i < nvalid) v[i] *= gt[i];
+  }
+  if (e.residual) {
+    const int64_t r = e.res_idx ? e.res_idx[m] : (e.res_mod > 0 ? m % e.res_mod : m);
+    const int64_t off = r * e.res_ld + n0;
+    if (e.res_dtype == DCB_BF16 && nvalid == 16 && (off & 7) == 0) {
+      const uint4* rp = reinterpret_cast<const uint4*>((const __nv_bfloat16*)e.residual + off);
+      float f[8];
+      unpack_bf16x8(rp[0], f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] += f[i];
+      unpack_bf16x8(rp[1], f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[8 + i] += f[i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (i < nvalid) v[i] += load_as_f(e.residual, e.res_dtype, off + i);
+    }
+  }
+  if (e.act_post != DCB_ACT_NONE) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = apply_act(e.act_post, v[i]);
+  }
+  if (e.mse_part) {
+    const float sc = e.mse_scale ? e.mse_scale[sample] : 1.f;
+    const float* tg = e.mse_target + ((int64_t)(sample / e.mse_div) * e.rows_per_sample + pix) * e.mse_ld + n0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (i < nvalid) {
+        float d = sc * v[i] - tg[i];
+        mse_acc = fmaf(d, d, mse_acc);
+      }
+  }
+  if (e.out) {
+    const int64_t off = (int64_t)m * e.out_ld + n0;
+    if (e.out_dtype == DCB_BF16 && nvalid == 16 && (off & 7) == 0) {
+      uint4* op = reinterpret_cast<uint4*>((__nv_bfloat16*)e.out + off);
+      op[0] = pack_bf16x8(v);
+      op[1] = pack_bf16x8(v + 8);
+    } else if (e.out_dtype == DCB_F32 && nvalid == 16 && (off & 3) == 0) {
+      float4* op = reinterpret_cast<float4*>((float*)e.out + off);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) op[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (i < nvalid) store_from_f(e.out, e.out_dtype, off + i, v[i]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+               const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB,
+               const __grid_constant__ TcParams p, const __grid_constant__ EpiDev e) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: [stages x (A tile | B tile)] then barriers
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int b_bytes = p.BN * TC_BK * 2;
+  const int stage_bytes = TC_A_BYTES + b_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  uint64_t* full_bar = bars;                          // [stages]
+  uint64_t* empty_bar = bars + TC_MAX_STAGES;         // [stages]
+  uint64_t* tfull_bar = bars + 2 * TC_MAX_STAGES;     // [2]
+  uint64_t* tempty_bar = bars + 2 * TC_MAX_STAGES + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_MAX_STAGES + 4);
+  float* mse_smem = reinterpret_cast<float*>(tmem_slot + 2);  // [4]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&mapA0);
+    prefetch_tmap(&mapB);
+    for (int i = 0; i < p.stages; ++i) {
+      mbar_init(smem_u32(&full_bar[i]), 1);
+      mbar_init(smem_u32(&empty_bar[i]), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&tfull_bar[i]), 1);
+      mbar_init(smem_u32(&tempty_bar[i]), 4);  // one arrive per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {  // TMEM allocation (whole 512 columns: 1 CTA per SM by construction)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int tn = tile % p.n_tiles;
+        int tm = tile / p.n_tiles;
+        const int tx = tm % p.tiles_x;
+        tm /= p.tiles_x;
+        const int ty = tm % p.tiles_y;
+        const int tb = tm / p.tiles_y;
+        const int x0 = tx * p.bw, y0 = ty * p.bh, nb0 = tb * p.bn;
+        int kb_glob = 0;
+        for (int s = 0; s < p.nseg; ++s) {
+          const TcSeg sg = p.seg[s];
+          const CUtensorMap* mp = sg.map == 0 ? &mapA0 : (sg.map == 1 ? &mapA1 : &mapA2);
+          for (int kb = 0; kb < sg.nkb; ++kb, ++kb_glob) {
+            mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+            const uint32_t fb = smem_u32(&full_bar[stage]);
+            mbar_expect_tx(fb, (uint32_t)stage_bytes);
+            uint8_t* sa = smem + (size_t)stage * stage_bytes;
+            tma_load_5d(smem_u32(sa), mp, fb, sg.c0 + kb * TC_BK, x0 + sg.dx, sg.p, y0 + sg.dy, nb0);
+            tma_load_2d(smem_u32(sa + TC_A_BYTES), &mapB, fb, kb_glob * TC_BK, tn * p.BN);
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      mbar_wait(smem_u32(&tempty_bar[as]), aphase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(as * 256);
+      for (int kb = 0; kb < p.total_kb; ++kb) {
+        mbar_wait(smem_u32(&full_bar[stage]), phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+          const uint64_t adesc = make_kmajor_sw128_desc(sa);
+          const uint64_t bdesc = make_kmajor_sw128_desc(sa + TC_A_BYTES);
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            // advance 16 elements (32 B) along K inside the swizzle atom: +2 in the (addr >> 4) field
+            umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), p.idesc, (kb | k) != 0);
+          }
+          umma_commit(smem_u32(&empty_bar[stage]));                      // frees the smem stage when the MMAs retire
+          if (kb == p.total_kb - 1) umma_commit(smem_u32(&tfull_bar[as]));  // accumulator complete
+        }
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  } else {
+    // ===================== epilogue warps 2..5 =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;  // accumulator row == pixel index inside the tile
+    const bool geglu = e.act == DCB_ACT_GEGLU;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int tn = tile % p.n_tiles;
+      int tm = tile / p.n_tiles;
+      const int tm_lin = tm;
+      const int tx = tm % p.tiles_x;
+      tm /= p.tiles_x;
+      const int ty = tm % p.tiles_y;
+      const int tb = tm / p.tiles_y;
+      const int xl = r % p.bw, yl = (r / p.bw) % p.bh, nl = r / (p.bw * p.bh);
+      const int x = tx * p.bw + xl, y = ty * p.bh + yl, nb = tb * p.bn + nl;
+      const bool row_ok = x < p.OW && y < p.OH && nb < p.NB;
+      const int pix = y * p.OW + x;
+      const int m = nb * e.rows_per_sample + pix;
+
+      mbar_wait(smem_u32(&tfull_bar[as]), aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 256);
+      float mse_acc = 0.f;
+      if (!geglu) {
+        for (int c = 0; c < p.BN; c += 16) {
+          const int n0 = tn * p.BN + c;
+          if (n0 >= e.N) break;  // warp-uniform
+          float v[16];
+          tmem_ld16(taddr + (uint32_t)c, v);
+          if (row_ok) {
+            if (e.bias) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (n0 + i < e.N) v[i] += e.bias[n0 + i];
+            }
+            epi_store16(e, m, n0, v, mse_acc, nb, pix);
+          }
+        }
+      } else {
+        // tile = [128 value rows | 128 gate rows] of the packed GEGLU weight: out = (a + ba) * gelu_erf(g + bg)
+        for (int c = 0; c < 128; c += 16) {
+          float a[16], g[16];
+          tmem_ld16(taddr + (uint32_t)c, a);
+          tmem_ld16(taddr + (uint32_t)(128 + c), g);
+          if (row_ok) {
+            const int wr = tn * 256 + c;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              float av = a[i] + (e.bias ? e.bias[wr + i] : 0.f);
+              float gv = g[i] + (e.bias ? e.bias[wr + 128 + i] : 0.f);
+              a[i] = av * gelu_erf_f(gv);
+            }
+            epi_store16(e, m, tn * 128 + c, a, mse_acc, nb, pix);
+          }
+        }
+      }
+      // release the accumulator stage
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[as]));
+      if (e.mse_part) {
+        mse_acc = warp_sum(mse_acc);
+        if (lane == 0) mse_smem[q] = mse_acc;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (warp == 2 && lane == 0)
+          e.mse_part[(int64_t)tm_lin * p.n_tiles + tn] = (mse_smem[0] + mse_smem[1]) + (mse_smem[2] + mse_smem[3]);
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// ---- host side ----------------------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+  });
+  return fn;
+}
+
+struct TcGeom {
+  int bw, bh, bn, tiles_x, tiles_y, tiles_nb, BN, n_tiles;
+};
+
+static int choose_geometry(const GemmDev& g, TcGeom* t) {
+  const int OW = g.OW, OH = g.OH, NB = g.NB;
+  if (OH == 1 && NB == 1) {
+    t->bw = 128; t->bh = 1; t->bn = 1;
+  } else if (OW >= 128) {
+    t->bw = 128; t->bh = 1; t->bn = 1;
+  } else {
+    DCB_REQUIRE(128 % OW == 0, "tcgen05 engine needs OW (%d) to divide 128 or be >= 128", OW);
+    t->bw = OW;
+    const int rem = 128 / OW;
+    if (OH >= rem) { t->bh = rem; t->bn = 1; }
+    else {
+      DCB_REQUIRE(rem % OH == 0, "tcgen05 engine needs OH (%d) to divide %d", OH, rem);
+      t->bh = OH; t->bn = rem / OH;
+    }
+  }
+  t->tiles_x = (OW + t->bw - 1) / t->bw;
+  t->tiles_y = (OH + t->bh - 1) / t->bh;
+  t->tiles_nb = (NB + t->bn - 1) / t->bn;
+  const int m_tiles = t->tiles_x * t->tiles_y * t->tiles_nb;
+  const int N = g.epi.N;
+  if (g.epi.act == DCB_ACT_GEGLU) {
+    DCB_REQUIRE(N % 256 == 0, "GEGLU needs N %% 256 == 0 (got %d)", N);
+    t->BN = 256;
+  } else if (N <= 256) {
+    t->BN = (N + 15) / 16 * 16;
+    // small-M layers: split N so that more SMs get a tile (smem-bandwidth cost is acceptable below one wave)
+    while (t->BN >= 128 && t->BN % 32 == 0 && m_tiles * ((N + t->BN - 1) / t->BN) < num_sms() / 2) t->BN /= 2;
+  } else {
+    t->BN = 256;
+    while (t->BN > 64 && m_tiles * ((N + t->BN - 1) / t->BN) < num_sms()) t->BN /= 2;
+  }
+  t->n_tiles = (N + t->BN - 1) / t->BN;
+  return DCB_OK;
+}
+
+int tc_geometry(const GemmDev& g, int* m_tiles, int* n_tiles, int* BN) {
+  TcGeom t;
+  int rc = choose_geometry(g, &t);
+  if (rc) return rc;
+  *m_tiles = t.tiles_x * t.tiles_y * t.tiles_nb;
+  *n_tiles = t.n_tiles;
+  *BN = t.BN;
+  return DCB_OK;
+}
+
+static int encode_a_map(CUtensorMap* map, const SegDev& s, int NBsrc, const TcGeom& t) {
+  auto enc = get_encode_fn();
+  DCB_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[5], strides[4];
+  const cuuint64_t es = 2, C = s.C, H = s.H, W = s.W;
+  if (s.stride == 1) {
+    dims[0] = C; dims[1] = W; dims[2] = 1; dims[3] = H; dims[4] = NBsrc;
+    strides[0] = C * es; strides[1] = W * C * es; strides[2] = W * C * es; strides[3] = H * W * C * es;
+  } else {
+    DCB_REQUIRE(s.stride == 2 && s.H % 2 == 0 && s.W % 2 == 0, "stride-2 segment needs even H, W");
+    dims[0] = 2 * C; dims[1] = W / 2; dims[2] = 2; dims[3] = H / 2; dims[4] = NBsrc;
+    strides[0] = 2 * C * es; strides[1] = W * C * es; strides[2] = 2 * W * C * es; strides[3] = H * W * C * es;
+  }
+  cuuint32_t box[5] = {(cuuint32_t)TC_BK, (cuuint32_t)t.bw, 1, (cuuint32_t)t.bh, (cuuint32_t)t.bn};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(s.src), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DCB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(A) failed: %d (C=%d H=%d W=%d NB=%d stride=%d box=%d,%d,%d)",
+              (int)r, s.C, s.H, s.W, NBsrc, s.stride, t.bw, t.bh, t.bn);
+  return DCB_OK;
+}
+
+int launch_gemm_tc(const GemmDev& g, cudaStream_t st) {
+  DCB_REQUIRE(g.dtype == DCB_BF16, "tcgen05 engine is bf16 only");
+  DCB_REQUIRE(g.K % TC_BK == 0, "tcgen05 engine needs K %% 64 == 0 (K=%d)", g.K);
+  DCB_REQUIRE(((uintptr_t)g.W & 15) == 0, "weights must be 16-byte aligned");
+  TcGeom t;
+  int rc = choose_geometry(g, &t);
+  if (rc) return rc;
+
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  CUtensorMap maps[3];
+  memset(maps, 0, sizeof(maps));
+  SegDev map_key[3];
+  int nmaps = 0;
+  p.nseg = g.nseg;
+  p.total_kb = 0;
+  for (int i = 0; i < g.nseg; ++i) {
+    const SegDev& s = g.seg[i];
+    DCB_REQUIRE(s.kc % TC_BK == 0 && s.c_off % 8 == 0 && s.C % 8 == 0, "segment %d: kc %% 64, c_off %% 8, C %% 8", i);
+    DCB_REQUIRE(((uintptr_t)s.src & 15) == 0, "segment %d: src must be 16-byte aligned", i);
+    int mi = -1;
+    for (int j = 0; j < nmaps; ++j)
+      if (map_key[j].src == s.src && map_key[j].C == s.C && map_key[j].H == s.H && map_key[j].W == s.W &&
+          map_key[j].stride == s.stride)
+        mi = j;
+    if (mi < 0) {
+      DCB_REQUIRE(nmaps < 3, "at most 3 distinct A sources per GEMM");
+      mi = nmaps++;
+      map_key[mi] = s;
+      rc = encode_a_map(&maps[mi], s, g.NB, t);
+      if (rc) return rc;
+    }
+    TcSeg& ts = p.seg[i];
+    ts.map = mi;
+    ts.nkb = s.kc / TC_BK;
+    if (s.stride == 1) {
+      ts.c0 = s.c_off; ts.dx = s.dx; ts.p = 0; ts.dy = s.dy;
+    } else {
+      // input x = 2*ox + dx = 2*(ox + floor(dx/2)) + (dx & 1)
+      const int px = s.dx & 1, py = s.dy & 1;
+      ts.c0 = px * s.C + s.c_off;
+      ts.dx = (s.dx - px) / 2;
+      ts.p = py;
+      ts.dy = (s.dy - py) / 2;
+    }
+    p.total_kb += ts.nkb;
+  }
+  for (int j = nmaps; j < 3; ++j) maps[j] = maps[0];
+
+  CUtensorMap mapB;
+  {
+    auto enc = get_encode_fn();
+    cuuint64_t dims[2] = {(cuuint64_t)g.K, (cuuint64_t)g.epi.N};
+    cuuint64_t strides[1] = {(cuuint64_t)g.K * 2};
+    cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)t.BN};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&mapB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(g.W), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    DCB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(W) failed: %d (K=%d N=%d BN=%d)", (int)r, g.K, g.epi.N, t.BN);
+  }
+
+  p.tiles_x = t.tiles_x; p.tiles_y = t.tiles_y; p.tiles_nb = t.tiles_nb; p.n_tiles = t.n_tiles;
+  p.total_tiles = t.tiles_x * t.tiles_y * t.tiles_nb * t.n_tiles;
+  p.bw = t.bw; p.bh = t.bh; p.bn = t.bn;
+  p.OW = g.OW; p.OH = g.OH; p.NB = g.NB;
+  p.BN = t.BN;
+  const int stage_bytes = TC_A_BYTES + t.BN * TC_BK * 2;
+  int stages = TC_SMEM_BUDGET / stage_bytes;
+  if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+  if (stages > p.total_kb) stages = p.total_kb < 2 ? 2 : p.total_kb;
+  p.stages = stages;
+  // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, both K-major, N>>3 @17, M>>4 @24
+  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(t.BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+
+  if (g.epi.mse_part) {
+    DCB_REQUIRE(t.bn == 1 && (g.OH * g.OW) % TC_BM == 0, "fused MSE needs OH*OW %% 128 == 0");
+  }
+  // always ask for more than half of the SM's shared memory so exactly one CTA (one TMEM owner) is resident
+  size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
+  if (smem < 120 * 1024) smem = 120 * 1024;
+  static std::once_flag attr_once;
+  std::call_once(attr_once, [] {
+    cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  });
+  int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+  gemm_tc_kernel<<<grid, TC_THREADS, smem, st>>>(maps[0], maps[1], maps[2], mapB, p, g.epi);
+  DCB_CHECK_LAUNCH("gemm_tc");
+  return DCB_OK;
+}
+
+}  // namespace dcb

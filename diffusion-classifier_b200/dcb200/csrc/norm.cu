@@ -1,0 +1,274 @@
+// norm.cu -- HBM-bound normalisation kernels on NHWC activations:
+//   GroupNorm(32 groups)+SiLU over an (optionally channel-concatenated) tensor   [diffusers ResnetBlock2D.norm1/2,
+//        Transformer2DModel.norm, UNet conv_norm_out; the torch.cat of the up-path skip is folded in here]
+//   LayerNorm with optional affine and optional adaLN modulation                 [BasicTransformerBlock.norm1/2/3,
+//        AdaLayerNormZero, DiT norm_out]
+// All reductions are fixed-order (no float atomics) so results are run-to-run deterministic.
+// Vectorised 16-byte accesses; one read for statistics + one read/one write for the apply pass.
+#include "common.cuh"
+
+namespace dcb {
+
+template <typename T>
+struct Vec;
+template <>
+struct Vec<__nv_bfloat16> {
+  static constexpr int N = 8;
+  __device__ static void load(const __nv_bfloat16* p, float* f) { unpack_bf16x8(*reinterpret_cast<const uint4*>(p), f); }
+  __device__ static void store(__nv_bfloat16* p, const float* f) { *reinterpret_cast<uint4*>(p) = pack_bf16x8(f); }
+};
+template <>
+struct Vec<float> {
+  static constexpr int N = 4;
+  __device__ static void load(const float* p, float* f) {
+    float4 v = *reinterpret_cast<const float4*>(p);
+    f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+  }
+  __device__ static void store(float* p, const float* f) {
+    *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+  }
+};
+
+constexpr int GN_THREADS = 256;
+
+// ---- GroupNorm statistics: part[((n*chunks + chunk)*G + g)*2 + {sum,sumsq}] -------------------------------
+template <typename T>
+__global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const T* __restrict__ x0, int C0, const T* __restrict__ x1,
+                                                              int C1, int HW, int G, int chunks, float* __restrict__ part) {
+  constexpr int VN = Vec<T>::N;
+  __shared__ float s_acc[GN_THREADS][VN][2];
+  const int n = blockIdx.y, chunk = blockIdx.x;
+  const int C = C0 + C1, V = C / VN, cpg = C / G;
+  const int ppc = (HW + chunks - 1) / chunks;
+  const int p0 = chunk * ppc, p1 = min(HW, p0 + ppc);
+  const int vslots = min(V, (int)blockDim.x);
+  const int nrows = blockDim.x / vslots;
+  const int prow = threadIdx.x / vslots, vs = threadIdx.x % vslots;
+  float* out = part + ((int64_t)(n * chunks + chunk) * G) * 2;
+  float gsum = 0.f, gsq = 0.f;  // owned by thread g < G
+
+  for (int vb = 0; vb < V; vb += vslots) {
+    const int v = vb + vs;
+    float s[VN], q[VN];
+#pragma unroll
+    for (int i = 0; i < VN; ++i) s[i] = q[i] = 0.f;
+    if (v < V && prow < nrows) {
+      const int c = v * VN;
+      const T* base;
+      int cs, cc;
+      if (c < C0) { base = x0 + (int64_t)n * HW * C0; cs = C0; cc = c; }
+      else { base = x1 + (int64_t)n * HW * C1; cs = C1; cc = c - C0; }
+      for (int p = p0 + prow; p < p1; p += nrows) {
+        float f[VN];
+        Vec<T>::load(base + (int64_t)p * cs + cc, f);
+#pragma unroll
+        for (int i = 0; i < VN; ++i) { s[i] += f[i]; q[i] = fmaf(f[i], f[i], q[i]); }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < VN; ++i) { s_acc[threadIdx.x][i][0] = s[i]; s_acc[threadIdx.x][i][1] = q[i]; }
+    __syncthreads();
+    if (threadIdx.x < G) {
+      const int g = threadIdx.x;
+      const int c_lo = max(g * cpg, vb * VN), c_hi = min((g + 1) * cpg, (vb + vslots) * VN);
+      for (int c = c_lo; c < c_hi; ++c) {
+        const int slot = c / VN - vb, i = c % VN;
+        for (int r = 0; r < nrows; ++r) {
+          gsum += s_acc[r * vslots + slot][i][0];
+          gsq += s_acc[r * vslots + slot][i][1];
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x < G) { out[threadIdx.x * 2] = gsum; out[threadIdx.x * 2 + 1] = gsq; }
+}
+
+// ---- GroupNorm apply (+SiLU), writes the concatenated normalised tensor [NB,HW,C0+C1] ----------------------
+template <typename T>
+__global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const T* __restrict__ x0, int C0, const T* __restrict__ x1,
+                                                              int C1, int HW, int G, int chunks,
+                                                              const float* __restrict__ part, const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta, float eps, int silu,
+                                                              T* __restrict__ out, int blocks_per_sample) {
+  constexpr int VN = Vec<T>::N;
+  extern __shared__ float s_ab[];  // [2][C]: y = x*A[c] + B[c]
+  __shared__ float s_mean[64], s_rstd[64];
+  const int n = blockIdx.y;
+  const int C = C0 + C1, V = C / VN, cpg = C / G;
+  if (threadIdx.x < G) {
+    double s = 0.0, q = 0.0;
+    const float* pp = part + ((int64_t)n * chunks * G + threadIdx.x) * 2;
+    for (int k = 0; k < chunks; ++k) { s += pp[(int64_t)k * G * 2]; q += pp[(int64_t)k * G * 2 + 1]; }
+    const double cnt = (double)HW * cpg;
+    const double mean = s / cnt;
+    double var = q / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    s_mean[threadIdx.x] = (float)mean;
+    s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    const float a = s_rstd[g] * gamma[c];
+    s_ab[c] = a;
+    s_ab[C + c] = beta[c] - s_mean[g] * a;
+  }
+  __syncthreads();
+  const int64_t items = (int64_t)HW * V;
+  const int64_t per_block = (items + blocks_per_sample - 1) / blocks_per_sample;
+  const int64_t i0 = blockIdx.x * per_block, i1 = min(items, i0 + per_block);
+  const T* b0 = x0 + (int64_t)n * HW * C0;
+  const T* b1 = x1 ? x1 + (int64_t)n * HW * C1 : nullptr;
+  T* ob = out + (int64_t)n * HW * C;
+  for (int64_t it = i0 + threadIdx.x; it < i1; it += blockDim.x) {
+    const int64_t p = it / V;
+    const int c = (int)(it - p * V) * VN;
+    float f[VN];
+    if (c < C0) Vec<T>::load(b0 + p * C0 + c, f);
+    else Vec<T>::load(b1 + p * C1 + (c - C0), f);
+#pragma unroll
+    for (int i = 0; i < VN; ++i) {
+      float y = fmaf(f[i], s_ab[c + i], s_ab[C + c + i]);
+      f[i] = silu ? silu_f(y) : y;
+    }
+    Vec<T>::store(ob + p * C + c, f);
+  }
+}
+
+static int gn_threads(int V) { return V >= GN_THREADS ? GN_THREADS : (GN_THREADS / V) * V; }
+
+template <typename T>
+static int gn_stats_t(const void* x0, int C0, const void* x1, int C1, int NB, int HW, int G, int chunks, float* part,
+                      cudaStream_t st) {
+  const int V = (C0 + C1) / Vec<T>::N;
+  dim3 grid(chunks, NB);
+  gn_stats_kernel<T><<<grid, gn_threads(V), 0, st>>>((const T*)x0, C0, (const T*)x1, C1, HW, G, chunks, part);
+  DCB_CHECK_LAUNCH("gn_stats");
+  return DCB_OK;
+}
+
+template <typename T>
+static int gn_apply_t(const void* x0, int C0, const void* x1, int C1, int NB, int HW, int G, int chunks, const float* part,
+                      const float* gamma, const float* beta, float eps, int silu, void* out, cudaStream_t st) {
+  const int C = C0 + C1;
+  const int64_t items = (int64_t)HW * (C / Vec<T>::N);
+  int bps = (int)((items + 4 * GN_THREADS - 1) / (4 * GN_THREADS));  // ~4 vectors per thread
+  const int want = (4 * num_sms() + NB - 1) / NB;                      // but do not shred small tensors
+  if (bps > want * 4) bps = want * 4;
+  if (bps < 1) bps = 1;
+  dim3 grid(bps, NB);
+  gn_apply_kernel<T><<<grid, GN_THREADS, 2 * C * sizeof(float), st>>>((const T*)x0, C0, (const T*)x1, C1, HW, G, chunks,
+                                                                      part, gamma, beta, eps, silu, (T*)out, bps);
+  DCB_CHECK_LAUNCH("gn_apply");
+  return DCB_OK;
+}
+
+static int gn_check(int dtype, int C0, int C1, int G, const void* x1) {
+  const int vn = dtype == DCB_BF16 ? 8 : 4;
+  DCB_REQUIRE(G > 0 && G <= 64 && (C0 + C1) % G == 0, "groupnorm: C=%d not divisible by G=%d (G<=64)", C0 + C1, G);
+  DCB_REQUIRE(C0 % vn == 0 && C1 % vn == 0, "groupnorm: channel counts must be multiples of %d", vn);
+  DCB_REQUIRE((C1 == 0) == (x1 == nullptr), "groupnorm: x1/C1 mismatch");
+  DCB_REQUIRE(2 * (C0 + C1) * sizeof(float) <= 48 * 1024, "groupnorm: C too large");
+  return DCB_OK;
+}
+
+// ---- LayerNorm: one warp per row, row cached in registers ---------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) layernorm_kernel(const T* __restrict__ x, int64_t rows, int C,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                       float eps, const float* __restrict__ scale,
+                                                       const float* __restrict__ shift, int mod_ld, int rows_per_group,
+                                                       T* __restrict__ out) {
+  constexpr int VN = Vec<T>::N;
+  constexpr int MAXV = 32 / VN;  // per-lane vectors: C <= 32 lanes * 32 elements = 1024
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int V = C / VN;
+  const T* xr = x + row * C;
+  float buf[MAXV][VN];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < MAXV; ++j) {
+    const int v = lane + j * 32;
+    if (v < V) {
+      Vec<T>::load(xr + v * VN, buf[j]);
+#pragma unroll
+      for (int i = 0; i < VN; ++i) s += buf[j][i];
+    }
+  }
+  const float mean = warp_sum(s) / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < MAXV; ++j) {
+    const int v = lane + j * 32;
+    if (v < V) {
+#pragma unroll
+      for (int i = 0; i < VN; ++i) { float d = buf[j][i] - mean; q = fmaf(d, d, q); }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+  const int64_t grp = rows_per_group > 0 ? row / rows_per_group : 0;
+  T* orow = out + row * C;
+#pragma unroll
+  for (int j = 0; j < MAXV; ++j) {
+    const int v = lane + j * 32;
+    if (v < V) {
+      const int c = v * VN;
+#pragma unroll
+      for (int i = 0; i < VN; ++i) {
+        float y = (buf[j][i] - mean) * rstd;
+        if (gamma) y = y * gamma[c + i] + (beta ? beta[c + i] : 0.f);
+        if (scale) y = y * (1.f + scale[grp * mod_ld + c + i]) + shift[grp * mod_ld + c + i];
+        buf[j][i] = y;
+      }
+      Vec<T>::store(orow + c, buf[j]);
+    }
+  }
+}
+
+}  // namespace dcb
+
+using namespace dcb;
+
+extern "C" int dcb_groupnorm_stats(int dtype, const void* x0, int C0, const void* x1, int C1, int NB, int HW, int G,
+                                   int chunks, float* part, dcb_stream stream) {
+  int rc = gn_check(dtype, C0, C1, G, x1);
+  if (rc) return rc;
+  DCB_REQUIRE(chunks >= 1 && NB >= 1 && NB <= 65535, "groupnorm: bad chunks/NB");
+  cudaStream_t st = (cudaStream_t)stream;
+  return dtype == DCB_BF16 ? gn_stats_t<__nv_bfloat16>(x0, C0, x1, C1, NB, HW, G, chunks, part, st)
+                           : gn_stats_t<float>(x0, C0, x1, C1, NB, HW, G, chunks, part, st);
+}
+
+extern "C" int dcb_groupnorm_apply(int dtype, const void* x0, int C0, const void* x1, int C1, int NB, int HW, int G,
+                                   int chunks, const float* part, const float* gamma, const float* beta, float eps,
+                                   int silu, void* out, dcb_stream stream) {
+  int rc = gn_check(dtype, C0, C1, G, x1);
+  if (rc) return rc;
+  DCB_REQUIRE(chunks >= 1 && NB >= 1 && NB <= 65535, "groupnorm: bad chunks/NB");
+  cudaStream_t st = (cudaStream_t)stream;
+  return dtype == DCB_BF16
+             ? gn_apply_t<__nv_bfloat16>(x0, C0, x1, C1, NB, HW, G, chunks, part, gamma, beta, eps, silu, out, st)
+             : gn_apply_t<float>(x0, C0, x1, C1, NB, HW, G, chunks, part, gamma, beta, eps, silu, out, st);
+}
+
+extern "C" int dcb_layernorm(int dtype, const void* x, int64_t rows, int C, const float* gamma, const float* beta,
+                             float eps, const float* scale, const float* shift, int mod_ld, int rows_per_group, void* out,
+                             dcb_stream stream) {
+  const int vn = dtype == DCB_BF16 ? 8 : 4;
+  DCB_REQUIRE(C % vn == 0 && C <= 1024, "layernorm: need C %% %d == 0 and C <= 1024 (C=%d)", vn, C);
+  DCB_REQUIRE((scale == nullptr) == (shift == nullptr), "layernorm: scale/shift must come together");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int wpb = 8;
+  const unsigned grid = (unsigned)((rows + wpb - 1) / wpb);
+  if (dtype == DCB_BF16)
+    layernorm_kernel<__nv_bfloat16><<<grid, wpb * 32, 0, st>>>((const __nv_bfloat16*)x, rows, C, gamma, beta, eps, scale,
+                                                               shift, mod_ld, rows_per_group, (__nv_bfloat16*)out);
+  else
+    layernorm_kernel<float><<<grid, wpb * 32, 0, st>>>((const float*)x, rows, C, gamma, beta, eps, scale, shift, mod_ld,
+                                                       rows_per_group, (float*)out);
+  DCB_CHECK_LAUNCH("layernorm");
+  return DCB_OK;
+}

@@ -1,0 +1,134 @@
+/* dcb200.h -- C ABI of libdcb200.so: hand-written sm_100a kernels for the ELBO-classification hot path
+ * of faverogian/diffusion-classifier (diffusion/diffusion_classifier.py:657-725 and the diffusers 0.31.0
+ * denoisers behind nets/unet.py:186-195, nets/dit.py:49-51).
+ *
+ * The reference has no FFI of its own (pure Python over torch/diffusers); the boundary a maintainer binds is
+ * this header, called from Python via ctypes (INTEGRATION.md shows the stub).  Conventions:
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless named host_*;
+ *   - the caller owns every buffer (inputs, outputs, workspaces); the library never allocates device memory;
+ *   - every entry point is stream-ordered on `stream` (a cudaStream_t passed as void*), re-entrant, and
+ *     returns 0 on success, a negative DCB_E* code or a positive cudaError_t; dcb_last_error() has the text;
+ *   - activations are NHWC ("pixels x channels"), dtype DCB_BF16 (fast path) or DCB_F32 (fp32-verify path);
+ *   - weights are [N][K] K-major in the activation dtype, packed once by the host (see docs in DESIGN.md).
+ */
+#ifndef DCB200_H
+#define DCB200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* dcb_stream; /* cudaStream_t */
+
+enum { DCB_F32 = 0, DCB_BF16 = 1 };
+enum { DCB_ACT_NONE = 0, DCB_ACT_SILU = 1, DCB_ACT_GELU_TANH = 2, DCB_ACT_GEGLU = 3 };
+enum { DCB_ENGINE_AUTO = 0, DCB_ENGINE_SIMT = 1, DCB_ENGINE_TCGEN05 = 2 };
+enum { DCB_OK = 0, DCB_EINVAL = -1, DCB_EUNSUPPORTED = -2, DCB_EDRIVER = -3 };
+
+#define DCB_MAX_SEGS 12
+
+/* ---- library ------------------------------------------------------------------------------------------ */
+int dcb_version(void);
+const char* dcb_last_error(void);
+/* number of kernel launches issued by this library since load (bench.py's "gpu_launches") */
+int64_t dcb_launch_count(void);
+
+/* ---- (1) prologue: q_sample fused with the denoiser's input staging ------------------------------------
+ * replaces DiffusionClassifier.diffuse (diffusion_classifier.py:100-117) + the first-layer unfold:
+ *   eps = predrawn[u] or Philox(seed, unit_id0+u);  z = alpha[u]*x[img[u]] + sigma[u]*eps
+ *   a_out[(u*rep + r) * rows + row][k] = im2col3x3(z) (mode 0, U-Net conv_in, K order (ky,kx,c)) or
+ *                                        patchify(z)  (mode 1, DiT PatchEmbed, K order (py,px,c)), zero padded to kpad
+ *   target[u*rows + row][c'] = eps - (v_param ? sigma[u]*z : 0)     (layout NHWC / token-major (py,px,c))
+ * x: [n_img,C,H,W] fp32 NCHW; eps_predrawn: [U,C,H,W] fp32 NCHW or NULL; img: [U] int32 or NULL (identity);
+ * sigma == NULL means "no noise" (z = alpha*x; plain forward); z_ws: [U,H,W,C] fp32 scratch holding z (NHWC). */
+int dcb_prologue(int mode, int dtype, const float* x, const float* eps_predrawn, uint64_t seed, int64_t unit_id0,
+                 const float* alpha, const float* sigma, const int32_t* img, int U, int rep, int C, int H, int W,
+                 int patch, int kpad, float* z_ws, void* a_out, float* target, int v_param, dcb_stream stream);
+
+/* sinusoidal embedding of the noise label (diffusers get_timestep_embedding):
+ * out[s][0:half] = cos(t*w_k), out[s][half:] = sin(t*w_k), w_k = exp(-ln(max_period)*k/(half-shift)); s = u*rep+r */
+int dcb_timestep_embed(int dtype, const float* t, int U, int rep, int dim, float shift, float max_period, void* out,
+                       dcb_stream stream);
+
+/* ---- (2) implicit GEMM: 3x3 / 1x1 / strided convolutions and linear layers ------------------------------ */
+typedef struct dcb_seg {
+  const void* src;  /* NHWC activations [NB,H,W,C] */
+  int32_t C, H, W;  /* src channel count / spatial dims */
+  int32_t c_off;    /* first src channel consumed by this segment */
+  int32_t kc;       /* channels consumed (K extent); multiple of 64 (tcgen05) / 16 (SIMT) */
+  int32_t dy, dx;   /* input pixel = (oy*stride + dy, ox*stride + dx); out-of-range reads as 0 (padding) */
+  int32_t stride;   /* 1 or 2 */
+  int32_t _r0, _r1;
+} dcb_seg;
+
+typedef struct dcb_gemm_desc {
+  int32_t dtype, engine;
+  int32_t NB, OH, OW; /* output rows m = (n*OH + y)*OW + x */
+  int32_t N;          /* weight rows (GEMM N); with DCB_ACT_GEGLU the output has N/2 columns */
+  int32_t nseg, _r0;
+  dcb_seg seg[DCB_MAX_SEGS]; /* K = concatenation of the segments, in order */
+  const void* W;             /* [N][K] */
+  const float* bias;         /* [N] or NULL */
+  const float* rowvec;       /* v += rowvec[g*rowvec_ld + n], g = m / rows_per_group, or rowvec_idx[g] when given
+                                (time-embedding projection / collapsed single-token cross-attention bias per class) */
+  const int32_t* rowvec_idx;
+  const float* gate;         /* v *= gate[(m / rows_per_group)*gate_ld + n]       (adaLN-Zero gates) */
+  const void* residual;      /* v += residual[row][n], row = res_idx ? res_idx[m] : (res_mod ? m % res_mod : m) */
+  const int32_t* res_idx;
+  void* out;                 /* [M][out_ld] or NULL when only the MSE epilogue is wanted */
+  const float* mse_target;   /* fused eps-MSE: part[tile] = sum_{rows,cols}(mse_scale[s]*v - target[(s/mse_div)*rps + pix][n])^2 */
+  const float* mse_scale;    /* [NB] or NULL (=1) */
+  float* mse_part;           /* [m_tiles * n_tiles] partial sums, reduced by dcb_mse_finalize */
+  int32_t rowvec_ld, gate_ld, rows_per_group;
+  int32_t act, act_post;     /* act before gate/residual, act_post after */
+  int32_t res_ld, res_mod, res_dtype;
+  int32_t out_ld, out_dtype;
+  int32_t mse_div, mse_ld;
+} dcb_gemm_desc;
+
+int dcb_gemm(const dcb_gemm_desc* d, dcb_stream stream);
+/* rows covered by one mse_part entry for descriptor d (128 for tcgen05, 64 for SIMT), and n-tile count */
+int dcb_gemm_mse_layout(const dcb_gemm_desc* d, int32_t* rows_per_part, int32_t* n_tiles);
+/* err[s] (+)= sum of parts_per_sample consecutive partials (fixed order => deterministic) */
+int dcb_mse_finalize(const float* part, int parts_per_sample, int S, float* err, int err_stride, dcb_stream stream);
+/* unfused eps-MSE (a7: diffusion_classifier.py:706-711): err[s] = sum_k (scale[s]*pred[s][k] - target[s/div][k])^2 */
+int dcb_eps_mse(int dtype, const void* pred, const float* target, const float* scale, int S, int div, int64_t K,
+                float* err, int err_stride, dcb_stream stream);
+
+/* ---- (3) normalisation ------------------------------------------------------------------------------ */
+/* GroupNorm (+optional SiLU) over the channel-concatenation of x0 [NB,HW,C0] and x1 [NB,HW,C1] (x1 may be NULL):
+ * stats pass writes part[NB][chunks][G][2] (sum, sumsq); apply pass reduces them in fixed order. */
+int dcb_groupnorm_stats(int dtype, const void* x0, int C0, const void* x1, int C1, int NB, int HW, int G, int chunks,
+                        float* part, dcb_stream stream);
+int dcb_groupnorm_apply(int dtype, const void* x0, int C0, const void* x1, int C1, int NB, int HW, int G, int chunks,
+                        const float* part, const float* gamma, const float* beta, float eps, int silu, void* out,
+                        dcb_stream stream);
+/* LayerNorm over C with optional affine (gamma,beta) and optional adaLN modulation
+ * y = LN(x)*(1 + scale[g]) + shift[g], g = row / rows_per_group */
+int dcb_layernorm(int dtype, const void* x, int64_t rows, int C, const float* gamma, const float* beta, float eps,
+                  const float* scale, const float* shift, int mod_ld, int rows_per_group, void* out, dcb_stream stream);
+
+/* ---- (4) self-attention: softmax(Q K^T * scale) V per (batch, head) ------------------------------------
+ * q/k/v: [B, Ntok, heads, d] views with row stride ld (elements); out [B, Ntok, heads*d] row stride out_ld */
+int dcb_attention(int dtype, const void* q, const void* k, const void* v, int ld, int B, int Ntok, int heads, int d,
+                  float scale, void* out, int out_ld, dcb_stream stream);
+
+/* ---- (5) Haar DWT / IDWT (utils/wavelet.py:4-35 / 37-67), batched NCHW fp32 -------------------------------
+ * dwt: [B,C,H,W] -> [B,4C,H/2,W/2] channel order 4i+{0,1,2,3} = cA,cH,cV,cD; out *= post_scale */
+int dcb_haar_dwt(const float* x, int B, int C, int H, int W, float post_scale, float* out, dcb_stream stream);
+int dcb_haar_idwt(const float* w, int B, int C4, int h, int wd, float pre_scale, float* out, dcb_stream stream);
+
+/* ---- data movement helpers ------------------------------------------------------------------------------ */
+int dcb_upsample2x(int dtype, const void* x, int NB, int H, int W, int C, void* out, dcb_stream stream);
+/* out[m][n] = x[m/div][n] + vec[m / rows_per_group][n]  (class expansion of a shared prefix; reserved) */
+int dcb_nhwc_to_nchw(int dtype, const void* x, int NB, int HW, int C, int ld, float* out, dcb_stream stream);
+/* DiT unpatchify: tok [B, g*g, p*p*C] (dtype) -> [B,C,g*p,g*p] fp32  ("nhwpqc->nchpwq") */
+int dcb_unpatchify(int dtype, const void* tok, int B, int g, int p, int C, int ld, float* out, dcb_stream stream);
+/* dst[i] = (dtype) src_f32[i] */
+int dcb_cast_f32(int dtype, const float* src, int64_t n, void* dst, dcb_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DCB200_H */

@@ -1,0 +1,163 @@
+"""GPU parity of the tcgen05/TMEM/TMA implicit-GEMM engine.
+
+Checked three ways on the same bf16 inputs: against torch fp32 math (conv2d / matmul on the bf16-rounded operands),
+against the independent CUDA-core SIMT engine of this library, and through fused-epilogue identities
+(fused eps-MSE == unfused reduction of the written prediction).  Tolerance: bf16 output rounding (4e-3 relative
+per element -> 1e-2 bound on the Frobenius-relative error; fp32 outputs must agree to 2e-5)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import conv_ref, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _ctx(dev, engine=0):
+    from dcb200 import engine as E
+    return E.Ctx(device=dev, precision="bf16", engine=engine)
+
+
+def _bf(*shape, dev, scale=1.0):
+    return (torch.randn(*shape, device=dev) * scale).to(torch.bfloat16)
+
+
+@pytest.mark.parametrize("M,K,N", [(128, 64, 128), (300, 128, 128), (64, 256, 48), (1000, 512, 256), (40, 128, 1536),
+                                    (128 * 160, 128, 128), (333, 192, 3)])
+def test_tc_linear(dev, M, K, N):
+    from dcb200 import _lib as L
+    from dcb200 import engine as E
+    torch.manual_seed(0)
+    x, w, b = _bf(M, K, dev=dev), _bf(N, K, dev=dev, scale=0.1), torch.randn(N, device=dev)
+    ref = x.float() @ w.float().t() + b
+    out32 = E.linear(_ctx(dev), x, w, N, bias=b, out_dtype=torch.float32)
+    assert rel_err(out32, ref) < 2e-5, "tcgen05 fp32-out vs torch"
+    simt = E.linear(_ctx(dev, L.ENGINE_SIMT), x, w, N, bias=b, out_dtype=torch.float32)
+    assert rel_err(out32, simt) < 2e-5, "tcgen05 vs SIMT engine"
+    out16 = E.linear(_ctx(dev), x, w, N, bias=b)
+    assert out16.dtype == torch.bfloat16 and rel_err(out16, ref) < 1e-2
+
+
+@pytest.mark.parametrize("NB,H,W,Ci,Co,stride", [
+    (2, 32, 32, 64, 128, 1),     # bw=32 bh=4
+    (3, 8, 8, 128, 256, 1),      # two samples per M tile (bn=2), ragged last tile
+    (9, 4, 4, 64, 512, 1),       # bn=8, N split over tiles
+    (1, 16, 256, 64, 64, 1),     # OW > 128: two x tiles per row
+    (2, 128, 128, 64, 128, 1),   # full-res geometry of unet-128 (bw=128)
+    (2, 32, 32, 64, 128, 2),     # Downsample2D: 5-D (2C, W/2, 2, H/2, N) view
+    (5, 8, 8, 256, 256, 2),      # stride 2 with bn>1 at the output (4x4 -> bn=8)
+    (2, 16, 16, 128, 3, 1),      # conv_out-like: N=3 (BN=16, masked columns)
+])
+def test_tc_conv3x3(dev, NB, H, W, Ci, Co, stride):
+    from dcb200 import _lib as L
+    from dcb200 import engine as E
+    torch.manual_seed(0)
+    x = _bf(NB, H, W, Ci, dev=dev)
+    w = (torch.randn(Co, Ci, 3, 3, device=dev) * 0.05).to(torch.bfloat16)
+    b = torch.randn(Co, device=dev)
+    wp = w.permute(0, 2, 3, 1).reshape(Co, -1).contiguous()
+    OH, OW = H // stride, W // stride
+    ref = conv_ref(x.float(), w.float(), b, stride).reshape(-1, Co)
+    out = E.gemm(_ctx(dev), E.conv3x3_segs(x, Ci, H, W, stride), wp, Co, NB, OH, OW, bias=b, out_dtype=torch.float32)
+    assert rel_err(out, ref) < 2e-5
+    simt = E.gemm(_ctx(dev, L.ENGINE_SIMT), E.conv3x3_segs(x, Ci, H, W, stride), wp, Co, NB, OH, OW, bias=b,
+                  out_dtype=torch.float32)
+    assert rel_err(out, simt) < 2e-5
+
+
+def test_tc_resnet_tail_concat_shortcut(dev):
+    """conv2 + 1x1 conv_shortcut over cat([h, skip]) as extra K segments of ONE GEMM (ResnetBlock2D in an up block)."""
+    from dcb200 import engine as E
+    torch.manual_seed(0)
+    NB, H, W, C0, C1, Co = 2, 16, 16, 256, 128, 128
+    a2, x0, x1 = _bf(NB, H, W, Co, dev=dev), _bf(NB, H, W, C0, dev=dev), _bf(NB, H, W, C1, dev=dev)
+    w2 = (torch.randn(Co, Co, 3, 3, device=dev) * 0.05).to(torch.bfloat16)
+    ws = (torch.randn(Co, C0 + C1, 1, 1, device=dev) * 0.05).to(torch.bfloat16)
+    b = torch.randn(Co, device=dev)
+    wp = torch.cat([w2.permute(0, 2, 3, 1).reshape(Co, -1), ws.reshape(Co, -1)], 1).contiguous()
+    segs = E.conv3x3_segs(a2, Co, H, W) + [E.seg(x0, C0, H, W), E.seg(x1, C1, H, W)]
+    out = E.gemm(_ctx(dev), segs, wp, Co, NB, H, W, bias=b, out_dtype=torch.float32)
+    ref = conv_ref(a2.float(), w2.float(), b) + conv_ref(torch.cat([x0, x1], -1).float(), ws.float(), None, 1, 0)
+    assert rel_err(out.reshape(NB, H, W, Co), ref) < 2e-5
+
+
+def test_tc_epilogue_flags(dev):
+    from dcb200 import _lib as L
+    from dcb200 import engine as E
+    torch.manual_seed(0)
+    M, K, N, rpg = 512, 128, 256, 128
+    x, w, b = _bf(M, K, dev=dev), _bf(N, K, dev=dev, scale=0.1), torch.randn(N, device=dev)
+    rv, gate = torch.randn(5, N, device=dev), torch.randn(4, N, device=dev)
+    res = _bf(M, N, dev=dev)
+    idx = torch.tensor([4, 0, 2, 1], device=dev, dtype=torch.int32)
+    out = E.linear(_ctx(dev), x, w, N, bias=b, rowvec=rv, rowvec_ld=N, rowvec_idx=idx, rows_per_group=rpg, gate=gate,
+                   gate_ld=N, residual=res, res_ld=N, act=L.ACT_GELU_TANH, act_post=L.ACT_SILU, out_dtype=torch.float32)
+    grp = torch.arange(M, device=dev) // rpg
+    v = x.float() @ w.float().t() + b + rv[idx.long()][grp]
+    ref = F.silu(F.gelu(v, approximate="tanh") * gate[grp] + res.float())
+    assert rel_err(out, ref) < 2e-5
+    # gathered residual rows (DiT label embedding) and modulo residual (DiT positional embedding)
+    table = _bf(7, N, dev=dev)
+    lab = torch.randint(0, 7, (M,), device=dev, dtype=torch.int32)
+    out = E.linear(_ctx(dev), x, w, N, residual=table, res_ld=N, res_idx=lab, out_dtype=torch.float32)
+    assert rel_err(out, x.float() @ w.float().t() + table.float()[lab.long()]) < 2e-5
+    pos = _bf(64, N, dev=dev)
+    out = E.linear(_ctx(dev), x, w, N, residual=pos, res_ld=N, res_mod=64, out_dtype=torch.float32)
+    assert rel_err(out, x.float() @ w.float().t() + pos.float().repeat(M // 64, 1)) < 2e-5
+
+
+def test_tc_geglu(dev):
+    from dcb200 import _lib as L
+    from dcb200 import engine as E
+    torch.manual_seed(0)
+    M, K, inner = 200, 256, 1024
+    x = _bf(M, K, dev=dev)
+    w, b = _bf(2 * inner, K, dev=dev, scale=0.1), torch.randn(2 * inner, device=dev)
+    wp = torch.cat([w[:inner].reshape(-1, 128, K), w[inner:].reshape(-1, 128, K)], 1).reshape(2 * inner, K).contiguous()
+    bp = torch.cat([b[:inner].reshape(-1, 128), b[inner:].reshape(-1, 128)], 1).reshape(-1).contiguous()
+    out = E.linear(_ctx(dev), x, wp, 2 * inner, bias=bp, act=L.ACT_GEGLU, out_dtype=torch.float32)
+    h, g = (x.float() @ w.float().t() + b).chunk(2, -1)
+    assert out.shape == (M, inner) and rel_err(out, h * F.gelu(g)) < 2e-5
+
+
+@pytest.mark.parametrize("v_param", [False, True])
+def test_tc_fused_mse_equals_unfused(dev, v_param):
+    """conv_out with the eps-MSE epilogue (pred never written) == ||scale*pred - target||^2 of the written pred
+    (diffusion_classifier.py:706-711), per sample, with target shared by `div` class slots."""
+    from dcb200 import engine as E
+    torch.manual_seed(0)
+    S, div, H, W, Ci, Co = 6, 2, 32, 32, 128, 3
+    a = _bf(S, H, W, Ci, dev=dev)
+    w = (torch.randn(Co, Ci, 3, 3, device=dev) * 0.05).to(torch.bfloat16)
+    b = torch.randn(Co, device=dev)
+    wp = w.permute(0, 2, 3, 1).reshape(Co, -1).contiguous()
+    tgt = torch.randn(S // div, H * W, Co, device=dev)
+    scale = torch.rand(S, device=dev) if v_param else None
+    err = torch.empty(S, device=dev)
+    ctx = _ctx(dev)
+    E.gemm(ctx, E.conv3x3_segs(a, Ci, H, W), wp, Co, S, H, W, bias=b, want_out=False,
+           mse=dict(target=tgt, scale=scale, div=div, ld=Co, err=err))
+    pred = conv_ref(a.float(), w.float(), b).reshape(S, H * W, Co)
+    sc = scale.view(-1, 1, 1) if v_param else 1.0
+    ref = ((sc * pred - tgt.repeat_interleave(div, 0)) ** 2).sum((1, 2))
+    assert rel_err(err, ref) < 2e-5
+    err2 = torch.empty(S, device=dev)
+    E.gemm(ctx, E.conv3x3_segs(a, Ci, H, W), wp, Co, S, H, W, bias=b, want_out=False,
+           mse=dict(target=tgt, scale=scale, div=div, ld=Co, err=err2))
+    assert torch.equal(err, err2), "fixed-order reduction must be run-to-run deterministic"
+
+
+def test_tc_persistent_many_tiles_deep_k(dev):
+    """more tiles than SMs (persistent loop, TMEM double buffering) and K deep enough to wrap the smem ring often."""
+    from dcb200 import engine as E
+    torch.manual_seed(0)
+    NB, H, W, Ci, Co = 4, 64, 64, 256, 256   # 128 M tiles... x1 N tile; K = 2304 (36 K blocks)
+    x = _bf(NB, H, W, Ci, dev=dev)
+    w = (torch.randn(Co, Ci, 3, 3, device=dev) * 0.03).to(torch.bfloat16)
+    wp = w.permute(0, 2, 3, 1).reshape(Co, -1).contiguous()
+    out = E.gemm(_ctx(dev), E.conv3x3_segs(x, Ci, H, W), wp, Co, NB, H, W, out_dtype=torch.float32)
+    assert rel_err(out, conv_ref(x.float(), w.float(), None).reshape(-1, Co)) < 2e-5
+    M, K, N = 128 * 400, 64, 128             # 400 tiles on 148 SMs, single K block each
+    a, wl = _bf(M, K, dev=dev), _bf(N, K, dev=dev, scale=0.1)
+    out = E.linear(_ctx(dev), a, wl, N, out_dtype=torch.float32)
+    assert rel_err(out, a.float() @ wl.float().t()) < 2e-5
