@@ -18,4 +18,7 @@ def dev():
     import torch
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
+    # the torch ops used as checkers must be true fp32 (cuDNN/cuBLAS default to TF32 for convs/matmuls)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
     return torch.device("cuda:0")

@@ -116,6 +116,11 @@ def test_classify_matches_reference_golden(dev, name, precision):
     cfg = base_cfg(**kw)
     torch.manual_seed(int(g["seed"]))
     o = (dr.UNet2DConditionModel if kind == "unet" else dr.DiTTransformer2DModel)(**arch)
+    f = float(g["factor"])
+    with torch.no_grad():
+        if kind == "dit":  # the fixture amplified the class pathway (oracle/make_golden.py:amplify_class_signal)
+            for b in o.transformer_blocks:
+                b.norm1.emb.class_embedder.embedding_table.weight.mul_(f)
     if abs(_checksum(o) - float(g["checksum"])) > 1e-6 * float(g["checksum"]):
         pytest.skip("torch default-init stream differs from the build that wrote the fixture")
     rng = torch.get_rng_state()
@@ -123,15 +128,10 @@ def test_classify_matches_reference_golden(dev, name, precision):
     net.load_state_dict(o.state_dict())
     torch.set_rng_state(rng)
     dc = dcb200.DiffusionClassifier(net, cfg)   # draws the encoder table next, like the reference's ctor (:68)
-    f = float(g["factor"])
     with torch.no_grad():
         if kind == "unet":
             dc.encoder.weight.mul_(f)
             assert abs(_checksum(dc.encoder) - float(g["enc_checksum"])) < 1e-6 * float(g["enc_checksum"])
-        else:
-            for m in (dc.model, dc.ema.ema_model):
-                for b in m.transformer_blocks:
-                    b.norm1.emb.class_embedder.embedding_table.weight.mul_(f)
     dc = dc.to(dev).eval()
     dc.ema.ema_model.precision = precision
     labels = dc.classify(torch.from_numpy(g["x"]).to(dev), t_all=torch.from_numpy(g["t_all"]),
@@ -198,4 +198,5 @@ def test_classify_reference_rng_semantics(dev):
     text = torch.tensor([5, 0, 3, 3], device=dev)
     dc.classify(x, text, fast=True)
     fin = torch.isfinite(dc.last_errors[:, :, 0])
-    assert fin.sum(1).tolist() == [3, 3, 3, 3] and bool(fin[torch.arange(4), text.cpu()].all())
+    # torch.randint draws the wrong classes WITH replacement (:676), so 2 or 3 distinct candidates per image
+    assert all(2 <= n <= 3 for n in fin.sum(1).tolist()) and bool(fin[torch.arange(4), text].all())
