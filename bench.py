@@ -1,0 +1,289 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the ELBO-classification hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload unet128|cifar|...]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...      (one rank per GPU, NCCL)
+
+A "step" is one DiffusionClassifier.classify() pass over one batch of synthetic images of the workload's shape
+(default: BASELINE configs[1], unet-128, 2 classes x 100 timesteps, bf16).  Prints ONE JSON line (rank 0).
+  value     evals/s with the images already resident in HBM (CUDA events, max over ranks)
+  e2e       same metric through the public API from pinned HOST images, H2D + label D2H inside the timed region
+  roofline  tcgen05 implicit-GEMM kernel: algorithmic FLOPs of its launches / their summed CUDA-event durations
+  cpu_baseline  the oracle port (oracle/: reference loop + restated diffusers U-Net, fp32) on the host cores
+--impl reference times that CPU port alone (the reference's own implementation is pure Python over diffusers,
+which is not installable offline).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "diffusion-classifier_b200"), os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # name: (arch key in tests/helpers.py, classes, timesteps, GFLOP/eval, images per GPU per step)
+    "unet128": ("UNET128", 2, 100, 175.79, 4),
+    "cifar": ("CIFAR_UNET", 10, 32, 10.454, 16),
+}
+
+
+def build_workload(name):
+    import helpers
+    arch = getattr(helpers, WORKLOADS[name][0])
+    _, classes, T, gflop, ipg = WORKLOADS[name]
+    S = arch["sample_size"]
+    cfg = helpers.base_cfg(classes=classes, evaluation_per_stage=[T], n_stages=1, n_keep_per_stage=[1], noise_d=S,
+                           image_size=S, schedule="cosine", pred_param="eps")
+    return arch, cfg, classes, T, gflop, ipg
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i] == "Active" for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except (OSError, ValueError):
+        return {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0}, "fallback"
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_port_run(arch, cfg, n_img, n_t, threads, seed=0):
+    """the oracle port on the host: restated classify loop (oracle/loop.py) around the restated fp32 U-Net."""
+    from oracle import diffusers_restated as dr
+    from oracle import loop
+    torch.set_num_threads(threads)
+    torch.manual_seed(seed)
+    net = dr.UNet2DConditionModel(**arch).eval()
+    enc = torch.nn.Embedding(cfg.classes + 1, arch["encoder_hid_dim"])
+    import copy
+    c2 = copy.deepcopy(cfg)
+    c2.evaluation_per_stage = [n_t]
+    S, C = arch["sample_size"], arch["in_channels"]
+    x = torch.rand(n_img, C, S, S) * 2 - 1
+
+    class Den(torch.nn.Module):
+        def forward(self, x, noise_labels, encoder_hidden_states):
+            return net(x, noise_labels, encoder_hidden_states)[0]
+
+    den = Den()
+    t0 = time.perf_counter()
+    loop.classify_oracle(den, enc, c2, x)
+    dt = time.perf_counter() - t0
+    return n_img * n_t * cfg.classes / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    arch, cfg, classes, T, gflop, ipg = build_workload(args.workload)
+    threads = len(os.sched_getaffinity(0))
+    n_t = 4 if args.workload == "unet128" else 8
+    for _ in range(args.warmup):
+        cpu_port_run(arch, cfg, 1, 1, threads)
+    vals, times = [], []
+    for _ in range(args.steps):
+        v, dt = cpu_port_run(arch, cfg, 1, n_t, threads)
+        vals.append(v)
+        times.append(dt)
+    val = sum(vals) / len(vals)
+    sample = f"1 image x {n_t} timesteps x {classes} classes ({n_t * classes} denoiser evals) per step, fp32, torch CPU"
+    line = {
+        "impl": "reference", "metric": "denoiser evals/sec", "value": val, "unit": "evals/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "images_per_sec": val / (classes * T),
+        "config": {"workload": workload_name(args.workload, classes, T), "sample": sample},
+        "cpu_baseline": {"value": val, "unit": "evals/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_name(w, classes, T):
+    return {"unet128": f"unet-128 class-conditional U-Net (models/unet-128.py) ELBO scoring, {classes} classes x {T} "
+                       f"timesteps, 3x128x128",
+            "cifar": f"CIFAR-10 32x32 class-conditional U-Net (experiments/cifar10) ELBO classification, {classes} "
+                     f"classes x {T} timesteps"}[w]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    import dcb200
+    from dcb200 import engine as E
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    arch, cfg, classes, T, gflop, ipg = build_workload(args.workload)
+    if args.images:
+        ipg = args.images
+    BS = ipg * world  # weak scaling: every rank owns 1/world of the (image x timestep) units of a world-x larger batch
+    cfg.dcb_shard = "timestep"
+    if args.max_batch:
+        cfg.dcb_max_batch = args.max_batch
+    torch.manual_seed(0)
+    net = dcb200.UNetCondition2D(**arch)
+    dc = dcb200.DiffusionClassifier(net, cfg).to(dev).eval()
+    S, C = arch["sample_size"], arch["in_channels"]
+    g = torch.Generator().manual_seed(0)
+    x_host = (torch.rand(BS, C, S, S, generator=g) * 2 - 1).pin_memory()
+    x_dev = x_host.to(dev)
+    evals_per_step = BS * classes * T
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    def step_resident():
+        torch.manual_seed(1234)  # same t stream on every rank (CPU generator, as diffusion_classifier.py:688)
+        return dc.classify(x_dev)
+
+    def step_e2e():
+        torch.manual_seed(1234)
+        labels = dc.classify(x_host.to(dev, non_blocking=True))
+        return labels.cpu()
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    n0 = dcb200.launch_count()
+    ms = timed(step_resident, args.steps)
+    launches = dcb200.launch_count() - n0
+    clocks = sampler.stop() if rank == 0 else None
+    value = evals_per_step * args.steps / (ms / 1e3)
+
+    step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    e2e_value = evals_per_step * args.steps / (ms_e2e / 1e3)
+
+    # roofline of the dominant kernel: CUDA-event pairs around every tcgen05 GEMM launch of one instrumented pass
+    E.PROFILE = prof = E.GemmProfile()
+    barrier()
+    for _ in range(min(2, args.steps)):
+        step_resident()
+    barrier()
+    E.PROFILE = None
+    gemm_ms, gemm_flops, n_gemm = prof.totals()
+    peaks, peak_src = measured_peaks()
+    peak = peaks["bf16_tflops_sustained"]
+    achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+    passes = min(2, args.steps)
+    roofline = {
+        "bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 implicit GEMM)", "achieved": achieved, "peak": peak,
+        "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None, "peak_source": f"{peak_src} bf16_tflops_sustained",
+        "launches_per_step": n_gemm // passes, "avg_launch_ms": gemm_ms / max(n_gemm, 1),
+        "kernel_share_of_step": (gemm_ms / passes) / (ms / args.steps),
+        "algorithmic_gflop_per_eval": gemm_flops / passes / (evals_per_step / world) / 1e9,
+        "whole_step_frac_of_peak": (gflop * 1e9 * evals_per_step / world) / (ms / args.steps / 1e3) / 1e12 / peak,
+    }
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        threads = len(os.sched_getaffinity(0))
+        n_t = 4 if args.workload == "unet128" else 8
+        cpu_port_run(arch, cfg, 1, 1, threads)
+        v, dt = cpu_port_run(arch, cfg, 1, n_t, threads)
+        cpu = {"value": v, "unit": "evals/s", "cores": threads, "kind": "port", "seconds": dt,
+               "sample": f"1 image x {n_t} timesteps x {classes} classes ({n_t * classes} evals) of the same workload, "
+                         f"fp32 oracle port (reference loop + restated diffusers U-Net) on torch CPU"}
+
+    if rank == 0:
+        line = {
+            "metric": "denoiser evals/sec", "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "images_per_sec": value / (classes * T),
+            "config": {"workload": workload_name(args.workload, classes, T), "images_per_step": BS,
+                       "evals_per_step": evals_per_step, "shard": "(image x timestep) units over ranks + 1 all-reduce",
+                       "eps": "in-kernel Philox", "weights": "random init (torch default, seed 0)",
+                       "l2": "activation working set per launch sequence is GBs (>> 126 MB L2); no flush needed"},
+            "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": x_host.numel() * 4,
+                    "d2h_bytes_per_step": BS * 8, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="unet128", choices=list(WORKLOADS))
+    ap.add_argument("--images", type=int, default=0, help="images per GPU per step")
+    ap.add_argument("--max-batch", type=int, default=0, help="denoiser samples per launch sequence")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -34,6 +34,31 @@ class Ctx:
         return torch.empty(*shape, device=self.device, dtype=dtype or self.tdtype)
 
 
+class GemmProfile:
+    """bench.py's roofline probe: CUDA-event pairs around every tcgen05 GEMM launch + its algorithmic FLOPs."""
+
+    def __init__(self):
+        self.rows = []  # (start_event, end_event, flops, tag)
+
+    def totals(self):
+        torch.cuda.synchronize()
+        ms = sum(a.elapsed_time(b) for a, b, _, _ in self.rows)
+        return ms, sum(f for _, _, f, _ in self.rows), len(self.rows)
+
+    def by_shape(self):
+        torch.cuda.synchronize()
+        out = {}
+        for a, b, f, tag in self.rows:
+            r = out.setdefault(tag, [0, 0.0, 0.0])
+            r[0] += 1
+            r[1] += a.elapsed_time(b)
+            r[2] += f
+        return out
+
+
+PROFILE = None
+
+
 def _p(t):
     return None if t is None else t.data_ptr()
 
@@ -48,7 +73,7 @@ def conv3x3_segs(src, C_, H, W, stride=1):
 
 def gemm(ctx: Ctx, segs, W, N, NB, OH, OW, *, bias=None, rowvec=None, rowvec_ld=0, rowvec_idx=None, rows_per_group=0,
          gate=None, gate_ld=0, residual=None, res_ld=0, res_mod=0, res_idx=None, act=L.ACT_NONE, act_post=L.ACT_NONE,
-         out=None, out_dtype=None, out_ld=None, mse=None, want_out=True):
+         out=None, out_dtype=None, out_ld=None, mse=None, want_out=True, k_alg=None):
     """D = sum_seg A_seg . W^T with the fused epilogue; returns the [M, n_out] output (or None if want_out=False).
 
     mse = dict(target=, scale=, div=, ld=, err=[S] fp32 out) enables the fused eps-MSE epilogue (tcgen05 only).
@@ -89,7 +114,15 @@ def gemm(ctx: Ctx, segs, W, N, NB, OH, OW, *, bias=None, rowvec=None, rowvec_ld=
         pps = (OH * OW) // rpp.value * nt.value
         part = torch.empty(NB * pps, device=ctx.device, dtype=torch.float32)
         d.mse_part = part.data_ptr()
+    prof = PROFILE if (PROFILE is not None and ctx.code == L.BF16 and ctx.engine != L.ENGINE_SIMT) else None
+    if prof is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     L.check(lib.dcb_gemm(C.byref(d), ctx.stream()), "gemm")
+    if prof is not None:
+        e1.record()
+        K = sum(sg[5] for sg in segs)
+        prof.rows.append((e0, e1, 2.0 * M * N * (k_alg or K), f"M{M}_N{N}_K{K}_seg{len(segs)}"))
     if mse is not None:
         L.check(lib.dcb_mse_finalize(part.data_ptr(), pps, NB, mse["err"].data_ptr(), 1, ctx.stream()), "mse_finalize")
     return out

@@ -388,7 +388,7 @@ class UNetCondition2D(nn.Module):
         e2 = E.linear(ctx, e1, pk.te2_w, pk.te2_w.shape[0], bias=pk.te2_b, act=L.ACT_SILU)
         temb = E.linear(ctx, e2, pk.temb_w, pk.temb_total, bias=pk.temb_b, out_dtype=torch.float32)
 
-        h = E.linear(ctx, a_in, pk.conv_in_w, boc[0], bias=pk.conv_in_b)
+        h = E.linear(ctx, a_in, pk.conv_in_w, boc[0], bias=pk.conv_in_b, k_alg=9 * self.config.in_channels)
         Ch = boc[0]
         skips = [(h, Ch)]
         for i, blk in enumerate(self.down_blocks):
