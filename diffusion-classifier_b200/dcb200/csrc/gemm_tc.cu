@@ -31,7 +31,10 @@ constexpr int TC_BK = 64;                         // 64 bf16 = 128 B = one swizz
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;     // 16 KB
 constexpr int TC_THREADS = 192;
 constexpr int TC_MAX_STAGES = 8;
-constexpr int TC_SMEM_BUDGET = 200 * 1024;
+constexpr int TC_SMEM_LIMIT = 227 * 1024;
+constexpr int TC_BAR_BYTES = 256;
+// staged epilogue: bf16 [128][128] tile + bias[256] + rowvec[128] + gate[128] + row ids [2][128] + residual rows [2][128]
+constexpr int TC_EPI_BYTES = 128 * 128 * 2 + 512 * 4 + 4 * 128 * 4;
 
 struct TcSeg {
   int map;  // which A tensor map
@@ -48,6 +51,8 @@ struct TcParams {
   int OW, OH, NB;
   int BN, stages, total_kb;
   uint32_t idesc;
+  int staged;   // epilogue through the swizzled smem staging tile + coalesced second pass
+  int uniform;  // every row of an M tile belongs to one rowvec/gate group (tile-constant vectors live in smem)
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------
@@ -134,6 +139,16 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile(
@@ -244,6 +259,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   uint64_t* tempty_bar = bars + 2 * TC_MAX_STAGES + 2;  // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_MAX_STAGES + 4);
   float* mse_smem = reinterpret_cast<float*>(tmem_slot + 2);  // [4]
+  float* stg = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + TC_BAR_BYTES);  // staged epilogue region
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -338,7 +354,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     const bool geglu = e.act == DCB_ACT_GEGLU;
     int as = 0;
     uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x, it = 0; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int tn = tile % p.n_tiles;
       int tm = tile / p.n_tiles;
       const int tm_lin = tm;
@@ -352,9 +368,136 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       const int pix = y * p.OW + x;
       const int m = nb * e.rows_per_sample + pix;
 
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 256);
+      if (p.staged) {
+        // ---------- staged epilogue (bf16 outputs, <= 128 output columns per tile) ----------
+        //  0. per-row ids + tile-constant bias/rowvec/gate vectors -> smem
+        //  1. cp.async prefetch of the whole residual tile (32 KB in flight per SM) into the swizzled staging tile
+        //  2. thread-per-row: TMEM -> regs -> bias, rowvec, act, gate, +residual (smem), act_post -> bf16 in place
+        //  3. coalesced copy-out: 16 threads cover one 256-byte output row
+        uint8_t* stg8 = reinterpret_cast<uint8_t*>(stg);            // [128 rows][16 chunks of 16 B], chunk ^= row & 7
+        float* s_bias = reinterpret_cast<float*>(stg8 + 128 * 256);  // [256]
+        float* s_rowvec = s_bias + 256;                              // [128]
+        float* s_gate = s_rowvec + 128;                              // [128]
+        int* s_m = reinterpret_cast<int*>(s_gate + 128) + (it & 1) * 128;
+        int* s_res = reinterpret_cast<int*>(s_gate + 128) + 256 + (it & 1) * 128;
+        const int et = threadIdx.x - 64;
+        const int wrow0 = tn * p.BN;
+        const int ncols_out = geglu ? 128 : p.BN;
+        const int ocol0 = geglu ? tn * 128 : tn * p.BN;
+        s_m[r] = row_ok ? m : -1;
+        if (e.residual) s_res[r] = row_ok ? (e.res_idx ? e.res_idx[m] : (e.res_mod > 0 ? m % e.res_mod : m)) : -1;
+        for (int c = et; c < p.BN; c += 128) s_bias[c] = (e.bias && wrow0 + c < e.N) ? e.bias[wrow0 + c] : 0.f;
+        if (p.uniform && (e.rowvec || e.gate) && et < ncols_out) {
+          const int m0 = (tb * p.bn) * e.rows_per_sample + (ty * p.bh) * p.OW + tx * p.bw;
+          const int grp0 = m0 / e.rows_per_group;
+          const bool ok = ocol0 + et < e.n_out;
+          if (e.rowvec)
+            s_rowvec[et] = ok ? e.rowvec[(int64_t)(e.rowvec_idx ? e.rowvec_idx[grp0] : grp0) * e.rowvec_ld + ocol0 + et] : 0.f;
+          if (e.gate) s_gate[et] = ok ? e.gate[(int64_t)grp0 * e.gate_ld + ocol0 + et] : 0.f;
+        }
+        epi_bar();  // ids/constants visible; everybody has finished copying the previous tile out of the staging tile
+        const int cc = et & 15, rr0 = et >> 4;            // coalesced role: 16-byte chunk cc of rows rr0, rr0+8, ...
+        const bool cc_ok = cc * 8 < ncols_out && ocol0 + cc * 8 + 8 <= e.n_out;
+        if (e.residual && cc_ok) {
+          const __nv_bfloat16* rbase = (const __nv_bfloat16*)e.residual + ocol0 + cc * 8;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int row = rr0 + 8 * i;
+            const int rrow = s_res[row];
+            if (rrow >= 0)
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(stg8 + row * 256 + ((cc ^ (row & 7)) << 4))),
+                           "l"(rbase + (int64_t)rrow * e.res_ld)
+                           : "memory");
+          }
+          asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+        mbar_wait(smem_u32(&tfull_bar[as]), aphase);
+        tc_fence_after();
+        if (e.residual) {
+          asm volatile("cp.async.wait_group 0;" ::: "memory");
+          epi_bar();
+        }
+        const int grp = (!p.uniform && e.rows_per_group > 0 && row_ok) ? m / e.rows_per_group : 0;
+        // ---- thread-per-row pass ----
+        for (int c = 0; c < ncols_out; c += 16) {
+          uint32_t ra[16], rg[16];
+          tmem_ld16_nowait(taddr + (uint32_t)c, ra);
+          if (geglu) tmem_ld16_nowait(taddr + (uint32_t)(128 + c), rg);
+          tmem_ld_wait();
+          float v[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float a = __uint_as_float(ra[i]) + s_bias[c + i];
+            if (geglu) a *= gelu_erf_f(__uint_as_float(rg[i]) + s_bias[128 + c + i]);
+            v[i] = a;
+          }
+          if (e.rowvec) {
+            if (p.uniform) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] += s_rowvec[c + i];
+            } else if (row_ok) {
+              const float* rv = e.rowvec + (int64_t)(e.rowvec_idx ? e.rowvec_idx[grp] : grp) * e.rowvec_ld + ocol0 + c;
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (ocol0 + c + i < e.n_out) v[i] += rv[i];
+            }
+          }
+          if (e.act == DCB_ACT_SILU || e.act == DCB_ACT_GELU_TANH) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = apply_act(e.act, v[i]);
+          }
+          if (e.gate) {
+            if (p.uniform) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] *= s_gate[c + i];
+            } else if (row_ok) {
+              const float* gt = e.gate + (int64_t)grp * e.gate_ld + ocol0 + c;
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (ocol0 + c + i < e.n_out) v[i] *= gt[i];
+            }
+          }
+          uint4* s0 = reinterpret_cast<uint4*>(stg8 + r * 256 + ((((c >> 3)) ^ (r & 7)) << 4));
+          uint4* s1 = reinterpret_cast<uint4*>(stg8 + r * 256 + ((((c >> 3) + 1) ^ (r & 7)) << 4));
+          if (e.residual && row_ok) {
+            float f[8];
+            unpack_bf16x8(*s0, f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] += f[i];
+            unpack_bf16x8(*s1, f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[8 + i] += f[i];
+          }
+          if (e.act_post != DCB_ACT_NONE) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = apply_act(e.act_post, v[i]);
+          }
+          *s0 = pack_bf16x8(v);
+          *s1 = pack_bf16x8(v + 8);
+        }
+        // accumulator fully drained: hand the TMEM stage back to the MMA warp
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[as]));
+        epi_bar();
+        // ---- coalesced copy-out ----
+        if (cc_ok) {
+          __nv_bfloat16* obase = (__nv_bfloat16*)e.out + ocol0 + cc * 8;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int row = rr0 + 8 * i;
+            const int mm = s_m[row];
+            if (mm >= 0)
+              *reinterpret_cast<uint4*>(obase + (int64_t)mm * e.out_ld) =
+                  *reinterpret_cast<const uint4*>(stg8 + row * 256 + ((cc ^ (row & 7)) << 4));
+          }
+        }
+        if (++as == 2) { as = 0; aphase ^= 1; }
+        continue;
+      }
       mbar_wait(smem_u32(&tfull_bar[as]), aphase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 256);
       float mse_acc = 0.f;
       if (!geglu) {
         for (int c = 0; c < p.BN; c += 16) {
@@ -457,10 +600,12 @@ static int choose_geometry(const GemmDev& g, TcGeom* t) {
     t->BN = 256;
   } else if (N <= 256) {
     t->BN = (N + 15) / 16 * 16;
+    // shallow K: the epilogue paces the tile, so prefer 128-wide tiles (deeper smem ring + staged epilogue)
+    if (t->BN == 256 && g.K <= 2304) t->BN = 128;
     // small-M layers: split N so that more SMs get a tile (smem-bandwidth cost is acceptable below one wave)
     while (t->BN >= 128 && t->BN % 32 == 0 && m_tiles * ((N + t->BN - 1) / t->BN) < num_sms() / 2) t->BN /= 2;
   } else {
-    t->BN = 256;
+    t->BN = g.K <= 2304 ? 128 : 256;
     while (t->BN > 64 && m_tiles * ((N + t->BN - 1) / t->BN) < num_sms()) t->BN /= 2;
   }
   t->n_tiles = (N + t->BN - 1) / t->BN;
@@ -568,7 +713,21 @@ int launch_gemm_tc(const GemmDev& g, cudaStream_t st) {
   p.OW = g.OW; p.OH = g.OH; p.NB = g.NB;
   p.BN = t.BN;
   const int stage_bytes = TC_A_BYTES + t.BN * TC_BK * 2;
-  int stages = TC_SMEM_BUDGET / stage_bytes;
+  {
+    const EpiDev& e = g.epi;
+    // bf16 outputs with <= 128 output columns per tile (BN <= 128, or GEGLU's 256 -> 128); 16-byte aligned rows
+    p.staged = e.out != nullptr && e.out_dtype == DCB_BF16 && e.mse_part == nullptr && e.n_out % 8 == 0 &&
+               e.out_ld % 8 == 0 && ((uintptr_t)e.out % 16) == 0 && (t.BN <= 128 || e.act == DCB_ACT_GEGLU) &&
+               (e.residual == nullptr ||
+                (e.res_dtype == DCB_BF16 && e.res_ld % 8 == 0 && ((uintptr_t)e.residual % 16) == 0));
+    if (getenv("DCB_TC_DIRECT_EPILOGUE")) p.staged = 0;
+    // all rows of an M tile fall into one rowvec/gate group?
+    if (e.rows_per_group <= 0) p.uniform = 1;
+    else if (g.OH == 1 && g.NB == 1) p.uniform = e.rows_per_group % TC_BM == 0;
+    else p.uniform = t.bn == 1 && e.rows_per_group % e.rows_per_sample == 0;
+  }
+  const int epi_bytes = p.staged ? TC_EPI_BYTES : 0;
+  int stages = (TC_SMEM_LIMIT - 1024 - TC_BAR_BYTES - epi_bytes) / stage_bytes;
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
   if (stages > p.total_kb) stages = p.total_kb < 2 ? 2 : p.total_kb;
   p.stages = stages;
@@ -579,7 +738,7 @@ int launch_gemm_tc(const GemmDev& g, cudaStream_t st) {
     DCB_REQUIRE(t.bn == 1 && (g.OH * g.OW) % TC_BM == 0, "fused MSE needs OH*OW %% 128 == 0");
   }
   // always ask for more than half of the SM's shared memory so exactly one CTA (one TMEM owner) is resident
-  size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
+  size_t smem = (size_t)stages * stage_bytes + 1024 + TC_BAR_BYTES + epi_bytes;
   if (smem < 120 * 1024) smem = 120 * 1024;
   static std::once_flag attr_once;
   std::call_once(attr_once, [] {

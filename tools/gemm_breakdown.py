@@ -27,6 +27,10 @@ E.PROFILE = prof = E.GemmProfile()
 dc.classify(x)
 rows = prof.by_shape()
 E.PROFILE = None
+if os.environ.get("PER_LAUNCH"):
+    for i, (a, b, f, tag) in enumerate(prof.rows[:int(os.environ["PER_LAUNCH"])]):
+        ms = a.elapsed_time(b)
+        print(f"{i:3d} {tag:34s} ms={ms:7.3f} TF/s={f/ms/1e9:8.1f}")
 tot = sum(r[1] for r in rows.values())
 print(f"gemm total ms {tot:.2f}")
 for tag, (n, ms, fl) in sorted(rows.items(), key=lambda kv: -kv[1][1]):
