@@ -15,6 +15,7 @@ template <>
 struct Vec<__nv_bfloat16> {
   static constexpr int N = 8;
   __device__ static void load(const __nv_bfloat16* p, float* f) { unpack_bf16x8(*reinterpret_cast<const uint4*>(p), f); }
+  __device__ static void unpack(const uint4& u, float* f) { unpack_bf16x8(u, f); }
   __device__ static void store(__nv_bfloat16* p, const float* f) { *reinterpret_cast<uint4*>(p) = pack_bf16x8(f); }
 };
 template <>
@@ -26,6 +27,9 @@ struct Vec<float> {
   }
   __device__ static void store(float* p, const float* f) {
     *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+  }
+  __device__ static void unpack(const uint4& u, float* f) {
+    f[0] = __uint_as_float(u.x); f[1] = __uint_as_float(u.y); f[2] = __uint_as_float(u.z); f[3] = __uint_as_float(u.w);
   }
 };
 
@@ -58,11 +62,21 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const T* __restric
       int cs, cc;
       if (c < C0) { base = x0 + (int64_t)n * HW * C0; cs = C0; cc = c; }
       else { base = x1 + (int64_t)n * HW * C1; cs = C1; cc = c - C0; }
-      for (int p = p0 + prow; p < p1; p += nrows) {
-        float f[VN];
-        Vec<T>::load(base + (int64_t)p * cs + cc, f);
+      // 8 raw 16-byte loads in flight per thread (Little: ~66 KB/SM must be outstanding to saturate HBM3e)
+      const T* bp = base + cc;
+      for (int p = p0 + prow; p < p1; p += 8 * nrows) {
+        uint4 raw[8];
 #pragma unroll
-        for (int i = 0; i < VN; ++i) { s[i] += f[i]; q[i] = fmaf(f[i], f[i], q[i]); }
+        for (int u = 0; u < 8; ++u)
+          if (p + u * nrows < p1) raw[u] = *reinterpret_cast<const uint4*>(bp + (int64_t)(p + u * nrows) * cs);
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (p + u * nrows < p1) {
+            float f[VN];
+            Vec<T>::unpack(raw[u], f);
+#pragma unroll
+            for (int i = 0; i < VN; ++i) { s[i] += f[i]; q[i] = fmaf(f[i], f[i], q[i]); }
+          }
       }
     }
 #pragma unroll
@@ -84,15 +98,28 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const T* __restric
   if (threadIdx.x < G) { out[threadIdx.x * 2] = gsum; out[threadIdx.x * 2 + 1] = gsq; }
 }
 
+// SiLU for the bf16 path: x * sigmoid(x) with sigmoid = 0.5*tanh(0.5x)+0.5 -> ONE MUFU op per element (the exp+rcp
+// form needs two and made this kernel SFU-bound: 16 MUFU/clk/SM); tanh.approx error (~2^-11) is below bf16 rounding.
+template <typename T>
+__device__ __forceinline__ float gn_silu(float y);
+template <>
+__device__ __forceinline__ float gn_silu<float>(float y) { return silu_f(y); }
+template <>
+__device__ __forceinline__ float gn_silu<__nv_bfloat16>(float y) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * y));
+  return y * fmaf(0.5f, t, 0.5f);
+}
+
 // ---- GroupNorm apply (+SiLU), writes the concatenated normalised tensor [NB,HW,C0+C1] ----------------------
+// thread -> fixed 16-byte channel slot (coefficients live in registers), loops over pixels with 4 loads in flight
 template <typename T>
 __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const T* __restrict__ x0, int C0, const T* __restrict__ x1,
                                                               int C1, int HW, int G, int chunks,
                                                               const float* __restrict__ part, const float* __restrict__ gamma,
                                                               const float* __restrict__ beta, float eps, int silu,
-                                                              T* __restrict__ out, int blocks_per_sample) {
+                                                              T* __restrict__ out, int pix_per_block) {
   constexpr int VN = Vec<T>::N;
-  extern __shared__ float s_ab[];  // [2][C]: y = x*A[c] + B[c]
   __shared__ float s_mean[64], s_rstd[64];
   const int n = blockIdx.y;
   const int C = C0 + C1, V = C / VN, cpg = C / G;
@@ -108,31 +135,44 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const T* __restric
     s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)eps));
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const int g = c / cpg;
-    const float a = s_rstd[g] * gamma[c];
-    s_ab[c] = a;
-    s_ab[C + c] = beta[c] - s_mean[g] * a;
-  }
-  __syncthreads();
-  const int64_t items = (int64_t)HW * V;
-  const int64_t per_block = (items + blocks_per_sample - 1) / blocks_per_sample;
-  const int64_t i0 = blockIdx.x * per_block, i1 = min(items, i0 + per_block);
-  const T* b0 = x0 + (int64_t)n * HW * C0;
-  const T* b1 = x1 ? x1 + (int64_t)n * HW * C1 : nullptr;
+  const int vslots = min(V, (int)blockDim.x);
+  const int nrows = blockDim.x / vslots;
+  const int prow = threadIdx.x / vslots, vs = threadIdx.x % vslots;
+  const int p0 = blockIdx.x * pix_per_block, p1 = min(HW, p0 + pix_per_block);
   T* ob = out + (int64_t)n * HW * C;
-  for (int64_t it = i0 + threadIdx.x; it < i1; it += blockDim.x) {
-    const int64_t p = it / V;
-    const int c = (int)(it - p * V) * VN;
-    float f[VN];
-    if (c < C0) Vec<T>::load(b0 + p * C0 + c, f);
-    else Vec<T>::load(b1 + p * C1 + (c - C0), f);
+  for (int vb = 0; vb < V; vb += vslots) {
+    const int v = vb + vs;
+    if (v >= V) continue;
+    const int c = v * VN;
+    float ca[VN], cbias[VN];
 #pragma unroll
     for (int i = 0; i < VN; ++i) {
-      float y = fmaf(f[i], s_ab[c + i], s_ab[C + c + i]);
-      f[i] = silu ? silu_f(y) : y;
+      const int g = (c + i) / cpg;
+      ca[i] = s_rstd[g] * gamma[c + i];
+      cbias[i] = beta[c + i] - s_mean[g] * ca[i];
     }
-    Vec<T>::store(ob + p * C + c, f);
+    const T* base;
+    int cs;
+    if (c < C0) { base = x0 + (int64_t)n * HW * C0 + c; cs = C0; }
+    else { base = x1 + (int64_t)n * HW * C1 + (c - C0); cs = C1; }
+    T* obase = ob + c;
+    for (int p = p0 + prow; p < p1; p += 4 * nrows) {
+      float f[4][VN];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (p + u * nrows < p1) Vec<T>::load(base + (int64_t)(p + u * nrows) * cs, f[u]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (p + u * nrows < p1) {
+#pragma unroll
+          for (int i = 0; i < VN; ++i) {
+            const float y = fmaf(f[u][i], ca[i], cbias[i]);
+            f[u][i] = silu ? gn_silu<T>(y) : y;
+          }
+          Vec<T>::store(obase + (int64_t)(p + u * nrows) * C, f[u]);
+        }
+      }
+    }
   }
 }
 
@@ -151,15 +191,15 @@ static int gn_stats_t(const void* x0, int C0, const void* x1, int C1, int NB, in
 template <typename T>
 static int gn_apply_t(const void* x0, int C0, const void* x1, int C1, int NB, int HW, int G, int chunks, const float* part,
                       const float* gamma, const float* beta, float eps, int silu, void* out, cudaStream_t st) {
-  const int C = C0 + C1;
-  const int64_t items = (int64_t)HW * (C / Vec<T>::N);
-  int bps = (int)((items + 4 * GN_THREADS - 1) / (4 * GN_THREADS));  // ~4 vectors per thread
-  const int want = (4 * num_sms() + NB - 1) / NB;                      // but do not shred small tensors
-  if (bps > want * 4) bps = want * 4;
-  if (bps < 1) bps = 1;
-  dim3 grid(bps, NB);
-  gn_apply_kernel<T><<<grid, GN_THREADS, 2 * C * sizeof(float), st>>>((const T*)x0, C0, (const T*)x1, C1, HW, G, chunks,
-                                                                      part, gamma, beta, eps, silu, (T*)out, bps);
+  const int V = (C0 + C1) / Vec<T>::N;
+  const int threads = gn_threads(V);
+  const int nrows = threads / (V < threads ? V : threads);
+  const int vwin = (V + threads - 1) / threads;           // channel windows a thread walks through
+  int ppb = nrows * (32 / (vwin < 32 ? vwin : 32));      // ~32 vectors per thread
+  if (ppb < nrows) ppb = nrows;
+  dim3 grid((HW + ppb - 1) / ppb, NB);
+  gn_apply_kernel<T><<<grid, threads, 0, st>>>((const T*)x0, C0, (const T*)x1, C1, HW, G, chunks, part, gamma, beta, eps,
+                                               silu, (T*)out, ppb);
   DCB_CHECK_LAUNCH("gn_apply");
   return DCB_OK;
 }
@@ -169,7 +209,6 @@ static int gn_check(int dtype, int C0, int C1, int G, const void* x1) {
   DCB_REQUIRE(G > 0 && G <= 64 && (C0 + C1) % G == 0, "groupnorm: C=%d not divisible by G=%d (G<=64)", C0 + C1, G);
   DCB_REQUIRE(C0 % vn == 0 && C1 % vn == 0, "groupnorm: channel counts must be multiples of %d", vn);
   DCB_REQUIRE((C1 == 0) == (x1 == nullptr), "groupnorm: x1/C1 mismatch");
-  DCB_REQUIRE(2 * (C0 + C1) * sizeof(float) <= 48 * 1024, "groupnorm: C too large");
   return DCB_OK;
 }
 

@@ -137,7 +137,7 @@ def linear(ctx, x, W, N, *, K=None, c_off=0, **kw):
 def gn_chunks(NB, HW, Ctot):
     """pixel chunks per sample for the GroupNorm statistics pass.  Deliberately a function of the per-sample shape
     only (never of the batch), so a sample's result is bit-identical however the batch is composed / sharded."""
-    return max(1, min((HW * Ctot) // 32768, 64, HW))
+    return max(1, min((HW * Ctot) // 131072, 64, HW))
 
 
 def groupnorm(ctx, x0, C0, x1, C1, NB, HW, gamma, beta, eps, silu, G=32):
