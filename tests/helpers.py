@@ -30,6 +30,27 @@ UNET128 = dict(
     mid_block_type="UNetMidBlock2DCrossAttn", encoder_hid_dim=512, encoder_hid_dim_type="text_proj",
     cross_attention_dim=512)
 
+UNET256 = dict(
+    sample_size=256, in_channels=3, out_channels=3, layers_per_block=2,
+    block_out_channels=(128, 128, 256, 256, 512, 1024),
+    down_block_types=("DownBlock2D", "DownBlock2D", "DownBlock2D", "DownBlock2D", "CrossAttnDownBlock2D", "DownBlock2D"),
+    up_block_types=("UpBlock2D", "CrossAttnUpBlock2D", "UpBlock2D", "UpBlock2D", "UpBlock2D", "UpBlock2D"),
+    mid_block_type="UNetMidBlock2DCrossAttn", encoder_hid_dim=512, encoder_hid_dim_type="text_proj",
+    cross_attention_dim=512)
+
+IPMSA5_DWT_UNET = dict(
+    sample_size=128, in_channels=40, out_channels=40, layers_per_block=(2, 2, 2, 4, 2),
+    block_out_channels=(128, 128, 256, 512, 768),
+    down_block_types=("DownBlock2D", "DownBlock2D", "DownBlock2D", "CrossAttnDownBlock2D", "DownBlock2D"),
+    up_block_types=("UpBlock2D", "CrossAttnUpBlock2D", "UpBlock2D", "UpBlock2D", "UpBlock2D"),
+    mid_block_type="UNetMidBlock2DCrossAttn", encoder_hid_dim=512, encoder_hid_dim_type="text_proj",
+    cross_attention_dim=512)
+
+DIT_B4_256 = dict(num_attention_heads=12, attention_head_dim=64, in_channels=3, out_channels=3, num_layers=12,
+                  dropout=0.0, norm_num_groups=32, attention_bias=True, sample_size=256, patch_size=4,
+                  activation_fn="gelu-approximate", num_embeds_ada_norm=1000, upcast_attention=False,
+                  norm_type="ada_norm_zero", norm_elementwise_affine=False, norm_eps=1e-5)
+
 TINY_DIT = dict(num_attention_heads=2, attention_head_dim=64, in_channels=3, out_channels=3, num_layers=2,
                 sample_size=32, patch_size=2, norm_eps=1e-5)
 
@@ -78,7 +99,7 @@ def make_pair(kind, arch, seed=0, device="cpu", amplify=1.0):
     else:
         o = dr.DiTTransformer2DModel(**arch)
         p = dcb200.DiT(**arch)
-    if amplify != 1.0 and kind == "dit":
+    if amplify != 1.0 and kind == "dit":  # random-init nets barely react to the class: make margins meaningful
         with torch.no_grad():
             for b in o.transformer_blocks:
                 b.norm1.emb.class_embedder.embedding_table.weight.mul_(amplify)

@@ -1,0 +1,71 @@
+"""BASELINE.json configs C2-C5 at their REAL architectures and image sizes (models/unet-128.py, models/unet-256.py,
+models/chexpert-256-dit-b4.py, models/ipmsa-5-dwt-unet.py): product classify() on the B200 vs the fp32 oracle loop on
+the host with identical pre-drawn noise, few timesteps (the oracle must finish in seconds).  bf16 tolerance 1e-2 on the
+per-class ELBO errors (north star); margin-aware label comparison."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import DIT_B4_256, IPMSA5_DWT_UNET, UNET128, UNET256, base_cfg, make_pair
+from test_gpu_c_models import _check_classify
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(dev, kind, arch, cfg, x, T, BS, amplify):
+    import dcb200
+    from oracle import loop
+    o, p = make_pair(kind, arch, seed=0, amplify=amplify)
+    torch.manual_seed(1)
+    dc = dcb200.DiffusionClassifier(p, cfg)
+    enc = None
+    if kind == "unet":
+        with torch.no_grad():
+            dc.encoder.weight.mul_(amplify)
+        enc = torch.nn.Embedding(cfg.classes + 1, arch["encoder_hid_dim"])
+        enc.load_state_dict(dc.encoder.state_dict())
+    g = torch.Generator().manual_seed(2)
+    t_all = torch.rand(T, BS, generator=g)
+    eps_all = torch.randn(T, *x.shape, generator=g)
+
+    class Den(torch.nn.Module):
+        def forward(self, x, noise_labels, encoder_hidden_states):
+            return o(x, noise_labels, encoder_hidden_states)[0]
+
+    ref_labels, ref_err = loop.classify_oracle(Den(), enc, cfg, x, t_all=t_all, eps_all=eps_all, return_errors=True)
+    dc = dc.to(dev).eval()
+    labels = dc.classify(x.to(dev), t_all=t_all, eps_all=eps_all)
+    _check_classify(labels.cpu(), dc.last_errors, ref_labels.numpy(), ref_err.mean(dim=2).numpy(), 1e-2)
+    return dc
+
+
+def test_c2_unet128(dev):
+    cfg = base_cfg(classes=2, evaluation_per_stage=[2], noise_d=128, image_size=128)
+    x = torch.rand(2, 3, 128, 128, generator=torch.Generator().manual_seed(0)) * 2 - 1
+    _run(dev, "unet", UNET128, cfg, x, 2, 2, 40.0)
+
+
+def test_c3_unet256_shifted_cosine(dev):
+    cfg = base_cfg(classes=2, evaluation_per_stage=[1], noise_d=64, image_size=256, schedule="shifted_cosine")
+    x = torch.rand(1, 3, 256, 256, generator=torch.Generator().manual_seed(0)) * 2 - 1
+    _run(dev, "unet", UNET256, cfg, x, 1, 1, 40.0)
+
+
+def test_c4_dit_b4_256(dev):
+    cfg = base_cfg(classes=2, evaluation_per_stage=[1], noise_d=64, image_size=256, schedule="shifted_cosine",
+                   encoder_type="DiT", pred_param="v")
+    x = torch.rand(1, 3, 256, 256, generator=torch.Generator().manual_seed(0)) * 2 - 1
+    _run(dev, "dit", DIT_B4_256, cfg, x, 1, 1, 20.0)
+
+
+def test_c5_ipmsa5_dwt_unet_with_gpu_haar(dev):
+    """pixel input [BS,10,256,256] -> Haar DWT /2 (utils/wavelet.py + experiments/ipmsa/inference.py:153-155) ->
+    [BS,40,128,128] wavelet-domain ELBO classification; DWT by dcb_haar_dwt vs the numpy oracle."""
+    import dcb200
+    from oracle import haar
+    pix = torch.rand(1, 10, 256, 256, generator=torch.Generator().manual_seed(0)) * 2 - 1
+    w_ref = torch.from_numpy(np.stack([haar.wavelet_dec_2_np(im.numpy()) for im in pix])) / 2
+    w = dcb200.wavelet_dec_2(pix.to(dev), 0.5)
+    assert w.shape == (1, 40, 128, 128) and (w.cpu() - w_ref).abs().max() < 1e-6
+    cfg = base_cfg(classes=2, evaluation_per_stage=[1], noise_d=128, image_size=128, wavelet_transform=True)
+    _run(dev, "unet", IPMSA5_DWT_UNET, cfg, w_ref, 1, 1, 40.0)
