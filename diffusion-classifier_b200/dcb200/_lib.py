@@ -39,6 +39,7 @@ _PROTOS = {
     "dcb_version": (c_int, []),
     "dcb_last_error": (C.c_char_p, []),
     "dcb_launch_count": (c_i64, []),
+    "dcb_note_graph_replay": (None, [c_i64]),
     "dcb_prologue": (c_int, [c_int, c_int, c_void_p, c_void_p, c_u64, c_i64, c_void_p, c_void_p, c_void_p, c_int, c_int,
                              c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "dcb_timestep_embed": (c_int, [c_int, c_void_p, c_int, c_int, c_int, c_float, c_float, c_void_p, c_void_p]),

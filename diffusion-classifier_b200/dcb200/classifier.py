@@ -22,6 +22,7 @@ import os
 import torch
 import torch.nn as nn
 
+from . import _lib as L
 from . import engine as E
 from .dit import DiT
 from .ema import EMA
@@ -48,6 +49,58 @@ def combine_stage_errors(errors, slab, classes, start, end, dist=None):
     alive.scatter_(1, classes, True)
     errors[:, :, start:end] = torch.where(alive.unsqueeze(-1), slab, errors[:, :, start:end])
     return errors
+
+
+class _GraphedDenoiser:
+    """One CUDA graph per (network, chunk shape): the ~500 kernel launches of a denoiser pass + fused eps-MSE are
+    captured once and replayed; the prologue writes straight into the graph's fixed input buffers.  (CUDA streams and
+    graphs instead of a tracing compiler -- the captured launches are exactly the eager ones.)"""
+    _pool = None
+
+    def __init__(self, net, ctx, pk, is_dit, U, nk, Cimg, H, W, patch, v_param, fused):
+        dev = ctx.device
+        rows = (H // patch) * (W // patch)
+        S = U * nk
+        self.a_in = ctx.empty(S * rows, pk.kpad_in)
+        self.target = torch.empty(U * H * W * Cimg, device=dev, dtype=torch.float32)
+        self.logsnr = torch.empty(U, device=dev, dtype=torch.float32)
+        self.cls = torch.empty(S, device=dev, dtype=torch.int32)
+        self.scale = torch.empty(S, device=dev, dtype=torch.float32) if v_param else None
+        self.err = torch.empty(S, device=dev, dtype=torch.float32)
+        self.table = None
+        self.graph = None
+        self.args = (net, ctx, pk, is_dit, U, nk, H, W, (patch * patch * Cimg) if is_dit else Cimg, fused)
+        self.warm = 0
+
+    def _run(self):
+        net, ctx, pk, is_dit, U, nk, H, W, No, fused = self.args
+        mse = dict(target=self.target, div=nk, ld=No, err=self.err, fused=fused, scale=self.scale)
+        if is_dit:
+            net.run(ctx, pk, self.a_in, self.logsnr, U, nk, self.cls, mse=mse)
+        else:
+            net.run(ctx, pk, self.a_in, self.logsnr, U, nk, H, W, self.table, xattn_idx=self.cls, mse=mse)
+
+    def launch(self):
+        if self.graph is not None:
+            self.graph.replay()
+            L.lib().dcb_note_graph_replay(self.n_kernels)
+            return
+        if self.warm < 2:                # eager first (sets kernel attributes, fills the allocator / tensor-map caches)
+            self._run()
+            self.warm += 1
+            return
+        torch.cuda.synchronize()         # third use of this chunk shape: capture, then replay
+        g = torch.cuda.CUDAGraph()
+        if _GraphedDenoiser._pool is None:
+            _GraphedDenoiser._pool = torch.cuda.graph_pool_handle()
+        n0 = L.launch_count()
+        with torch.cuda.graph(g, pool=_GraphedDenoiser._pool):
+            self._run()
+        self.n_kernels = L.launch_count() - n0
+        L.lib().dcb_note_graph_replay(-self.n_kernels)   # captured launches did not execute
+        self.graph = g
+        self.graph.replay()
+        L.lib().dcb_note_graph_replay(self.n_kernels)
 
 
 class DiffusionClassifier(nn.Module):
@@ -80,6 +133,8 @@ class DiffusionClassifier(nn.Module):
             self.null_token = self.config.classes
         self.last_errors = None  # [BS, classes, T] fp32 table of the most recent classify() call
         self._eps_calls = 0
+        self._graphs = {}
+        self._table_buf = None
 
     # ---- schedule (diffusion_classifier.py:119-161), evaluated exactly as the reference does ------------------
     def logsnr_schedule_cosine(self, t, logsnr_min=-15, logsnr_max=15):
@@ -152,8 +207,14 @@ class DiffusionClassifier(nn.Module):
         xin = x.contiguous().float()
         v_param = self.pred_param == 'v'
         table = None
-        if not is_dit:  # collapsed cross-attention bias per class, once per call
-            table = net.cross_attn_table(ctx, pk, E.cast(ctx, self.encoder.weight))
+        if not is_dit:  # collapsed cross-attention bias per class, once per call (persistent buffer: graphs read it)
+            tb = net.cross_attn_table(ctx, pk, E.cast(ctx, self.encoder.weight))
+            if self._table_buf is None or self._table_buf.shape != tb.shape or self._table_buf.device != tb.device:
+                self._table_buf = torch.empty_like(tb)
+            self._table_buf.copy_(tb)
+            table = self._table_buf
+        use_graph = ctx.precision == "bf16" and getattr(cfg, "dcb_cuda_graph", None) is not False \
+            and os.environ.get("DCB_CUDA_GRAPH", "1") != "0"
         patch = net.config.patch_size if is_dit else 1
         No = (patch * patch * Cimg) if is_dit else Cimg
         rows = (H // patch) * (W // patch)
@@ -194,17 +255,35 @@ class DiffusionClassifier(nn.Module):
                 jrel = units // BS
                 cls = classes[img.long()]                              # [U, nk]
                 cls32 = cls.reshape(-1).to(torch.int32).contiguous()
-                a_in, target = E.prologue(
-                    ctx, 1 if is_dit else 0, xin, U, nk, Cimg, H, W, pk.kpad_in, patch=patch,
-                    eps=None if eps_stage is None else eps_stage[u0:u0 + U], seed=seed, unit_id0=start * BS + u0,
-                    alpha=alpha[u0:u0 + U], sigma=sigma[u0:u0 + U], img=img, want_target=True, v_param=v_param)
-                err = torch.empty(U * nk, device=dev, dtype=torch.float32)
-                mse = dict(target=target, div=nk, ld=No, err=err, fused=fused,
-                           scale=alpha[u0:u0 + U].repeat_interleave(nk).contiguous() if v_param else None)
-                if is_dit:
-                    net.run(ctx, pk, a_in, logsnr[u0:u0 + U], U, nk, cls32, mse=mse)
+                pro = dict(patch=patch, eps=None if eps_stage is None else eps_stage[u0:u0 + U], seed=seed,
+                           unit_id0=start * BS + u0, alpha=alpha[u0:u0 + U], sigma=sigma[u0:u0 + U], img=img,
+                           want_target=True, v_param=v_param)
+                if use_graph:
+                    key = (id(net), id(pk), is_dit, U, nk, Cimg, H, W, v_param, fused, str(dev))
+                    gr = self._graphs.get(key)
+                    if gr is None:
+                        if len(self._graphs) >= 6:      # stale shapes / repacked weights: drop old graphs
+                            self._graphs.clear()
+                        gr = self._graphs[key] = _GraphedDenoiser(net, ctx, pk, is_dit, U, nk, Cimg, H, W, patch,
+                                                                  v_param, fused)
+                    gr.table = table
+                    E.prologue(ctx, 1 if is_dit else 0, xin, U, nk, Cimg, H, W, pk.kpad_in, a_out=gr.a_in,
+                               target_out=gr.target, **pro)
+                    gr.logsnr.copy_(logsnr[u0:u0 + U])
+                    gr.cls.copy_(cls32)
+                    if v_param:
+                        gr.scale.copy_(alpha[u0:u0 + U].repeat_interleave(nk))
+                    gr.launch()
+                    err = gr.err
                 else:
-                    net.run(ctx, pk, a_in, logsnr[u0:u0 + U], U, nk, H, W, table, xattn_idx=cls32, mse=mse)
+                    a_in, target = E.prologue(ctx, 1 if is_dit else 0, xin, U, nk, Cimg, H, W, pk.kpad_in, **pro)
+                    err = torch.empty(U * nk, device=dev, dtype=torch.float32)
+                    mse = dict(target=target, div=nk, ld=No, err=err, fused=fused,
+                               scale=alpha[u0:u0 + U].repeat_interleave(nk).contiguous() if v_param else None)
+                    if is_dit:
+                        net.run(ctx, pk, a_in, logsnr[u0:u0 + U], U, nk, cls32, mse=mse)
+                    else:
+                        net.run(ctx, pk, a_in, logsnr[u0:u0 + U], U, nk, H, W, table, xattn_idx=cls32, mse=mse)
                 b_idx = img.long().repeat_interleave(nk)
                 j_idx = jrel.repeat_interleave(nk)
                 if slab is None:

@@ -84,6 +84,7 @@ using namespace dcb;
 extern "C" int dcb_version(void) { return 100; }
 extern "C" const char* dcb_last_error(void) { return g_err; }
 extern "C" int64_t dcb_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+extern "C" void dcb_note_graph_replay(int64_t n_kernels) { g_launches.fetch_add(n_kernels, std::memory_order_relaxed); }
 
 extern "C" int dcb_gemm(const dcb_gemm_desc* d, dcb_stream stream) {
   GemmDev g;

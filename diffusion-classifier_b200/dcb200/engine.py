@@ -190,12 +190,14 @@ def timestep_embed(ctx, t, U, rep, dim, shift, max_period=10000.0):
 
 
 def prologue(ctx, mode, x, U, rep, C_, H, W, kpad, *, patch=1, eps=None, seed=0, unit_id0=0, alpha=None, sigma=None,
-             img=None, want_target=False, v_param=False):
-    """q_sample + first-layer operand staging.  Returns (a_in [U*rep*rows, kpad], target or None)."""
+             img=None, want_target=False, v_param=False, a_out=None, target_out=None):
+    """q_sample + first-layer operand staging.  Returns (a_in [U*rep*rows, kpad], target or None).
+    ``a_out`` / ``target_out`` let the caller supply persistent buffers (CUDA-graph replay reads fixed addresses)."""
     rows = H * W if mode == 0 else (H // patch) * (W // patch)
     z_ws = torch.empty(U * H * W * C_, device=ctx.device, dtype=torch.float32)
-    a = ctx.empty(U * rep * rows, kpad)
-    tgt = torch.empty(U * H * W * C_, device=ctx.device, dtype=torch.float32) if want_target else None
+    a = a_out if a_out is not None else ctx.empty(U * rep * rows, kpad)
+    tgt = target_out if target_out is not None else (
+        torch.empty(U * H * W * C_, device=ctx.device, dtype=torch.float32) if want_target else None)
     L.check(L.lib().dcb_prologue(mode, ctx.code, x.data_ptr(), _p(eps), seed, unit_id0, _p(alpha), _p(sigma), _p(img), U,
                                  rep, C_, H, W, patch, kpad, z_ws.data_ptr(), a.data_ptr(), _p(tgt), int(v_param),
                                  ctx.stream()), "prologue")

@@ -33,6 +33,8 @@ int dcb_version(void);
 const char* dcb_last_error(void);
 /* number of kernel launches issued by this library since load (bench.py's "gpu_launches") */
 int64_t dcb_launch_count(void);
+/* the host replayed a CUDA graph that holds n_kernels of this library's launches (keeps dcb_launch_count honest) */
+void dcb_note_graph_replay(int64_t n_kernels);
 
 /* ---- (1) prologue: q_sample fused with the denoiser's input staging ------------------------------------
  * replaces DiffusionClassifier.diffuse (diffusion_classifier.py:100-117) + the first-layer unfold:

@@ -200,3 +200,27 @@ def test_classify_reference_rng_semantics(dev):
     fin = torch.isfinite(dc.last_errors[:, :, 0])
     # torch.randint draws the wrong classes WITH replacement (:676), so 2 or 3 distinct candidates per image
     assert all(2 <= n <= 3 for n in fin.sum(1).tolist()) and bool(fin[torch.arange(4), text].all())
+
+
+def test_cuda_graph_replay_is_bit_identical_to_eager(dev):
+    """the captured launch sequence is the eager one: graph replays (3rd use of a chunk shape onwards) must reproduce the
+    eager error table bit for bit, and the launch counter must keep counting replayed kernels."""
+    import dcb200
+    _, p = make_pair("unet", TINY_UNET, seed=0)
+    cfg = base_cfg(classes=3, evaluation_per_stage=[8], noise_d=16, image_size=16, dcb_max_batch=6)
+    dc = dcb200.DiffusionClassifier(p, cfg).to(dev).eval()
+    g = torch.Generator().manual_seed(3)
+    x = (torch.rand(2, 3, 16, 16, generator=g) * 2 - 1).to(dev)
+    t_all, eps_all = torch.rand(8, 2, generator=g), torch.randn(8, 2, 3, 16, 16, generator=g)
+    cfg.dcb_cuda_graph = False
+    dc.classify(x, t_all=t_all, eps_all=eps_all)
+    eager = dc.last_errors.clone()
+    cfg.dcb_cuda_graph = None
+    n0 = dcb200.launch_count()
+    dc.classify(x, t_all=t_all, eps_all=eps_all)      # 8 chunks of 2 units: eager, eager, capture+replay, replay...
+    n1 = dcb200.launch_count()
+    assert any(g.graph is not None for g in dc._graphs.values())
+    assert torch.equal(dc.last_errors, eager)
+    dc.classify(x, t_all=t_all, eps_all=eps_all)      # all replays
+    assert torch.equal(dc.last_errors, eager)
+    assert dcb200.launch_count() - n1 == n1 - n0 > 0

@@ -23,6 +23,7 @@ torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record(); dc.classify(x); e1.record(); torch.cuda.synchronize()
 print("step ms", e0.elapsed_time(e1))
+cfg.dcb_cuda_graph = False
 E.PROFILE = prof = E.GemmProfile()
 dc.classify(x)
 rows = prof.by_shape()
