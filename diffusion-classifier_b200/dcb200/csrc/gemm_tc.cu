@@ -22,26 +22,12 @@
 
 #include <mutex>
 
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace dcb {
 
-constexpr int TC_BM = 128;
-constexpr int TC_BK = 64;                         // 64 bf16 = 128 B = one swizzle-128B row
-constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;     // 16 KB
 constexpr int TC_THREADS = 192;
 constexpr int TC_MAX_STAGES = 8;
-constexpr int TC_SMEM_LIMIT = 227 * 1024;
-constexpr int TC_BAR_BYTES = 256;
-// staged epilogue: bf16 [128][128] tile + bias[256] + rowvec[128] + gate[128] + row ids [2][128] + residual rows [2][128]
-constexpr int TC_EPI_BYTES = 128 * 128 * 2 + 512 * 4 + 4 * 128 * 4;
-
-struct TcSeg {
-  int map;  // which A tensor map
-  int c0;   // channel coordinate (dim 0) of the first K block (includes the x-parity offset for stride 2)
-  int dx, p, dy;
-  int nkb;  // K blocks (of 64) in this segment
-};
 
 struct TcParams {
   int nseg;
@@ -54,122 +40,6 @@ struct TcParams {
   int staged;   // epilogue through the swizzled smem staging tile + coalesced second pass
   int uniform;  // every row of an M tile belongs to one rowvec/gate group (tile-constant vectors live in smem)
 };
-
-// ---- PTX wrappers ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ uint64_t globaltimer_ns() {
-  uint64_t t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-// Bounded wait: a protocol bug becomes a trap (an error the host sees) instead of a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0;
-  uint64_t t0 = 0;
-  for (uint32_t spins = 0;; ++spins) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (done) return;
-    if ((spins & 0x3ff) == 0x3ff) {
-      uint64_t now = globaltimer_ns();
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > 4000000000ull) {
-        printf("dcb gemm_tc: mbarrier wait timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x,
-               bar, parity);
-        __trap();
-      }
-    }
-  }
-}
-__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
-                                            int c3, int c4) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                         uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// 32 lanes x 16 consecutive fp32 columns: thread t of the warp receives lane (base_lane + t)
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-  uint32_t r[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "elect.sync _|p, 0xffffffff;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(pred));
-  return pred != 0;
-}
-
-// K-major, 128B-swizzled operand tile ([rows][64 bf16], 8-row atoms of 1024 B): SBO = 1024 B, LBO unused (=1),
-// descriptor version 1 (Blackwell), layout type 2 (SWIZZLE_128B).  cf. cute::UMMA::SmemDescriptor.
-__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
 
 // ---- epilogue for 16 consecutive output columns of one row ------------------------------------------------
 // v[] holds acc (+bias already added by caller for GEGLU); n0 is the first OUTPUT column.
@@ -370,129 +240,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
 
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 256);
       if (p.staged) {
-        // ---------- staged epilogue (bf16 outputs, <= 128 output columns per tile) ----------
-        //  0. per-row ids + tile-constant bias/rowvec/gate vectors -> smem
-        //  1. cp.async prefetch of the whole residual tile (32 KB in flight per SM) into the swizzled staging tile
-        //  2. thread-per-row: TMEM -> regs -> bias, rowvec, act, gate, +residual (smem), act_post -> bf16 in place
-        //  3. coalesced copy-out: 16 threads cover one 256-byte output row
-        uint8_t* stg8 = reinterpret_cast<uint8_t*>(stg);            // [128 rows][16 chunks of 16 B], chunk ^= row & 7
-        float* s_bias = reinterpret_cast<float*>(stg8 + 128 * 256);  // [256]
-        float* s_rowvec = s_bias + 256;                              // [128]
-        float* s_gate = s_rowvec + 128;                              // [128]
-        int* s_m = reinterpret_cast<int*>(s_gate + 128) + (it & 1) * 128;
-        int* s_res = reinterpret_cast<int*>(s_gate + 128) + 256 + (it & 1) * 128;
-        const int et = threadIdx.x - 64;
-        const int wrow0 = tn * p.BN;
-        const int ncols_out = geglu ? 128 : p.BN;
-        const int ocol0 = geglu ? tn * 128 : tn * p.BN;
-        s_m[r] = row_ok ? m : -1;
-        if (e.residual) s_res[r] = row_ok ? (e.res_idx ? e.res_idx[m] : (e.res_mod > 0 ? m % e.res_mod : m)) : -1;
-        for (int c = et; c < p.BN; c += 128) s_bias[c] = (e.bias && wrow0 + c < e.N) ? e.bias[wrow0 + c] : 0.f;
-        if (p.uniform && (e.rowvec || e.gate) && et < ncols_out) {
-          const int m0 = (tb * p.bn) * e.rows_per_sample + (ty * p.bh) * p.OW + tx * p.bw;
-          const int grp0 = m0 / e.rows_per_group;
-          const bool ok = ocol0 + et < e.n_out;
-          if (e.rowvec)
-            s_rowvec[et] = ok ? e.rowvec[(int64_t)(e.rowvec_idx ? e.rowvec_idx[grp0] : grp0) * e.rowvec_ld + ocol0 + et] : 0.f;
-          if (e.gate) s_gate[et] = ok ? e.gate[(int64_t)grp0 * e.gate_ld + ocol0 + et] : 0.f;
-        }
-        epi_bar();  // ids/constants visible; everybody has finished copying the previous tile out of the staging tile
-        const int cc = et & 15, rr0 = et >> 4;            // coalesced role: 16-byte chunk cc of rows rr0, rr0+8, ...
-        const bool cc_ok = cc * 8 < ncols_out && ocol0 + cc * 8 + 8 <= e.n_out;
-        if (e.residual && cc_ok) {
-          const __nv_bfloat16* rbase = (const __nv_bfloat16*)e.residual + ocol0 + cc * 8;
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int row = rr0 + 8 * i;
-            const int rrow = s_res[row];
-            if (rrow >= 0)
-              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(stg8 + row * 256 + ((cc ^ (row & 7)) << 4))),
-                           "l"(rbase + (int64_t)rrow * e.res_ld)
-                           : "memory");
-          }
-          asm volatile("cp.async.commit_group;" ::: "memory");
-        }
-        mbar_wait(smem_u32(&tfull_bar[as]), aphase);
-        tc_fence_after();
-        if (e.residual) {
-          asm volatile("cp.async.wait_group 0;" ::: "memory");
-          epi_bar();
-        }
-        const int grp = (!p.uniform && e.rows_per_group > 0 && row_ok) ? m / e.rows_per_group : 0;
-        // ---- thread-per-row pass ----
-        for (int c = 0; c < ncols_out; c += 16) {
-          uint32_t ra[16], rg[16];
-          tmem_ld16_nowait(taddr + (uint32_t)c, ra);
-          if (geglu) tmem_ld16_nowait(taddr + (uint32_t)(128 + c), rg);
-          tmem_ld_wait();
-          float v[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float a = __uint_as_float(ra[i]) + s_bias[c + i];
-            if (geglu) a *= gelu_erf_f(__uint_as_float(rg[i]) + s_bias[128 + c + i]);
-            v[i] = a;
-          }
-          if (e.rowvec) {
-            if (p.uniform) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] += s_rowvec[c + i];
-            } else if (row_ok) {
-              const float* rv = e.rowvec + (int64_t)(e.rowvec_idx ? e.rowvec_idx[grp] : grp) * e.rowvec_ld + ocol0 + c;
-#pragma unroll
-              for (int i = 0; i < 16; ++i)
-                if (ocol0 + c + i < e.n_out) v[i] += rv[i];
-            }
-          }
-          if (e.act == DCB_ACT_SILU || e.act == DCB_ACT_GELU_TANH) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = apply_act(e.act, v[i]);
-          }
-          if (e.gate) {
-            if (p.uniform) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] *= s_gate[c + i];
-            } else if (row_ok) {
-              const float* gt = e.gate + (int64_t)grp * e.gate_ld + ocol0 + c;
-#pragma unroll
-              for (int i = 0; i < 16; ++i)
-                if (ocol0 + c + i < e.n_out) v[i] *= gt[i];
-            }
-          }
-          uint4* s0 = reinterpret_cast<uint4*>(stg8 + r * 256 + ((((c >> 3)) ^ (r & 7)) << 4));
-          uint4* s1 = reinterpret_cast<uint4*>(stg8 + r * 256 + ((((c >> 3) + 1) ^ (r & 7)) << 4));
-          if (e.residual && row_ok) {
-            float f[8];
-            unpack_bf16x8(*s0, f);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] += f[i];
-            unpack_bf16x8(*s1, f);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[8 + i] += f[i];
-          }
-          if (e.act_post != DCB_ACT_NONE) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = apply_act(e.act_post, v[i]);
-          }
-          *s0 = pack_bf16x8(v);
-          *s1 = pack_bf16x8(v + 8);
-        }
-        // accumulator fully drained: hand the TMEM stage back to the MMA warp
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[as]));
-        epi_bar();
-        // ---- coalesced copy-out ----
-        if (cc_ok) {
-          __nv_bfloat16* obase = (__nv_bfloat16*)e.out + ocol0 + cc * 8;
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int row = rr0 + 8 * i;
-            const int mm = s_m[row];
-            if (mm >= 0)
-              *reinterpret_cast<uint4*>(obase + (int64_t)mm * e.out_ld) =
-                  *reinterpret_cast<const uint4*>(stg8 + row * 256 + ((cc ^ (row & 7)) << 4));
-          }
-        }
+        EpiGeom gq{p.tiles_x, p.tiles_y, p.bw, p.bh, p.bn, p.OW, p.OH, p.NB, p.uniform};
+        staged_epilogue(gq, e, reinterpret_cast<uint8_t*>(stg), it & 1, tm_lin, tn, p.BN, taddr,
+                        smem_u32(&tfull_bar[as]), aphase, true, smem_u32(&tempty_bar[as]), true);
         if (++as == 2) { as = 0; aphase ^= 1; }
         continue;
       }
@@ -557,7 +307,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
 }
 
 // ---- host side ----------------------------------------------------------------------------------------------
-static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+PFN_cuTensorMapEncodeTiled_v12000 tc_encode_fn() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
   static std::once_flag once;
   std::call_once(once, [] {
@@ -623,7 +373,7 @@ int tc_geometry(const GemmDev& g, int* m_tiles, int* n_tiles, int* BN) {
 }
 
 static int encode_a_map(CUtensorMap* map, const SegDev& s, int NBsrc, const TcGeom& t) {
-  auto enc = get_encode_fn();
+  auto enc = tc_encode_fn();
   DCB_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[5], strides[4];
   const cuuint64_t es = 2, C = s.C, H = s.H, W = s.W;
@@ -644,6 +394,9 @@ static int encode_a_map(CUtensorMap* map, const SegDev& s, int NBsrc, const TcGe
               (int)r, s.C, s.H, s.W, NBsrc, s.stride, t.bw, t.bh, t.bn);
   return DCB_OK;
 }
+
+int launch_gemm_tc2(const GemmDev& g, cudaStream_t st, int bw, int bh, int bn, int tiles_x, int tiles_y, int tiles_nb,
+                    int BN, int uniform);
 
 int launch_gemm_tc(const GemmDev& g, cudaStream_t st) {
   DCB_REQUIRE(g.dtype == DCB_BF16, "tcgen05 engine is bf16 only");
@@ -696,7 +449,7 @@ int launch_gemm_tc(const GemmDev& g, cudaStream_t st) {
 
   CUtensorMap mapB;
   {
-    auto enc = get_encode_fn();
+    auto enc = tc_encode_fn();
     cuuint64_t dims[2] = {(cuuint64_t)g.K, (cuuint64_t)g.epi.N};
     cuuint64_t strides[1] = {(cuuint64_t)g.K * 2};
     cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)t.BN};
@@ -725,6 +478,12 @@ int launch_gemm_tc(const GemmDev& g, cudaStream_t st) {
     if (e.rows_per_group <= 0) p.uniform = 1;
     else if (g.OH == 1 && g.NB == 1) p.uniform = e.rows_per_group % TC_BM == 0;
     else p.uniform = t.bn == 1 && e.rows_per_group % e.rows_per_sample == 0;
+  }
+  // big N<=128-wide problems: 256-pixel CTAs with split A/B rings (+ x-halo reuse for 3x3 convs), see gemm_tc2.cu
+  if (p.staged && t.BN <= 128 && g.epi.act != DCB_ACT_GEGLU && !getenv("DCB_NO_TC2") &&
+      t.tiles_x * t.tiles_y * t.tiles_nb * t.n_tiles >= 4 * num_sms()) {
+    rc = launch_gemm_tc2(g, st, t.bw, t.bh, t.bn, t.tiles_x, t.tiles_y, t.tiles_nb, t.BN, p.uniform);
+    if (rc != DCB_EUNSUPPORTED) return rc;
   }
   const int epi_bytes = p.staged ? TC_EPI_BYTES : 0;
   int stages = (TC_SMEM_LIMIT - 1024 - TC_BAR_BYTES - epi_bytes) / stage_bytes;

@@ -1,0 +1,336 @@
+// gemm_tc2.cu -- tcgen05 implicit GEMM, 256 output pixels per CTA (two 128-row TMEM accumulators sharing every weight
+// block) with SPLIT activation / weight smem rings and an x-halo mode for stride-1 3x3 convolutions.
+//
+// Why: with 128x128 tiles the dominant N=128 full-resolution convs of the U-Nets are bound by L2->SMEM traffic
+// (16 KB A + 16 KB B per 64-deep K block per 128 pixels ~ 590 KB/tile -> ~850 TF/s measured), not by the tensor pipe.
+//   * 256 pixels per CTA: each weight block feeds two MMAs (two accumulators)           -> B traffic / 2
+//   * x-halo mode: one [130 px x 64 ch] activation box per (ky, channel block) serves the three kx taps; the tap
+//     shift is a 128-byte row offset of the UMMA descriptor start address                -> A traffic / 3
+//   => ~244 KB per 128 pixels instead of 590 KB; the kernel becomes MMA / SMEM-bandwidth bound.
+// Warp roles, barriers, TMEM double buffering and the staged epilogue are as in gemm_tc.cu (see tc_common.cuh).
+#include <cudaTypedefs.h>
+
+#include <mutex>
+
+#include "tc_common.cuh"
+
+namespace dcb {
+
+constexpr int T2_THREADS = 192;
+constexpr int T2_MAX_SLOTS = 8;
+constexpr int T2_HALO_SUB = 17 * 1024;  // 130 rows x 128 B = 16640 B, padded to the 1024-B swizzle repeat
+
+struct Tc2Params {
+  int nseg;
+  TcSeg seg[DCB_MAX_SEGS];
+  int halo;      // segments 0..8 are a stride-1 3x3 conv served by x-halo boxes (map 0); segments 9.. are plain taps
+  int nkb_conv;  // K blocks per tap of that conv (Cin / 64)
+  int tiles_x, tiles_y, tiles_nb, m_tiles, n_tiles, total_tiles;  // m_tiles counts 128-row sub-tiles; a CTA tile = 2
+  int bw, bh, bn, OW, OH, NB, BN;
+  int a_slots, b_slots, a_slot_bytes;
+  uint32_t idesc;
+  int uniform, base_off_mode;
+};
+
+struct SubTile {
+  int x0, y0, nb0;
+};
+__device__ __forceinline__ SubTile decode_sub(const Tc2Params& p, int tm_lin) {
+  SubTile s;
+  if (tm_lin >= p.m_tiles) {  // odd tail: a fully out-of-range box (zero filled), rows masked by the epilogue
+    s.x0 = 0; s.y0 = 0; s.nb0 = p.tiles_nb * p.bn;
+    return s;
+  }
+  const int tx = tm_lin % p.tiles_x;
+  tm_lin /= p.tiles_x;
+  s.x0 = tx * p.bw;
+  s.y0 = (tm_lin % p.tiles_y) * p.bh;
+  s.nb0 = (tm_lin / p.tiles_y) * p.bn;
+  return s;
+}
+
+__global__ void __launch_bounds__(T2_THREADS, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+                const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB,
+                const __grid_constant__ Tc2Params p, const __grid_constant__ EpiDev e) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int b_bytes = p.BN * TC_BK * 2;
+  uint8_t* a_ring = smem;
+  uint8_t* b_ring = a_ring + (size_t)p.a_slots * p.a_slot_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b_ring + (size_t)p.b_slots * b_bytes);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = bars + T2_MAX_SLOTS;
+  uint64_t* b_full = bars + 2 * T2_MAX_SLOTS;
+  uint64_t* b_empty = bars + 3 * T2_MAX_SLOTS;
+  uint64_t* tfull_bar = bars + 4 * T2_MAX_SLOTS;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint8_t* stg8 = reinterpret_cast<uint8_t*>(bars) + 512;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&mapA0);
+    prefetch_tmap(&mapB);
+    for (int i = 0; i < p.a_slots; ++i) { mbar_init(smem_u32(&a_full[i]), 1); mbar_init(smem_u32(&a_empty[i]), 1); }
+    for (int i = 0; i < p.b_slots; ++i) { mbar_init(smem_u32(&b_full[i]), 1); mbar_init(smem_u32(&b_empty[i]), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&tfull_bar[i]), 1); mbar_init(smem_u32(&tempty_bar[i]), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int first_tap_seg = p.halo ? 9 : 0;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int ai = 0, bi = 0;
+      uint32_t aph = 0, bph = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int tn = tile % p.n_tiles, tp = tile / p.n_tiles;
+        const SubTile s0 = decode_sub(p, 2 * tp), s1 = decode_sub(p, 2 * tp + 1);
+        auto load_b = [&](int kb_glob) {
+          mbar_wait(smem_u32(&b_empty[bi]), bph ^ 1);
+          const uint32_t fb = smem_u32(&b_full[bi]);
+          mbar_expect_tx(fb, (uint32_t)b_bytes);
+          tma_load_2d(smem_u32(b_ring + (size_t)bi * b_bytes), &mapB, fb, kb_glob * TC_BK, tn * p.BN);
+          if (++bi == p.b_slots) { bi = 0; bph ^= 1; }
+        };
+        if (p.halo) {
+          for (int ky = 0; ky < 3; ++ky)
+            for (int kb = 0; kb < p.nkb_conv; ++kb) {
+              mbar_wait(smem_u32(&a_empty[ai]), aph ^ 1);
+              const uint32_t fa = smem_u32(&a_full[ai]);
+              mbar_expect_tx(fa, 2u * 130u * 128u);
+              uint8_t* sa = a_ring + (size_t)ai * p.a_slot_bytes;
+              tma_load_5d(smem_u32(sa), &mapA0, fa, kb * TC_BK, s0.x0 - 1, 0, s0.y0 + ky - 1, s0.nb0);
+              tma_load_5d(smem_u32(sa + T2_HALO_SUB), &mapA0, fa, kb * TC_BK, s1.x0 - 1, 0, s1.y0 + ky - 1, s1.nb0);
+              if (++ai == p.a_slots) { ai = 0; aph ^= 1; }
+              for (int kx = 0; kx < 3; ++kx) load_b((ky * 3 + kx) * p.nkb_conv + kb);
+            }
+        }
+        int kb_glob = p.halo ? 9 * p.nkb_conv : 0;
+        for (int s = first_tap_seg; s < p.nseg; ++s) {
+          const TcSeg sg = p.seg[s];
+          const CUtensorMap* mp = sg.map == 0 ? &mapA0 : (sg.map == 1 ? &mapA1 : &mapA2);
+          for (int kb = 0; kb < sg.nkb; ++kb, ++kb_glob) {
+            mbar_wait(smem_u32(&a_empty[ai]), aph ^ 1);
+            const uint32_t fa = smem_u32(&a_full[ai]);
+            mbar_expect_tx(fa, 2u * TC_A_BYTES);
+            uint8_t* sa = a_ring + (size_t)ai * p.a_slot_bytes;
+            tma_load_5d(smem_u32(sa), mp, fa, sg.c0 + kb * TC_BK, s0.x0 + sg.dx, sg.p, s0.y0 + sg.dy, s0.nb0);
+            tma_load_5d(smem_u32(sa + TC_A_BYTES), mp, fa, sg.c0 + kb * TC_BK, s1.x0 + sg.dx, sg.p, s1.y0 + sg.dy, s1.nb0);
+            if (++ai == p.a_slots) { ai = 0; aph ^= 1; }
+            load_b(kb_glob);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    int ai = 0, bi = 0, as = 0;
+    uint32_t aph = 0, bph = 0, aphase = 0;
+    int halo_items = p.halo ? 3 * p.nkb_conv : 0;
+    int tap_items = 0;
+    for (int s = first_tap_seg; s < p.nseg; ++s) tap_items += p.seg[s].nkb;
+    const int items = halo_items + tap_items;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      mbar_wait(smem_u32(&tempty_bar[as]), aphase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(as * 256);
+      uint32_t accumulate = 0;
+      for (int item = 0; item < items; ++item) {
+        const bool is_halo = item < halo_items;
+        const int nb_blocks = is_halo ? 3 : 1;
+        mbar_wait(smem_u32(&a_full[ai]), aph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(a_ring + (size_t)ai * p.a_slot_bytes);
+        for (int j = 0; j < nb_blocks; ++j) {
+          mbar_wait(smem_u32(&b_full[bi]), bph);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(b_ring + (size_t)bi * b_bytes));
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+              // halo box: output pixel xl with tap kx=j reads smem row xl + j  ->  start the operand j rows (128 B) in
+              const uint32_t a_addr = is_halo ? sa + (uint32_t)(s * T2_HALO_SUB + j * 128) : sa + (uint32_t)(s * TC_A_BYTES);
+              const uint64_t adesc = is_halo ? make_kmajor_sw128_desc_off(a_addr, p.base_off_mode)
+                                             : make_kmajor_sw128_desc(a_addr);
+#pragma unroll
+              for (int k = 0; k < TC_BK / 16; ++k)
+                umma_f16(d_tmem + (uint32_t)(s * 128), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), p.idesc,
+                         accumulate | (uint32_t)k);
+            }
+            accumulate = 1;
+            umma_commit(smem_u32(&b_empty[bi]));
+            if (j == nb_blocks - 1) umma_commit(smem_u32(&a_empty[ai]));
+            if (item == items - 1 && j == nb_blocks - 1) umma_commit(smem_u32(&tfull_bar[as]));
+          }
+          __syncwarp();
+          if (++bi == p.b_slots) { bi = 0; bph ^= 1; }
+        }
+        if (++ai == p.a_slots) { ai = 0; aph ^= 1; }
+      }
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  } else {
+    // ===================== epilogue warps 2..5 =====================
+    const int q = warp & 3;
+    EpiGeom gq{p.tiles_x, p.tiles_y, p.bw, p.bh, p.bn, p.OW, p.OH, p.NB, p.uniform};
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x, it = 0; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int tn = tile % p.n_tiles, tp = tile / p.n_tiles;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 256);
+      staged_epilogue(gq, e, stg8, 0, 2 * tp, tn, p.BN, taddr, smem_u32(&tfull_bar[as]), aphase, true,
+                      smem_u32(&tempty_bar[as]), false);
+      staged_epilogue(gq, e, stg8, 1, 2 * tp + 1, tn, p.BN, taddr + 128u, smem_u32(&tfull_bar[as]), aphase, false,
+                      smem_u32(&tempty_bar[as]), true);
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// ---- host side ----------------------------------------------------------------------------------------------
+PFN_cuTensorMapEncodeTiled_v12000 tc_encode_fn();
+
+static int encode_map(CUtensorMap* map, const SegDev& s, int NBsrc, int bx, int by, int bnb) {
+  auto enc = tc_encode_fn();
+  DCB_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[5], strides[4];
+  const cuuint64_t es = 2, C = s.C, H = s.H, W = s.W;
+  if (s.stride == 1) {
+    dims[0] = C; dims[1] = W; dims[2] = 1; dims[3] = H; dims[4] = NBsrc;
+    strides[0] = C * es; strides[1] = W * C * es; strides[2] = W * C * es; strides[3] = H * W * C * es;
+  } else {
+    dims[0] = 2 * C; dims[1] = W / 2; dims[2] = 2; dims[3] = H / 2; dims[4] = NBsrc;
+    strides[0] = 2 * C * es; strides[1] = W * C * es; strides[2] = 2 * W * C * es; strides[3] = H * W * C * es;
+  }
+  cuuint32_t box[5] = {(cuuint32_t)TC_BK, (cuuint32_t)bx, 1, (cuuint32_t)by, (cuuint32_t)bnb};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(s.src), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DCB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(A/tc2) failed: %d", (int)r);
+  return DCB_OK;
+}
+
+// returns DCB_EUNSUPPORTED when the descriptor does not fit this kernel (the caller falls back to gemm_tc_kernel)
+int launch_gemm_tc2(const GemmDev& g, cudaStream_t st, int bw, int bh, int bn, int tiles_x, int tiles_y, int tiles_nb,
+                    int BN, int uniform) {
+  const EpiDev& e = g.epi;
+  Tc2Params p;
+  memset(&p, 0, sizeof(p));
+  p.bw = bw; p.bh = bh; p.bn = bn; p.tiles_x = tiles_x; p.tiles_y = tiles_y; p.tiles_nb = tiles_nb;
+  p.m_tiles = tiles_x * tiles_y * tiles_nb;
+  p.OW = g.OW; p.OH = g.OH; p.NB = g.NB; p.BN = BN;
+  p.n_tiles = (e.N + BN - 1) / BN;
+  p.total_tiles = ((p.m_tiles + 1) / 2) * p.n_tiles;
+  p.uniform = uniform;
+  // measured on B200: the UMMA 128B swizzle is a pure function of the absolute smem address, so an operand that
+  // starts j rows into a 1024-B-aligned swizzled box needs base_offset = 0 (setting it per the "(addr>>7)&7" rule breaks)
+  static const int base_off_env = getenv("DCB_TC2_BASE_OFFSET") ? atoi(getenv("DCB_TC2_BASE_OFFSET")) : 0;
+  p.base_off_mode = base_off_env;
+  p.nseg = g.nseg;
+
+  // x-halo mode: the first 9 segments are a stride-1 3x3 conv over one source in (ky,kx) order, full 128-px rows
+  bool halo = g.nseg >= 9 && bw == 128 && bh == 1 && bn == 1 && g.OW % 128 == 0 && !getenv("DCB_TC2_NO_HALO");
+  for (int i = 0; halo && i < 9; ++i) {
+    const SegDev& s = g.seg[i];
+    halo = s.src == g.seg[0].src && s.C == g.seg[0].C && s.H == g.OH && s.W == g.OW && s.stride == 1 && s.c_off == 0 &&
+           s.kc == s.C && s.dy == i / 3 - 1 && s.dx == i % 3 - 1;
+  }
+  for (int i = 9; halo && i < g.nseg; ++i) halo = g.seg[i].src != g.seg[0].src;
+  p.halo = halo;
+  p.nkb_conv = halo ? g.seg[0].kc / TC_BK : 0;
+
+  CUtensorMap maps[3];
+  memset(maps, 0, sizeof(maps));
+  SegDev map_key[3];
+  int nmaps = 0;
+  int rc;
+  if (halo) {
+    rc = encode_map(&maps[0], g.seg[0], g.NB, 130, 1, 1);
+    if (rc) return rc;
+    map_key[0] = g.seg[0];
+    map_key[0].src = nullptr;  // never matches a tap segment: the halo map has a different box
+    nmaps = 1;
+  }
+  for (int i = halo ? 9 : 0; i < g.nseg; ++i) {
+    const SegDev& s = g.seg[i];
+    int mi = -1;
+    for (int j = 0; j < nmaps; ++j)
+      if (map_key[j].src == s.src && map_key[j].C == s.C && map_key[j].H == s.H && map_key[j].W == s.W &&
+          map_key[j].stride == s.stride)
+        mi = j;
+    if (mi < 0) {
+      if (nmaps >= 3) return DCB_EUNSUPPORTED;
+      mi = nmaps++;
+      map_key[mi] = s;
+      rc = encode_map(&maps[mi], s, g.NB, bw, bh, bn);
+      if (rc) return rc;
+    }
+    TcSeg& ts = p.seg[i];
+    ts.map = mi;
+    ts.nkb = s.kc / TC_BK;
+    if (s.stride == 1) {
+      ts.c0 = s.c_off; ts.dx = s.dx; ts.p = 0; ts.dy = s.dy;
+    } else {
+      const int px = s.dx & 1, py = s.dy & 1;
+      ts.c0 = px * s.C + s.c_off;
+      ts.dx = (s.dx - px) / 2;
+      ts.p = py;
+      ts.dy = (s.dy - py) / 2;
+    }
+  }
+  for (int j = nmaps; j < 3; ++j) maps[j] = maps[0];
+
+  CUtensorMap mapB;
+  {
+    auto enc = tc_encode_fn();
+    cuuint64_t dims[2] = {(cuuint64_t)g.K, (cuuint64_t)e.N};
+    cuuint64_t strides[1] = {(cuuint64_t)g.K * 2};
+    cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)BN};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&mapB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(g.W), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    DCB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(W/tc2) failed: %d", (int)r);
+  }
+
+  const int b_bytes = BN * TC_BK * 2;
+  p.a_slot_bytes = halo ? 2 * T2_HALO_SUB : 2 * TC_A_BYTES;
+  p.a_slots = 3;
+  const int fixed = 1024 + 512 + TC_EPI_BYTES + p.a_slots * p.a_slot_bytes;
+  int b_slots = (TC_SMEM_LIMIT - fixed) / b_bytes;
+  if (b_slots > T2_MAX_SLOTS) b_slots = T2_MAX_SLOTS;
+  if (b_slots < 3) return DCB_EUNSUPPORTED;
+  p.b_slots = b_slots;
+  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+
+  const size_t smem = (size_t)fixed + (size_t)b_slots * b_bytes;
+  static std::once_flag attr_once;
+  std::call_once(attr_once, [] {
+    cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT);
+  });
+  const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+  gemm_tc2_kernel<<<grid, T2_THREADS, smem, st>>>(maps[0], maps[1], maps[2], mapB, p, e);
+  DCB_CHECK_LAUNCH("gemm_tc2");
+  return DCB_OK;
+}
+
+}  // namespace dcb

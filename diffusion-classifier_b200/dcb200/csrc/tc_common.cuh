@@ -1,0 +1,297 @@
+// tc_common.cuh -- PTX wrappers (mbarrier / TMA / tcgen05 / TMEM) and the staged epilogue shared by the tcgen05 GEMM
+// kernels (gemm_tc.cu: 128-row tiles; gemm_tc2.cu: 256-row tiles with split A/B rings and x-halo reuse).
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace dcb {
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 64;                      // 64 bf16 = 128 B = one swizzle-128B row
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;  // 16 KB
+constexpr int TC_SMEM_LIMIT = 227 * 1024;
+constexpr int TC_BAR_BYTES = 256;
+// staged epilogue: bf16 [128][128] tile + bias[256] + rowvec[128] + gate[128] + row ids [2][128] + residual rows [2][128]
+constexpr int TC_EPI_BYTES = 128 * 128 * 2 + 512 * 4 + 4 * 128 * 4;
+
+struct TcSeg {
+  int map;  // which A tensor map
+  int c0;   // channel coordinate (dim 0) of the first K block (includes the x-parity offset for stride 2)
+  int dx, p, dy;
+  int nkb;  // K blocks (of 64) in this segment
+};
+
+
+// ---- PTX wrappers ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// Bounded wait: a protocol bug becomes a trap (an error the host sees) instead of a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  uint64_t t0 = 0;
+  for (uint32_t spins = 0;; ++spins) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+    if ((spins & 0x3ff) == 0x3ff) {
+      uint64_t now = globaltimer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ull) {
+        printf("dcb gemm_tc: mbarrier wait timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x,
+               bar, parity);
+        __trap();
+      }
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 lanes x 16 consecutive fp32 columns: thread t of the warp receives lane (base_lane + t)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+// K-major, 128B-swizzled operand tile ([rows][64 bf16], 8-row atoms of 1024 B): SBO = 1024 B, LBO unused (=1),
+// descriptor version 1 (Blackwell), layout type 2 (SWIZZLE_128B).  cf. cute::UMMA::SmemDescriptor.
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// descriptor for an operand that starts at an arbitrary 128-byte row of a 1024-byte-aligned swizzled buffer (x-halo reuse):
+// base_offset (bits 49-51) = (start address >> 7) & 7 when the start is not aligned to the swizzle repeat
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc_off(uint32_t smem_addr, int base_off_mode) {
+  uint64_t d = make_kmajor_sw128_desc(smem_addr);
+  if (base_off_mode) d |= (uint64_t)((smem_addr >> 7) & 7) << 49;
+  return d;
+}
+
+// ---- staged epilogue of one 128-row accumulator sub-tile (bf16 outputs, <= 128 output columns per tile) --------
+//  0. per-row ids + tile-constant bias/rowvec/gate vectors -> smem
+//  1. cp.async prefetch of the whole residual tile (32 KB in flight per SM) into the swizzled staging tile
+//  2. thread-per-row: TMEM -> regs -> bias, rowvec, act, gate, +residual (smem), act_post -> bf16 in place
+//  3. coalesced copy-out: 16 threads cover one 256-byte output row
+// Called by the 4 epilogue warps (128 threads, named barrier 1).  stg8: TC_EPI_BYTES of smem.
+struct EpiGeom {
+  int tiles_x, tiles_y, bw, bh, bn, OW, OH, NB, uniform;
+};
+
+__device__ __forceinline__ void staged_epilogue(const EpiGeom& gq, const EpiDev& e, uint8_t* stg8, int parity, int tm_lin,
+                                                int tn, int BN, uint32_t taddr, uint32_t full_bar, uint32_t full_parity,
+                                                bool do_wait, uint32_t empty_bar, bool do_release) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = warp & 3;
+  const int r = q * 32 + lane;           // accumulator row (TMEM lane) owned in the thread-per-row pass
+  const int et = (threadIdx.x & 127);    // any bijection onto 0..127 works for the coalesced passes
+  const bool geglu = e.act == DCB_ACT_GEGLU;
+  int tm = tm_lin;
+  const int tx = tm % gq.tiles_x;
+  tm /= gq.tiles_x;
+  const int ty = tm % gq.tiles_y;
+  const int tb = tm / gq.tiles_y;
+  const int xl = r % gq.bw, yl = (r / gq.bw) % gq.bh, nl = r / (gq.bw * gq.bh);
+  const int x = tx * gq.bw + xl, y = ty * gq.bh + yl, nb = tb * gq.bn + nl;
+  const bool row_ok = x < gq.OW && y < gq.OH && nb < gq.NB;
+  const int m = nb * e.rows_per_sample + y * gq.OW + x;
+    float* s_bias = reinterpret_cast<float*>(stg8 + 128 * 256);  // [256]
+    float* s_rowvec = s_bias + 256;                              // [128]
+    float* s_gate = s_rowvec + 128;                              // [128]
+    int* s_m = reinterpret_cast<int*>(s_gate + 128) + parity * 128;
+    int* s_res = reinterpret_cast<int*>(s_gate + 128) + 256 + parity * 128;
+            const int wrow0 = tn * BN;
+    const int ncols_out = geglu ? 128 : BN;
+    const int ocol0 = geglu ? tn * 128 : tn * BN;
+    s_m[r] = row_ok ? m : -1;
+    if (e.residual) s_res[r] = row_ok ? (e.res_idx ? e.res_idx[m] : (e.res_mod > 0 ? m % e.res_mod : m)) : -1;
+    for (int c = et; c < BN; c += 128) s_bias[c] = (e.bias && wrow0 + c < e.N) ? e.bias[wrow0 + c] : 0.f;
+    if (gq.uniform && (e.rowvec || e.gate) && et < ncols_out) {
+      const int m0 = (tb * gq.bn) * e.rows_per_sample + (ty * gq.bh) * gq.OW + tx * gq.bw;
+      const int grp0 = m0 / e.rows_per_group;
+      const bool ok = ocol0 + et < e.n_out;
+      if (e.rowvec)
+        s_rowvec[et] = ok ? e.rowvec[(int64_t)(e.rowvec_idx ? e.rowvec_idx[grp0] : grp0) * e.rowvec_ld + ocol0 + et] : 0.f;
+      if (e.gate) s_gate[et] = ok ? e.gate[(int64_t)grp0 * e.gate_ld + ocol0 + et] : 0.f;
+    }
+    epi_bar();  // ids/constants visible; everybody has finished copying the previous tile out of the staging tile
+    const int cc = et & 15, rr0 = et >> 4;            // coalesced role: 16-byte chunk cc of rows rr0, rr0+8, ...
+    const bool cc_ok = cc * 8 < ncols_out && ocol0 + cc * 8 + 8 <= e.n_out;
+    if (e.residual && cc_ok) {
+      const __nv_bfloat16* rbase = (const __nv_bfloat16*)e.residual + ocol0 + cc * 8;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int row = rr0 + 8 * i;
+        const int rrow = s_res[row];
+        if (rrow >= 0)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(stg8 + row * 256 + ((cc ^ (row & 7)) << 4))),
+                       "l"(rbase + (int64_t)rrow * e.res_ld)
+                       : "memory");
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    if (do_wait) {
+      mbar_wait(full_bar, full_parity);
+      tc_fence_after();
+    }
+    if (e.residual) {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      epi_bar();
+    }
+    const int grp = (!gq.uniform && e.rows_per_group > 0 && row_ok) ? m / e.rows_per_group : 0;
+    // ---- thread-per-row pass ----
+    for (int c = 0; c < ncols_out; c += 16) {
+      uint32_t ra[16], rg[16];
+      tmem_ld16_nowait(taddr + (uint32_t)c, ra);
+      if (geglu) tmem_ld16_nowait(taddr + (uint32_t)(128 + c), rg);
+      tmem_ld_wait();
+      float v[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        float a = __uint_as_float(ra[i]) + s_bias[c + i];
+        if (geglu) a *= gelu_erf_f(__uint_as_float(rg[i]) + s_bias[128 + c + i]);
+        v[i] = a;
+      }
+      if (e.rowvec) {
+        if (gq.uniform) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] += s_rowvec[c + i];
+        } else if (row_ok) {
+          const float* rv = e.rowvec + (int64_t)(e.rowvec_idx ? e.rowvec_idx[grp] : grp) * e.rowvec_ld + ocol0 + c;
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (ocol0 + c + i < e.n_out) v[i] += rv[i];
+        }
+      }
+      if (e.act == DCB_ACT_SILU || e.act == DCB_ACT_GELU_TANH) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = apply_act(e.act, v[i]);
+      }
+      if (e.gate) {
+        if (gq.uniform) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] *= s_gate[c + i];
+        } else if (row_ok) {
+          const float* gt = e.gate + (int64_t)grp * e.gate_ld + ocol0 + c;
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (ocol0 + c + i < e.n_out) v[i] *= gt[i];
+        }
+      }
+      uint4* s0 = reinterpret_cast<uint4*>(stg8 + r * 256 + ((((c >> 3)) ^ (r & 7)) << 4));
+      uint4* s1 = reinterpret_cast<uint4*>(stg8 + r * 256 + ((((c >> 3) + 1) ^ (r & 7)) << 4));
+      if (e.residual && row_ok) {
+        float f[8];
+        unpack_bf16x8(*s0, f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] += f[i];
+        unpack_bf16x8(*s1, f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[8 + i] += f[i];
+      }
+      if (e.act_post != DCB_ACT_NONE) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = apply_act(e.act_post, v[i]);
+      }
+      *s0 = pack_bf16x8(v);
+      *s1 = pack_bf16x8(v + 8);
+    }
+    // accumulator fully drained: hand the TMEM stage back to the MMA warp
+    tc_fence_before();
+    __syncwarp();
+    if (do_release && lane == 0) mbar_arrive(empty_bar);
+    epi_bar();
+    // ---- coalesced copy-out ----
+    if (cc_ok) {
+      __nv_bfloat16* obase = (__nv_bfloat16*)e.out + ocol0 + cc * 8;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int row = rr0 + 8 * i;
+        const int mm = s_m[row];
+        if (mm >= 0)
+          *reinterpret_cast<uint4*>(obase + (int64_t)mm * e.out_ld) =
+              *reinterpret_cast<const uint4*>(stg8 + row * 256 + ((cc ^ (row & 7)) << 4));
+      }
+    }
+}
+
+}  // namespace dcb

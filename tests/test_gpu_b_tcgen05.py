@@ -161,3 +161,60 @@ def test_tc_persistent_many_tiles_deep_k(dev):
     a, wl = _bf(M, K, dev=dev), _bf(N, K, dev=dev, scale=0.1)
     out = E.linear(_ctx(dev), a, wl, N, out_dtype=torch.float32)
     assert rel_err(out, a.float() @ wl.float().t()) < 2e-5
+
+
+# ---- 256-pixel CTA kernel (gemm_tc2.cu): split A/B rings, two accumulators, x-halo reuse -------------------------
+@pytest.mark.parametrize("NB,H,W,Ci,Co,stride,res", [
+    (5, 128, 128, 64, 128, 1, False),    # x-halo mode, OW=128 (sub-tiles = two image rows)
+    (5, 64, 256, 128, 128, 1, True),     # x-halo mode, OW=256 (sub-tiles = two halves of a row) + residual prefetch
+    (5, 128, 128, 128, 64, 1, False),    # x-halo, BN=64
+    (20, 64, 64, 64, 128, 1, True),      # tap mode (bw=64, bh=2)
+    (10, 128, 128, 64, 128, 2, False),   # tap mode, stride 2
+    (37, 32, 32, 64, 128, 1, False),     # tap mode, odd number of 128-row sub-tiles (tail box fully out of range)
+])
+def test_tc2_conv3x3(dev, NB, H, W, Ci, Co, stride, res):
+    from dcb200 import _lib as L
+    from dcb200 import engine as E
+    torch.manual_seed(0)
+    x = _bf(NB, H, W, Ci, dev=dev)
+    w = (torch.randn(Co, Ci, 3, 3, device=dev) * 0.05).to(torch.bfloat16)
+    b = torch.randn(Co, device=dev)
+    wp = w.permute(0, 2, 3, 1).reshape(Co, -1).contiguous()
+    OH, OW = H // stride, W // stride
+    r = _bf(NB * OH * OW, Co, dev=dev) if res else None
+    ref = conv_ref(x.float(), w.float(), b, stride).reshape(-1, Co)
+    if res:
+        ref = ref + r.float()
+    kw = dict(bias=b, residual=r, res_ld=Co) if res else dict(bias=b)
+    out = E.gemm(_ctx(dev), E.conv3x3_segs(x, Ci, H, W, stride), wp, Co, NB, OH, OW, **kw)
+    assert out.dtype == torch.bfloat16 and rel_err(out, ref) < 5e-3
+    simt = E.gemm(_ctx(dev, L.ENGINE_SIMT), E.conv3x3_segs(x, Ci, H, W, stride), wp, Co, NB, OH, OW, **kw)
+    assert rel_err(out, simt.float()) < 1e-3      # same bf16 inputs, both round the fp32 result to bf16 once
+
+
+def test_tc2_halo_with_shortcut_segments_and_rowvec(dev):
+    """full-resolution up-block resnet tail: 3x3 conv (x-halo) + 1x1 shortcut over cat([h, skip]) as plain tap segments,
+    and conv1-style per-sample row vector, in the 256-pixel kernel."""
+    from dcb200 import engine as E
+    torch.manual_seed(0)
+    NB, H, W, C0, C1, Co = 5, 128, 128, 128, 64, 128
+    a2, x0, x1 = _bf(NB, H, W, Co, dev=dev), _bf(NB, H, W, C0, dev=dev), _bf(NB, H, W, C1, dev=dev)
+    w2 = (torch.randn(Co, Co, 3, 3, device=dev) * 0.05).to(torch.bfloat16)
+    ws = (torch.randn(Co, C0 + C1, 1, 1, device=dev) * 0.05).to(torch.bfloat16)
+    b, rv = torch.randn(Co, device=dev), torch.randn(NB, Co, device=dev)
+    wp = torch.cat([w2.permute(0, 2, 3, 1).reshape(Co, -1), ws.reshape(Co, -1)], 1).contiguous()
+    segs = E.conv3x3_segs(a2, Co, H, W) + [E.seg(x0, C0, H, W), E.seg(x1, C1, H, W)]
+    out = E.gemm(_ctx(dev), segs, wp, Co, NB, H, W, bias=b, rowvec=rv, rowvec_ld=Co, rows_per_group=H * W)
+    ref = conv_ref(a2.float(), w2.float(), b) + conv_ref(torch.cat([x0, x1], -1).float(), ws.float(), None, 1, 0)
+    ref = ref + rv[:, None, None, :]
+    assert rel_err(out.reshape(NB, H, W, Co), ref) < 5e-3
+
+
+def test_tc2_linear_odd_tiles(dev):
+    from dcb200 import engine as E
+    torch.manual_seed(0)
+    M, K, N = 128 * 601 + 77, 128, 128
+    x, w, b = _bf(M, K, dev=dev), _bf(N, K, dev=dev, scale=0.1), torch.randn(N, device=dev)
+    r = _bf(M, N, dev=dev)
+    out = E.linear(_ctx(dev), x, w, N, bias=b, residual=r, res_ld=N)
+    assert rel_err(out, x.float() @ w.float().t() + b + r.float()) < 5e-3
