@@ -30,6 +30,7 @@ struct Tc2Params {
   int a_slots, b_slots, a_slot_bytes;
   uint32_t idesc;
   int uniform, base_off_mode;
+  int dbg;  // experiments: 1 = no TMA traffic (barriers only), 2 = no epilogue work, 4 = no MMA issue
 };
 
 struct SubTile {
@@ -99,8 +100,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
         auto load_b = [&](int kb_glob) {
           mbar_wait(smem_u32(&b_empty[bi]), bph ^ 1);
           const uint32_t fb = smem_u32(&b_full[bi]);
-          mbar_expect_tx(fb, (uint32_t)b_bytes);
-          tma_load_2d(smem_u32(b_ring + (size_t)bi * b_bytes), &mapB, fb, kb_glob * TC_BK, tn * p.BN);
+          if (p.dbg & 1) mbar_arrive(fb);
+          else {
+            mbar_expect_tx(fb, (uint32_t)b_bytes);
+            tma_load_2d(smem_u32(b_ring + (size_t)bi * b_bytes), &mapB, fb, kb_glob * TC_BK, tn * p.BN);
+          }
           if (++bi == p.b_slots) { bi = 0; bph ^= 1; }
         };
         if (p.halo) {
@@ -108,10 +112,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
             for (int kb = 0; kb < p.nkb_conv; ++kb) {
               mbar_wait(smem_u32(&a_empty[ai]), aph ^ 1);
               const uint32_t fa = smem_u32(&a_full[ai]);
-              mbar_expect_tx(fa, 2u * 130u * 128u);
               uint8_t* sa = a_ring + (size_t)ai * p.a_slot_bytes;
-              tma_load_5d(smem_u32(sa), &mapA0, fa, kb * TC_BK, s0.x0 - 1, 0, s0.y0 + ky - 1, s0.nb0);
-              tma_load_5d(smem_u32(sa + T2_HALO_SUB), &mapA0, fa, kb * TC_BK, s1.x0 - 1, 0, s1.y0 + ky - 1, s1.nb0);
+              if (p.dbg & 1) mbar_arrive(fa);
+              else {
+                mbar_expect_tx(fa, 2u * 130u * 128u);
+                tma_load_5d(smem_u32(sa), &mapA0, fa, kb * TC_BK, s0.x0 - 1, 0, s0.y0 + ky - 1, s0.nb0);
+                tma_load_5d(smem_u32(sa + T2_HALO_SUB), &mapA0, fa, kb * TC_BK, s1.x0 - 1, 0, s1.y0 + ky - 1, s1.nb0);
+              }
               if (++ai == p.a_slots) { ai = 0; aph ^= 1; }
               for (int kx = 0; kx < 3; ++kx) load_b((ky * 3 + kx) * p.nkb_conv + kb);
             }
@@ -123,10 +130,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
           for (int kb = 0; kb < sg.nkb; ++kb, ++kb_glob) {
             mbar_wait(smem_u32(&a_empty[ai]), aph ^ 1);
             const uint32_t fa = smem_u32(&a_full[ai]);
-            mbar_expect_tx(fa, 2u * TC_A_BYTES);
             uint8_t* sa = a_ring + (size_t)ai * p.a_slot_bytes;
-            tma_load_5d(smem_u32(sa), mp, fa, sg.c0 + kb * TC_BK, s0.x0 + sg.dx, sg.p, s0.y0 + sg.dy, s0.nb0);
-            tma_load_5d(smem_u32(sa + TC_A_BYTES), mp, fa, sg.c0 + kb * TC_BK, s1.x0 + sg.dx, sg.p, s1.y0 + sg.dy, s1.nb0);
+            if (p.dbg & 1) mbar_arrive(fa);
+            else {
+              mbar_expect_tx(fa, 2u * TC_A_BYTES);
+              tma_load_5d(smem_u32(sa), mp, fa, sg.c0 + kb * TC_BK, s0.x0 + sg.dx, sg.p, s0.y0 + sg.dy, s0.nb0);
+              tma_load_5d(smem_u32(sa + TC_A_BYTES), mp, fa, sg.c0 + kb * TC_BK, s1.x0 + sg.dx, sg.p, s1.y0 + sg.dy, s1.nb0);
+            }
             if (++ai == p.a_slots) { ai = 0; aph ^= 1; }
             load_b(kb_glob);
           }
@@ -158,7 +168,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
           if (lane == 0) {
             const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(b_ring + (size_t)bi * b_bytes));
 #pragma unroll
-            for (int s = 0; s < 2; ++s) {
+            for (int s = 0; s < ((p.dbg & 4) ? 0 : 2); ++s) {
               // halo box: output pixel xl with tap kx=j reads smem row xl + j  ->  start the operand j rows (128 B) in
               const uint32_t a_addr = is_halo ? sa + (uint32_t)(s * T2_HALO_SUB + j * 128) : sa + (uint32_t)(s * TC_A_BYTES);
               const uint64_t adesc = is_halo ? make_kmajor_sw128_desc_off(a_addr, p.base_off_mode)
@@ -189,6 +199,15 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
     for (int tile = blockIdx.x, it = 0; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int tn = tile % p.n_tiles, tp = tile / p.n_tiles;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 256);
+      if (p.dbg & 2) {
+        mbar_wait(smem_u32(&tfull_bar[as]), aphase);
+        tc_fence_after();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[as]));
+        if (++as == 2) { as = 0; aphase ^= 1; }
+        continue;
+      }
       staged_epilogue(gq, e, stg8, 0, 2 * tp, tn, p.BN, taddr, smem_u32(&tfull_bar[as]), aphase, true,
                       smem_u32(&tempty_bar[as]), false);
       staged_epilogue(gq, e, stg8, 1, 2 * tp + 1, tn, p.BN, taddr + 128u, smem_u32(&tfull_bar[as]), aphase, false,
@@ -245,6 +264,7 @@ int launch_gemm_tc2(const GemmDev& g, cudaStream_t st, int bw, int bh, int bn, i
   // starts j rows into a 1024-B-aligned swizzled box needs base_offset = 0 (setting it per the "(addr>>7)&7" rule breaks)
   static const int base_off_env = getenv("DCB_TC2_BASE_OFFSET") ? atoi(getenv("DCB_TC2_BASE_OFFSET")) : 0;
   p.base_off_mode = base_off_env;
+  p.dbg = getenv("DCB_TC2_DBG") ? atoi(getenv("DCB_TC2_DBG")) : 0;
   p.nseg = g.nseg;
 
   // x-halo mode: the first 9 segments are a stride-1 3x3 conv over one source in (ky,kx) order, full 128-px rows

@@ -1,0 +1,39 @@
+"""micro-benchmark of single GEMM / conv launches through the C ABI (CUDA events, L2-cold inputs >> L2)."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "diffusion-classifier_b200"), os.path.join(ROOT, "tests")):
+    sys.path.insert(0, p)
+import torch
+from dcb200 import engine as E
+dev = torch.device("cuda:0")
+ctx = E.Ctx(device=dev, precision="bf16")
+
+def bench(fn, flops, n=10):
+    for _ in range(3): fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n): fn()
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    return ms, flops / ms / 1e9
+
+cases = sys.argv[1:] or ["conv128", "conv256to128", "lin128", "lin256", "lin64"]
+NB, H, W = 100, 128, 128
+for c in cases:
+    if c.startswith("conv"):
+        Ci, Co = {"conv128": (128, 128), "conv256to128": (256, 128), "conv128to256": (128, 256), "conv64": (64, 64)}[c]
+        x = torch.randn(NB, H, W, Ci, device=dev).to(torch.bfloat16)
+        w = (torch.randn(Co, 9 * Ci, device=dev) * 0.05).to(torch.bfloat16)
+        fn = lambda: E.gemm(ctx, E.conv3x3_segs(x, Ci, H, W), w, Co, NB, H, W)
+        fl = 2.0 * NB * H * W * Co * 9 * Ci
+    else:
+        N = int(c[3:])
+        K = 1152
+        M = NB * H * W
+        x = torch.randn(M, K, device=dev).to(torch.bfloat16)
+        w = (torch.randn(N, K, device=dev) * 0.05).to(torch.bfloat16)
+        fn = lambda: E.linear(ctx, x, w, N)
+        fl = 2.0 * M * N * K
+    ms, tf = bench(fn, fl)
+    print(f"{c:14s} env={os.environ.get('DCB_TC2_DBG','0')} notc2={os.environ.get('DCB_NO_TC2','')} nohalo={os.environ.get('DCB_TC2_NO_HALO','')}  {ms:7.3f} ms  {tf:7.1f} TF/s")
