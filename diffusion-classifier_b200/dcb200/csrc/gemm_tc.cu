@@ -131,7 +131,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   float* mse_smem = reinterpret_cast<float*>(tmem_slot + 2);  // [4]
   float* stg = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + TC_BAR_BYTES);  // staged epilogue region
 
-  const int warp = threadIdx.x >> 5;
+  // warp index through a shuffle: ptxas then knows every role branch below is warp-uniform and keeps loop state, smem
+  // addresses and descriptors in uniform registers.  (With a per-thread `lane == 0` region every UTCHMMA / UTMALDG is
+  // wrapped in an R2UR + BRA.U.ANY waterfall loop and the MMA thread cannot keep the pipe fed: 75 % -> 98 % of the pipe
+  // in profiles/r01_mma_issue_probes.txt.)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
@@ -157,59 +161,61 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int tn = tile % p.n_tiles;
-        int tm = tile / p.n_tiles;
-        const int tx = tm % p.tiles_x;
-        tm /= p.tiles_x;
-        const int ty = tm % p.tiles_y;
-        const int tb = tm / p.tiles_y;
-        const int x0 = tx * p.bw, y0 = ty * p.bh, nb0 = tb * p.bn;
-        int kb_glob = 0;
-        for (int s = 0; s < p.nseg; ++s) {
-          const TcSeg sg = p.seg[s];
-          const CUtensorMap* mp = sg.map == 0 ? &mapA0 : (sg.map == 1 ? &mapA1 : &mapA2);
-          for (int kb = 0; kb < sg.nkb; ++kb, ++kb_glob) {
-            mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
-            const uint32_t fb = smem_u32(&full_bar[stage]);
+    // ===================== TMA producer (warp-uniform bookkeeping, one elected lane issues) =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int tn = tile % p.n_tiles;
+      int tm = tile / p.n_tiles;
+      const int tx = tm % p.tiles_x;
+      tm /= p.tiles_x;
+      const int ty = tm % p.tiles_y;
+      const int tb = tm / p.tiles_y;
+      const int x0 = tx * p.bw, y0 = ty * p.bh, nb0 = tb * p.bn;
+      int kb_glob = 0;
+      for (int s = 0; s < p.nseg; ++s) {
+        const TcSeg sg = p.seg[s];
+        const CUtensorMap* mp = sg.map == 0 ? &mapA0 : (sg.map == 1 ? &mapA1 : &mapA2);
+        for (int kb = 0; kb < sg.nkb; ++kb, ++kb_glob) {
+          mbar_wait(empty0 + stage * 8, phase ^ 1);
+          if (elect_one()) {
+            const uint32_t fb = full0 + stage * 8;
             mbar_expect_tx(fb, (uint32_t)stage_bytes);
-            uint8_t* sa = smem + (size_t)stage * stage_bytes;
-            tma_load_5d(smem_u32(sa), mp, fb, sg.c0 + kb * TC_BK, x0 + sg.dx, sg.p, y0 + sg.dy, nb0);
-            tma_load_2d(smem_u32(sa + TC_A_BYTES), &mapB, fb, kb_glob * TC_BK, tn * p.BN);
-            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            const uint32_t sa = smem_base + (uint32_t)(stage * stage_bytes);
+            tma_load_5d(sa, mp, fb, sg.c0 + kb * TC_BK, x0 + sg.dx, sg.p, y0 + sg.dy, nb0);
+            tma_load_2d(sa + TC_A_BYTES, &mapB, fb, kb_glob * TC_BK, tn * p.BN);
           }
+          __syncwarp();
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+    // ===================== MMA issuer (warp-uniform bookkeeping, one elected lane issues) =====================
     int stage = 0;
     uint32_t phase = 0;
     int as = 0;
     uint32_t aphase = 0;
+    const uint32_t desc_hi = (uint32_t)(make_kmajor_sw128_desc(0) >> 32);
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       mbar_wait(smem_u32(&tempty_bar[as]), aphase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(as * 256);
       for (int kb = 0; kb < p.total_kb; ++kb) {
-        mbar_wait(smem_u32(&full_bar[stage]), phase);
+        mbar_wait(full0 + stage * 8, phase);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-          const uint64_t adesc = make_kmajor_sw128_desc(sa);
-          const uint64_t bdesc = make_kmajor_sw128_desc(sa + TC_A_BYTES);
+        // descriptor low words: (address >> 4); +2 advances 16 elements (32 B) along K inside the swizzle atom
+        const uint32_t alo = ((smem_base + (uint32_t)(stage * stage_bytes)) & 0x3FFFFu) >> 4 | (1u << 16);
+        const uint32_t blo = alo + (TC_A_BYTES >> 4);
+        if (elect_one()) {
+          umma_f16_lohi(d_tmem, alo, blo, desc_hi, p.idesc, (uint32_t)kb);
 #pragma unroll
-          for (int k = 0; k < TC_BK / 16; ++k) {
-            // advance 16 elements (32 B) along K inside the swizzle atom: +2 in the (addr >> 4) field
-            umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), p.idesc, (kb | k) != 0);
-          }
-          umma_commit(smem_u32(&empty_bar[stage]));                      // frees the smem stage when the MMAs retire
+          for (int k = 1; k < TC_BK / 16; ++k) umma_f16_lohi(d_tmem, alo + 2 * k, blo + 2 * k, desc_hi, p.idesc, 1u);
+          umma_commit(empty0 + stage * 8);                                  // frees the smem stage when the MMAs retire
           if (kb == p.total_kb - 1) umma_commit(smem_u32(&tfull_bar[as]));  // accumulator complete
         }
         __syncwarp();

@@ -69,7 +69,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   uint8_t* stg8 = reinterpret_cast<uint8_t*>(bars) + 512;
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp-uniform role dispatch (see gemm_tc.cu): loop state and descriptors stay in uniform registers
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&mapA0);
     prefetch_tmap(&mapB);
@@ -89,68 +90,81 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
   const uint32_t tmem_base = *tmem_slot;
   const int first_tap_seg = p.halo ? 9 : 0;
 
+  const uint32_t a_ring0 = smem_u32(a_ring), b_ring0 = smem_u32(b_ring);
+  const uint32_t a_full0 = smem_u32(a_full), a_empty0 = smem_u32(a_empty);
+  const uint32_t b_full0 = smem_u32(b_full), b_empty0 = smem_u32(b_empty);
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      int ai = 0, bi = 0;
-      uint32_t aph = 0, bph = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int tn = tile % p.n_tiles, tp = tile / p.n_tiles;
-        const SubTile s0 = decode_sub(p, 2 * tp), s1 = decode_sub(p, 2 * tp + 1);
-        auto load_b = [&](int kb_glob) {
-          mbar_wait(smem_u32(&b_empty[bi]), bph ^ 1);
-          const uint32_t fb = smem_u32(&b_full[bi]);
-          if (p.dbg & 1) mbar_arrive(fb);
+    // ===================== TMA producer (warp-uniform bookkeeping, one elected lane issues) =====================
+    int ai = 0, bi = 0;
+    uint32_t aph = 0, bph = 0;
+    const bool no_tma = (p.dbg & 1) != 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int tn = tile % p.n_tiles, tp = tile / p.n_tiles;
+      const SubTile s0 = decode_sub(p, 2 * tp), s1 = decode_sub(p, 2 * tp + 1);
+      auto load_b = [&](int kb_glob) {
+        mbar_wait(b_empty0 + bi * 8, bph ^ 1);
+        if (elect_one()) {
+          const uint32_t fb = b_full0 + bi * 8;
+          if (no_tma) mbar_arrive(fb);
           else {
             mbar_expect_tx(fb, (uint32_t)b_bytes);
-            tma_load_2d(smem_u32(b_ring + (size_t)bi * b_bytes), &mapB, fb, kb_glob * TC_BK, tn * p.BN);
+            tma_load_2d(b_ring0 + (uint32_t)(bi * b_bytes), &mapB, fb, kb_glob * TC_BK, tn * p.BN);
           }
-          if (++bi == p.b_slots) { bi = 0; bph ^= 1; }
-        };
-        if (p.halo) {
-          for (int ky = 0; ky < 3; ++ky)
-            for (int kb = 0; kb < p.nkb_conv; ++kb) {
-              mbar_wait(smem_u32(&a_empty[ai]), aph ^ 1);
-              const uint32_t fa = smem_u32(&a_full[ai]);
-              uint8_t* sa = a_ring + (size_t)ai * p.a_slot_bytes;
-              if (p.dbg & 1) mbar_arrive(fa);
+        }
+        __syncwarp();
+        if (++bi == p.b_slots) { bi = 0; bph ^= 1; }
+      };
+      if (p.halo) {
+        for (int ky = 0; ky < 3; ++ky)
+          for (int kb = 0; kb < p.nkb_conv; ++kb) {
+            mbar_wait(a_empty0 + ai * 8, aph ^ 1);
+            if (elect_one()) {
+              const uint32_t fa = a_full0 + ai * 8;
+              const uint32_t sa = a_ring0 + (uint32_t)(ai * p.a_slot_bytes);
+              if (no_tma) mbar_arrive(fa);
               else {
                 mbar_expect_tx(fa, 2u * 130u * 128u);
-                tma_load_5d(smem_u32(sa), &mapA0, fa, kb * TC_BK, s0.x0 - 1, 0, s0.y0 + ky - 1, s0.nb0);
-                tma_load_5d(smem_u32(sa + T2_HALO_SUB), &mapA0, fa, kb * TC_BK, s1.x0 - 1, 0, s1.y0 + ky - 1, s1.nb0);
+                tma_load_5d(sa, &mapA0, fa, kb * TC_BK, s0.x0 - 1, 0, s0.y0 + ky - 1, s0.nb0);
+                tma_load_5d(sa + T2_HALO_SUB, &mapA0, fa, kb * TC_BK, s1.x0 - 1, 0, s1.y0 + ky - 1, s1.nb0);
               }
-              if (++ai == p.a_slots) { ai = 0; aph ^= 1; }
-              for (int kx = 0; kx < 3; ++kx) load_b((ky * 3 + kx) * p.nkb_conv + kb);
             }
-        }
-        int kb_glob = p.halo ? 9 * p.nkb_conv : 0;
-        for (int s = first_tap_seg; s < p.nseg; ++s) {
-          const TcSeg sg = p.seg[s];
-          const CUtensorMap* mp = sg.map == 0 ? &mapA0 : (sg.map == 1 ? &mapA1 : &mapA2);
-          for (int kb = 0; kb < sg.nkb; ++kb, ++kb_glob) {
-            mbar_wait(smem_u32(&a_empty[ai]), aph ^ 1);
-            const uint32_t fa = smem_u32(&a_full[ai]);
-            uint8_t* sa = a_ring + (size_t)ai * p.a_slot_bytes;
-            if (p.dbg & 1) mbar_arrive(fa);
+            __syncwarp();
+            if (++ai == p.a_slots) { ai = 0; aph ^= 1; }
+            for (int kx = 0; kx < 3; ++kx) load_b((ky * 3 + kx) * p.nkb_conv + kb);
+          }
+      }
+      int kb_glob = p.halo ? 9 * p.nkb_conv : 0;
+      for (int s = first_tap_seg; s < p.nseg; ++s) {
+        const TcSeg sg = p.seg[s];
+        const CUtensorMap* mp = sg.map == 0 ? &mapA0 : (sg.map == 1 ? &mapA1 : &mapA2);
+        for (int kb = 0; kb < sg.nkb; ++kb, ++kb_glob) {
+          mbar_wait(a_empty0 + ai * 8, aph ^ 1);
+          if (elect_one()) {
+            const uint32_t fa = a_full0 + ai * 8;
+            const uint32_t sa = a_ring0 + (uint32_t)(ai * p.a_slot_bytes);
+            if (no_tma) mbar_arrive(fa);
             else {
               mbar_expect_tx(fa, 2u * TC_A_BYTES);
-              tma_load_5d(smem_u32(sa), mp, fa, sg.c0 + kb * TC_BK, s0.x0 + sg.dx, sg.p, s0.y0 + sg.dy, s0.nb0);
-              tma_load_5d(smem_u32(sa + TC_A_BYTES), mp, fa, sg.c0 + kb * TC_BK, s1.x0 + sg.dx, sg.p, s1.y0 + sg.dy, s1.nb0);
+              tma_load_5d(sa, mp, fa, sg.c0 + kb * TC_BK, s0.x0 + sg.dx, sg.p, s0.y0 + sg.dy, s0.nb0);
+              tma_load_5d(sa + TC_A_BYTES, mp, fa, sg.c0 + kb * TC_BK, s1.x0 + sg.dx, sg.p, s1.y0 + sg.dy, s1.nb0);
             }
-            if (++ai == p.a_slots) { ai = 0; aph ^= 1; }
-            load_b(kb_glob);
           }
+          __syncwarp();
+          if (++ai == p.a_slots) { ai = 0; aph ^= 1; }
+          load_b(kb_glob);
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+    // ===================== MMA issuer (warp-uniform bookkeeping, one elected lane issues) =====================
     int ai = 0, bi = 0, as = 0;
     uint32_t aph = 0, bph = 0, aphase = 0;
-    int halo_items = p.halo ? 3 * p.nkb_conv : 0;
+    const int halo_items = p.halo ? 3 * p.nkb_conv : 0;
     int tap_items = 0;
     for (int s = first_tap_seg; s < p.nseg; ++s) tap_items += p.seg[s].nkb;
     const int items = halo_items + tap_items;
+    const uint32_t desc_hi = (uint32_t)(make_kmajor_sw128_desc(0) >> 32);
+    const bool no_mma = (p.dbg & 4) != 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       mbar_wait(smem_u32(&tempty_bar[as]), aphase ^ 1);
       tc_fence_after();
@@ -159,31 +173,36 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
       for (int item = 0; item < items; ++item) {
         const bool is_halo = item < halo_items;
         const int nb_blocks = is_halo ? 3 : 1;
-        mbar_wait(smem_u32(&a_full[ai]), aph);
+        mbar_wait(a_full0 + ai * 8, aph);
         tc_fence_after();
-        const uint32_t sa = smem_u32(a_ring + (size_t)ai * p.a_slot_bytes);
+        const uint32_t sa = a_ring0 + (uint32_t)(ai * p.a_slot_bytes);
+        const uint32_t sub_stride = is_halo ? (uint32_t)T2_HALO_SUB : (uint32_t)TC_A_BYTES;
         for (int j = 0; j < nb_blocks; ++j) {
-          mbar_wait(smem_u32(&b_full[bi]), bph);
+          mbar_wait(b_full0 + bi * 8, bph);
           tc_fence_after();
-          if (lane == 0) {
-            const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(b_ring + (size_t)bi * b_bytes));
+          // halo box: output pixel xl with tap kx=j reads smem row xl + j  ->  start the operand j rows (128 B) in
+          const uint32_t a_addr0 = sa + (uint32_t)(j * 128);
+          const uint32_t alo0 = ((a_addr0 & 0x3FFFFu) >> 4) | (1u << 16);
+          const uint32_t alo1 = (((a_addr0 + sub_stride) & 0x3FFFFu) >> 4) | (1u << 16);
+          const uint32_t blo = (((b_ring0 + (uint32_t)(bi * b_bytes)) & 0x3FFFFu) >> 4) | (1u << 16);
+          // base_offset (descriptor bits 49-51) experiment knob; 0 is what the hardware wants here (see launch code)
+          const uint32_t ahi = desc_hi | ((is_halo && p.base_off_mode) ? (((a_addr0 >> 7) & 7u) << 17) : 0u);
+          if (elect_one()) {
+            if (!no_mma) {
+              // k outer / sub-tile inner: consecutive MMAs alternate between the two TMEM accumulators
 #pragma unroll
-            for (int s = 0; s < ((p.dbg & 4) ? 0 : 2); ++s) {
-              // halo box: output pixel xl with tap kx=j reads smem row xl + j  ->  start the operand j rows (128 B) in
-              const uint32_t a_addr = is_halo ? sa + (uint32_t)(s * T2_HALO_SUB + j * 128) : sa + (uint32_t)(s * TC_A_BYTES);
-              const uint64_t adesc = is_halo ? make_kmajor_sw128_desc_off(a_addr, p.base_off_mode)
-                                             : make_kmajor_sw128_desc(a_addr);
-#pragma unroll
-              for (int k = 0; k < TC_BK / 16; ++k)
-                umma_f16(d_tmem + (uint32_t)(s * 128), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), p.idesc,
-                         accumulate | (uint32_t)k);
+              for (int k = 0; k < TC_BK / 16; ++k) {
+                const uint32_t acc = k == 0 ? accumulate : 1u;
+                umma_f16_lohi2(d_tmem, alo0 + 2 * k, ahi, blo + 2 * k, desc_hi, p.idesc, acc);
+                umma_f16_lohi2(d_tmem + 128u, alo1 + 2 * k, ahi, blo + 2 * k, desc_hi, p.idesc, acc);
+              }
             }
-            accumulate = 1;
-            umma_commit(smem_u32(&b_empty[bi]));
-            if (j == nb_blocks - 1) umma_commit(smem_u32(&a_empty[ai]));
+            umma_commit(b_empty0 + bi * 8);
+            if (j == nb_blocks - 1) umma_commit(a_empty0 + ai * 8);
             if (item == items - 1 && j == nb_blocks - 1) umma_commit(smem_u32(&tfull_bar[as]));
           }
           __syncwarp();
+          accumulate = 1;
           if (++bi == p.b_slots) { bi = 0; bph ^= 1; }
         }
         if (++ai == p.a_slots) { ai = 0; aph ^= 1; }

@@ -35,5 +35,7 @@ for c in cases:
         w = (torch.randn(N, K, device=dev) * 0.05).to(torch.bfloat16)
         fn = lambda: E.linear(ctx, x, w, N)
         fl = 2.0 * M * N * K
-    ms, tf = bench(fn, fl)
-    print(f"{c:14s} env={os.environ.get('DCB_TC2_DBG','0')} notc2={os.environ.get('DCB_NO_TC2','')} nohalo={os.environ.get('DCB_TC2_NO_HALO','')}  {ms:7.3f} ms  {tf:7.1f} TF/s")
+    for dbg in os.environ.get("DBG_SWEEP", "0").split(","):
+      os.environ["DCB_TC2_DBG"] = dbg
+      ms, tf = bench(fn, fl)
+      print(f"{c:14s} env={os.environ.get('DCB_TC2_DBG','0')} notc2={os.environ.get('DCB_NO_TC2','')} nohalo={os.environ.get('DCB_TC2_NO_HALO','')}  {ms:7.3f} ms  {tf:7.1f} TF/s")

@@ -183,6 +183,295 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int N, int kblocks, int sl
   }
 }
 
+
+// ---- pipelined skeleton: producer warp (bulk copies of A+B bytes per stage, or bare arrives) -> full[] -> MMA warp -> commit
+// empty[] -> producer.  Reports cycles per K block (4 MMAs) as a function of ring depth: what a real mainloop can sustain.
+__global__ void __launch_bounds__(128, 1) pipe_kernel(int N, int kblocks, int stages, int do_copy, int do_mma, int src_blocks, int variant,
+                                                      const uint8_t* gsrc, Res* out) {
+  extern __shared__ __align__(1024) uint8_t raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+  const int stage_bytes = 16384 + N * 128;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + stages * stage_bytes);
+  uint64_t* empty = full + 8;
+  uint64_t* done = empty + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < stages * stage_bytes / 2; i += blockDim.x) {
+    uint32_t h = (uint32_t)i * 2654435761u + blockIdx.x * 40503u;
+    h ^= h >> 15;
+    reinterpret_cast<uint16_t*>(smem)[i] = (uint16_t)(0x3c00u | (h & 0x807fu));
+  }
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < stages; ++i) { mbar_init(smem_u32(&full[i]), 1); mbar_init(smem_u32(&empty[i]), 1); }
+    mbar_init(smem_u32(done), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  if (warp == 0 && lane == 0) {
+    int stage = 0; uint32_t phase = 0;
+    for (int kb = 0; kb < kblocks; ++kb) {
+      mbar_wait(smem_u32(&empty[stage]), phase ^ 1);
+      const uint32_t fb = smem_u32(&full[stage]);
+      if (do_copy) {
+        mbar_expect_tx(fb, stage_bytes);
+        const uint8_t* src = gsrc + (size_t)((blockIdx.x * 7 + kb) % src_blocks) * 49152;
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         smem_u32(smem + stage * stage_bytes)), "l"(src), "r"(stage_bytes), "r"(fb) : "memory");
+      } else {
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(fb) : "memory");
+      }
+      if (++stage == stages) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp == 1 && (!(variant & 4) || lane == 0)) {
+    long long c0 = clock64();
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    int stage = 0; uint32_t phase = 0;
+    for (int kb = 0; kb < kblocks; ++kb) {
+      mbar_wait(smem_u32(&full[stage]), phase);
+      if (!(variant & 2)) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (lane == 0) {
+        const uint32_t sa = smem_u32(smem + stage * stage_bytes);
+        const uint64_t ad = make_desc(sa), bd = make_desc(sa + 16384);
+        if (do_mma) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma<1>(tmem_base + (uint32_t)((kb >> 4) & 1) * 256, ad + 2 * k, bd + 2 * k, idesc, 1);
+        }
+        if (variant & 1) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty[stage])) : "memory");
+        else commit<1>(smem_u32(&empty[stage]));
+      }
+      if (!(variant & 4)) __syncwarp();
+      if (++stage == stages) { stage = 0; phase ^= 1; }
+    }
+    if (lane == 0) commit<1>(smem_u32(done));
+    mbar_wait(smem_u32(done), 0);
+    long long c1 = clock64();
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (lane == 0) { out[blockIdx.x].cycles = c1 - c0; out[blockIdx.x].ns = (long long)(t1 - t0); }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+static void run_pipe(int N, int stages, int do_copy, int do_mma, int src_blocks, const uint8_t* gsrc, Res* dres, int variant = 0) {
+  const int kblocks = 4096, grid = 148;
+  const int stage_bytes = 16384 + N * 128;
+  const size_t smem = (size_t)stages * stage_bytes + 512 + 1024;
+  if (smem > 227 * 1024) return;
+  cudaFuncSetAttribute(pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaMemset(dres, 0, sizeof(Res) * 148);
+  for (int rep = 0; rep < 2; ++rep) {
+    pipe_kernel<<<grid, 128, smem>>>(N, kblocks, stages, do_copy, do_mma, src_blocks, variant, gsrc, dres);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("pipe kernel failed: %s\n", cudaGetErrorString(e)); exit(1); }
+  }
+  Res h[148];
+  cudaMemcpy(h, dres, sizeof(Res) * 148, cudaMemcpyDeviceToHost);
+  long long cyc = 0, ns = 0;
+  for (int i = 0; i < grid; ++i) if (h[i].cycles > cyc) { cyc = h[i].cycles; ns = h[i].ns; }
+  const double flops = 4.0 * kblocks * 2.0 * 128 * N * 16 * grid;
+  printf("pipe v=%d N=%3d stages=%d copy=%d mma=%d src=%5.0f MB  cyc/kblock=%7.1f (mma floor %5.1f)  clk=%.3f GHz  chip %7.1f TF/s  load %6.2f TB/s\n",
+         variant, N, stages, do_copy, do_mma, src_blocks * 49152 / 1e6, (double)cyc / kblocks, 4 * 128.0 * N / 256.0, (double)cyc / ns,
+         do_mma ? flops / ns / 1e3 : 0.0, do_copy ? (double)stage_bytes * kblocks * grid / ns / 1e3 : 0.0);
+}
+
+// ---- what is additive with MMA issue in the issuing thread?  One thread per CTA loops over "K blocks" of 4 MMAs plus
+// optional extras.  bits: 1 = 4 MMAs, 2 = try_wait on an already-completed barrier phase, 4 = tcgen05.commit to a dummy
+// barrier (count huge), 8 = plain mbarrier.arrive on the dummy, 16 = tcgen05.fence::after_thread_sync, 32 = N=256 MMAs
+__global__ void __launch_bounds__(128, 1) issue_kernel(int kblocks, int mode, int period, Res* out) {
+  extern __shared__ __align__(1024) uint8_t raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+  const int N = (mode & 32) ? 256 : 128;
+  const int stage_bytes = 16384 + N * 128;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 4 * stage_bytes);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 4 * stage_bytes / 2; i += blockDim.x) {
+    uint32_t h = (uint32_t)i * 2654435761u + blockIdx.x * 40503u;
+    h ^= h >> 15;
+    reinterpret_cast<uint16_t*>(smem)[i] = (uint16_t)(0x3c00u | (h & 0x807fu));
+  }
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&bars[0]), 1);          // completed once below -> parity-0 waits always succeed
+    mbar_init(smem_u32(&bars[1]), 0xfffff);    // dummy sink for commits / arrives
+    mbar_init(smem_u32(&bars[2]), 1);          // final
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bars[0])) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  if (warp == 1 && lane == 0) {
+    long long c0 = clock64();
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    int stage = 0;
+    for (int kb = 0; kb < kblocks; ++kb) {
+      if (mode & 2) mbar_wait(smem_u32(&bars[0]), 0);
+      if (mode & 16) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (mode & 1) {
+        const uint32_t sa = smem_u32(smem + stage * stage_bytes);
+        const uint64_t ad = make_desc(sa), bd = make_desc(sa + 16384);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma<1>(tmem_base + (uint32_t)(((kb * 4 + k) / period) & 1) * 256, ad + 2 * k, bd + 2 * k, idesc, 1);
+      }
+      if (mode & 4) commit<1>(smem_u32(&bars[1]));
+      if (mode & 8) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bars[1])) : "memory");
+      if (++stage == 4) stage = 0;
+    }
+    commit<1>(smem_u32(&bars[2]));
+    mbar_wait(smem_u32(&bars[2]), 0);
+    long long c1 = clock64();
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    out[blockIdx.x].cycles = c1 - c0;
+    out[blockIdx.x].ns = (long long)(t1 - t0);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+static void run_issue(int mode, Res* dres, int period = 64) {
+  const int kblocks = 4096, grid = 148;
+  const size_t smem = 4 * (16384 + 256 * 128) + 512 + 1024;
+  cudaFuncSetAttribute(issue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  for (int rep = 0; rep < 2; ++rep) {
+    issue_kernel<<<grid, 128, smem>>>(kblocks, mode, period, dres);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("issue kernel failed: %s\n", cudaGetErrorString(e)); exit(1); }
+  }
+  Res h[148];
+  cudaMemcpy(h, dres, sizeof(Res) * 148, cudaMemcpyDeviceToHost);
+  long long cyc = 0;
+  for (int i = 0; i < grid; ++i) if (h[i].cycles > cyc) cyc = h[i].cycles;
+  printf("issue period=%2d mode=%2d [%s%s%s%s%s%s]  cyc/iter=%7.1f\n", period, mode, mode & 1 ? "4mma " : "", mode & 32 ? "N256 " : "", mode & 2 ? "try_wait " : "",
+         mode & 16 ? "fence " : "", mode & 4 ? "commit " : "", mode & 8 ? "arrive " : "", (double)cyc / kblocks);
+}
+
+// ---- lean mainloop: what a carefully written MMA-issue loop sustains.  Producer warp re-arms full[] when empty[] completes
+// (no data movement); the MMA thread does try_wait(full) -> NM MMAs (alternating NACC accumulators) -> commit(empty).
+// Descriptors are built from 32-bit low words (one IMAD per K block); no 64-bit arithmetic, no runtime mode flags.
+__device__ __forceinline__ void umma_lohi(uint32_t d, uint32_t alo, uint32_t blo, uint32_t hi, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .b64 da, db;\n\tmov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, 1;\n\t}" ::"r"(d), "r"(alo), "r"(blo), "r"(hi), "r"(idesc)
+      : "memory");
+}
+template <int N, int NM, int NACC, int LANES>
+__global__ void __launch_bounds__(128, 1) lean_kernel(int kblocks, int stages, Res* out) {
+  extern __shared__ __align__(1024) uint8_t raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+  constexpr int stage_bytes = (NM / 4) * 16384 + N * 128;   // NM/4 A sub-tiles + one B tile per stage
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + stages * stage_bytes);
+  uint64_t* empty = full + 8;
+  uint64_t* done = empty + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < stages * stage_bytes / 2; i += blockDim.x) {
+    uint32_t h = (uint32_t)i * 2654435761u + blockIdx.x * 40503u;
+    h ^= h >> 15;
+    reinterpret_cast<uint16_t*>(smem)[i] = (uint16_t)(0x3c00u | (h & 0x807fu));
+  }
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < stages; ++i) { mbar_init(smem_u32(&full[i]), 1); mbar_init(smem_u32(&empty[i]), 1); }
+    mbar_init(smem_u32(done), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+  constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  if (warp == 0 && lane == 0) {
+    int stage = 0; uint32_t phase = 0;
+    for (int kb = 0; kb < kblocks; ++kb) {
+      mbar_wait(smem_u32(&empty[stage]), phase ^ 1);
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full[stage])) : "memory");
+      if (++stage == stages) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp == 1 && lane < LANES) {
+    long long c0 = clock64();
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    const uint32_t hi = (uint32_t)(make_desc(0) >> 32);
+    const uint32_t lo0 = (uint32_t)make_desc(smem_u32(smem));
+    const uint32_t full0 = smem_u32(full), empty0 = smem_u32(empty);
+    int stage = 0; uint32_t phase = 0;
+    for (int kb = 0; kb < kblocks; ++kb) {
+      mbar_wait(full0 + stage * 8, phase);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (lane == 0) {
+        const uint32_t alo = lo0 + (uint32_t)stage * (stage_bytes >> 4);
+        const uint32_t blo = alo + (NM / 4) * (16384 >> 4);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+          for (int s = 0; s < NM / 4; ++s)
+            umma_lohi(tmem_base + (uint32_t)((s % NACC) * N), alo + s * (16384 >> 4) + 2 * k, blo + 2 * k, hi, idesc);
+        commit<1>(empty0 + stage * 8);
+      }
+      if (LANES > 1) __syncwarp();
+      if (++stage == stages) { stage = 0; phase ^= 1; }
+    }
+    if (lane == 0) commit<1>(smem_u32(done));
+    mbar_wait(smem_u32(done), 0);
+    long long c1 = clock64();
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (lane == 0) { out[blockIdx.x].cycles = c1 - c0; out[blockIdx.x].ns = (long long)(t1 - t0); }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+template <int N, int NM, int NACC, int LANES>
+static void run_lean(int stages, Res* dres) {
+  const int kblocks = 4096, grid = 148;
+  const int stage_bytes = (NM / 4) * 16384 + N * 128;
+  const size_t smem = (size_t)stages * stage_bytes + 512 + 1024;
+  cudaFuncSetAttribute(lean_kernel<N, NM, NACC, LANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  for (int rep = 0; rep < 2; ++rep) {
+    lean_kernel<N, NM, NACC, LANES><<<grid, 128, smem>>>(kblocks, stages, dres);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("lean kernel failed: %s\n", cudaGetErrorString(e)); exit(1); }
+  }
+  Res h[148];
+  cudaMemcpy(h, dres, sizeof(Res) * 148, cudaMemcpyDeviceToHost);
+  long long cyc = 0;
+  for (int i = 0; i < grid; ++i) if (h[i].cycles > cyc) cyc = h[i].cycles;
+  printf("lean N=%3d mma/kblock=%d accumulators=%d lanes=%2d stages=%d  cyc/kblock=%7.1f  (pipe floor %5.0f)  -> %4.1f%% of pipe\n", N, NM, NACC, LANES,
+         stages, (double)cyc / kblocks, NM * 128.0 * N / 256.0, 100.0 * NM * 128.0 * N / 256.0 / ((double)cyc / kblocks));
+}
+
 template <int CG>
 static void run(int N, int grid, int traffic, int bytes_per_copy, const uint8_t* gsrc, Res* dres) {
   const int slots = 4, kblocks = 4096;
@@ -223,23 +512,48 @@ static void run(int N, int grid, int traffic, int bytes_per_copy, const uint8_t*
          (4096.0 + (N / CG) * 32.0) / (cyc / mmas), (double)cp * bytes_per_copy / grid / cyc);
 }
 
-int main() {
+int main(int argc, char** argv) {
   uint8_t* gsrc;
   Res* dres;
-  cudaMalloc(&gsrc, 64 * 32768 + 32768);
-  cudaMemset(gsrc, 0x3c, 64 * 32768 + 32768);
+  const int max_blocks = 40000;  // 40000 x 48 KB = 1.97 GB  (>> L2)
+  cudaMalloc(&gsrc, (size_t)max_blocks * 49152 + 49152);
+  cudaMemset(gsrc, 0x3c, (size_t)max_blocks * 49152 + 49152);
   cudaMalloc(&dres, sizeof(Res) * 148);
-  const int Ns[3] = {64, 128, 256};
-  for (int grid : {2, 148})
-    for (int traffic : {0, 1})
-      for (int N : Ns) {
-        run<1>(N, grid, traffic, 32768, gsrc, dres);
-        run<2>(N, grid, traffic, 32768, gsrc, dres);
+  if (argc > 1 && argv[1][0] == 'r') {
+    const int Ns[3] = {64, 128, 256};
+    for (int grid : {2, 148})
+      for (int traffic : {0, 1})
+        for (int N : Ns) {
+          run<1>(N, grid, traffic, 32768, gsrc, dres);
+          run<2>(N, grid, traffic, 32768, gsrc, dres);
+        }
+  }
+  if (argc > 1 && argv[1][0] == 'p') {
+    for (int N : {128, 256})
+      for (int stages : {2, 3, 4, 5, 6}) {
+        run_pipe(N, stages, 0, 0, 1, gsrc, dres);       // skeleton only
+        run_pipe(N, stages, 0, 1, 1, gsrc, dres);       // + MMAs
+        run_pipe(N, stages, 1, 0, 1000, gsrc, dres);    // copies only, L2-resident source (49 MB)
+        run_pipe(N, stages, 1, 1, 1000, gsrc, dres);    // copies (L2) + MMAs
+        run_pipe(N, stages, 1, 1, max_blocks, gsrc, dres);  // copies (HBM) + MMAs
       }
-  // paced-ish traffic: smaller copies
-  for (int N : Ns) {
-    run<1>(N, 148, 1, 8192, gsrc, dres);
-    run<2>(N, 148, 1, 8192, gsrc, dres);
+  }
+  run_lean<128, 4, 1, 32>(4, dres);
+  run_lean<128, 4, 1, 1>(4, dres);
+  run_lean<128, 8, 2, 32>(3, dres);
+  run_lean<128, 8, 2, 1>(3, dres);
+  run_lean<128, 8, 1, 1>(3, dres);
+  run_lean<256, 4, 1, 32>(3, dres);
+  run_lean<256, 4, 1, 1>(3, dres);
+  run_lean<64, 8, 2, 1>(4, dres);
+  if (argc > 1 && argv[1][0] == 'i') for (int period : {1, 2, 4, 8, 16, 64}) for (int m : {1, 7, 33}) run_issue(m, dres, period);
+  if (argc > 1 && argv[1][0] == 'v')
+  // which part of the MMA warp's loop costs the ~288 cycles per K block?  variant bits: 1 = plain arrive instead of
+  // tcgen05.commit, 2 = no tcgen05.fence::after_thread_sync, 4 = single-thread loop (no warp-wide wait / __syncwarp)
+  for (int v = 0; v < 8; ++v) {
+    run_pipe(128, 4, 0, 0, 1, gsrc, dres, v);
+    run_pipe(128, 4, 0, 1, 1, gsrc, dres, v);
+    run_pipe(128, 4, 1, 1, 1000, gsrc, dres, v);
   }
   return 0;
 }
