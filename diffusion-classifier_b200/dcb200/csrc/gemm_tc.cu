@@ -26,7 +26,7 @@
 
 namespace dcb {
 
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;  // TMA warp, MMA warp, 2 epilogue groups x 4 warps (group g owns TMEM stage g)
 constexpr int TC_MAX_STAGES = 8;
 
 struct TcParams {
@@ -128,7 +128,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   uint64_t* tfull_bar = bars + 2 * TC_MAX_STAGES;     // [2]
   uint64_t* tempty_bar = bars + 2 * TC_MAX_STAGES + 2;  // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_MAX_STAGES + 4);
-  float* mse_smem = reinterpret_cast<float*>(tmem_slot + 2);  // [4]
+  float* mse_smem = reinterpret_cast<float*>(tmem_slot + 2);  // [2 groups][4]
   float* stg = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + TC_BAR_BYTES);  // staged epilogue region
 
   // warp index through a shuffle: ptxas then knows every role branch below is warp-uniform and keeps loop state, smem
@@ -224,13 +224,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
   } else {
-    // ===================== epilogue warps 2..5 =====================
+    // ===================== epilogue: two groups of 4 warps; group g drains the tiles that use TMEM stage g ==============
+    // (tile it of this CTA -> stage it & 1), so the epilogue of tile i overlaps the epilogue of tile i+1 and the mainloop
+    // of whichever tile owns the other stage
     const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int grp = (warp - 2) >> 2;
+    const int bar_id = 1 + grp;
     const int r = q * 32 + lane;  // accumulator row == pixel index inside the tile
     const bool geglu = e.act == DCB_ACT_GEGLU;
-    int as = 0;
+    uint8_t* my_stg = reinterpret_cast<uint8_t*>(stg) + grp * TC_EPI_BYTES;
+    float* my_mse = mse_smem + grp * 4;
+    const int as = grp;
     uint32_t aphase = 0;
-    for (int tile = blockIdx.x, it = 0; tile < p.total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = blockIdx.x + grp * gridDim.x, it = 0; tile < p.total_tiles; tile += 2 * gridDim.x, ++it, aphase ^= 1) {
       const int tn = tile % p.n_tiles;
       int tm = tile / p.n_tiles;
       const int tm_lin = tm;
@@ -247,9 +253,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 256);
       if (p.staged) {
         EpiGeom gq{p.tiles_x, p.tiles_y, p.bw, p.bh, p.bn, p.OW, p.OH, p.NB, p.uniform};
-        staged_epilogue(gq, e, reinterpret_cast<uint8_t*>(stg), it & 1, tm_lin, tn, p.BN, taddr,
-                        smem_u32(&tfull_bar[as]), aphase, true, smem_u32(&tempty_bar[as]), true);
-        if (++as == 2) { as = 0; aphase ^= 1; }
+        staged_epilogue(gq, e, my_stg, it & 1, tm_lin, tn, p.BN, taddr, smem_u32(&tfull_bar[as]), aphase, true,
+                        smem_u32(&tempty_bar[as]), true, bar_id);
         continue;
       }
       mbar_wait(smem_u32(&tfull_bar[as]), aphase);
@@ -294,13 +299,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[as]));
       if (e.mse_part) {
         mse_acc = warp_sum(mse_acc);
-        if (lane == 0) mse_smem[q] = mse_acc;
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (warp == 2 && lane == 0)
-          e.mse_part[(int64_t)tm_lin * p.n_tiles + tn] = (mse_smem[0] + mse_smem[1]) + (mse_smem[2] + mse_smem[3]);
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (lane == 0) my_mse[q] = mse_acc;
+        epi_bar(bar_id);
+        if (q == 0 && lane == 0)
+          e.mse_part[(int64_t)tm_lin * p.n_tiles + tn] = (my_mse[0] + my_mse[1]) + (my_mse[2] + my_mse[3]);
+        epi_bar(bar_id);
       }
-      if (++as == 2) { as = 0; aphase ^= 1; }
     }
   }
 
@@ -491,7 +495,7 @@ int launch_gemm_tc(const GemmDev& g, cudaStream_t st) {
     rc = launch_gemm_tc2(g, st, t.bw, t.bh, t.bn, t.tiles_x, t.tiles_y, t.tiles_nb, t.BN, p.uniform);
     if (rc != DCB_EUNSUPPORTED) return rc;
   }
-  const int epi_bytes = p.staged ? TC_EPI_BYTES : 0;
+  const int epi_bytes = p.staged ? 2 * TC_EPI_BYTES : 0;
   int stages = (TC_SMEM_LIMIT - 1024 - TC_BAR_BYTES - epi_bytes) / stage_bytes;
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
   if (stages > p.total_kb) stages = p.total_kb < 2 ? 2 : p.total_kb;

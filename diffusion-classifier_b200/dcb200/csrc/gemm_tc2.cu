@@ -16,7 +16,7 @@
 
 namespace dcb {
 
-constexpr int T2_THREADS = 192;
+constexpr int T2_THREADS = 320;  // TMA warp, MMA warp, 2 epilogue groups x 4 warps (group g drains sub-tile g)
 constexpr int T2_MAX_SLOTS = 8;
 constexpr int T2_HALO_SUB = 17 * 1024;  // 130 rows x 128 B = 16640 B, padded to the 1024-B swizzle repeat
 
@@ -76,7 +76,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
     prefetch_tmap(&mapB);
     for (int i = 0; i < p.a_slots; ++i) { mbar_init(smem_u32(&a_full[i]), 1); mbar_init(smem_u32(&a_empty[i]), 1); }
     for (int i = 0; i < p.b_slots; ++i) { mbar_init(smem_u32(&b_full[i]), 1); mbar_init(smem_u32(&b_empty[i]), 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&tfull_bar[i]), 1); mbar_init(smem_u32(&tempty_bar[i]), 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&tfull_bar[i]), 1); mbar_init(smem_u32(&tempty_bar[i]), 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -210,14 +210,16 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
   } else {
-    // ===================== epilogue warps 2..5 =====================
-    const int q = warp & 3;
+    // ===================== epilogue: warps 2..5 drain sub-tile 0, warps 6..9 sub-tile 1, concurrently =====================
+    const int q = warp & 3;             // TMEM lane quarter this warp may access
+    const int grp = (warp - 2) >> 2;    // epilogue group == sub-tile == accumulator half
+    uint8_t* my_stg = stg8 + grp * TC_EPI_BYTES;
     EpiGeom gq{p.tiles_x, p.tiles_y, p.bw, p.bh, p.bn, p.OW, p.OH, p.NB, p.uniform};
     int as = 0;
     uint32_t aphase = 0;
     for (int tile = blockIdx.x, it = 0; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int tn = tile % p.n_tiles, tp = tile / p.n_tiles;
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 256);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 256 + grp * 128);
       if (p.dbg & 2) {
         mbar_wait(smem_u32(&tfull_bar[as]), aphase);
         tc_fence_after();
@@ -227,10 +229,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
         if (++as == 2) { as = 0; aphase ^= 1; }
         continue;
       }
-      staged_epilogue(gq, e, stg8, 0, 2 * tp, tn, p.BN, taddr, smem_u32(&tfull_bar[as]), aphase, true,
-                      smem_u32(&tempty_bar[as]), false);
-      staged_epilogue(gq, e, stg8, 1, 2 * tp + 1, tn, p.BN, taddr + 128u, smem_u32(&tfull_bar[as]), aphase, false,
-                      smem_u32(&tempty_bar[as]), true);
+      staged_epilogue(gq, e, my_stg, it & 1, 2 * tp + grp, tn, p.BN, taddr, smem_u32(&tfull_bar[as]), aphase, true,
+                      smem_u32(&tempty_bar[as]), true, 1 + grp);
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
   }
@@ -353,8 +353,8 @@ int launch_gemm_tc2(const GemmDev& g, cudaStream_t st, int bw, int bh, int bn, i
 
   const int b_bytes = BN * TC_BK * 2;
   p.a_slot_bytes = halo ? 2 * T2_HALO_SUB : 2 * TC_A_BYTES;
-  p.a_slots = 3;
-  const int fixed = 1024 + 512 + TC_EPI_BYTES + p.a_slots * p.a_slot_bytes;
+  p.a_slots = 2;
+  const int fixed = 1024 + 512 + 2 * TC_EPI_BYTES + p.a_slots * p.a_slot_bytes;
   int b_slots = (TC_SMEM_LIMIT - fixed) / b_bytes;
   if (b_slots > T2_MAX_SLOTS) b_slots = T2_MAX_SLOTS;
   if (b_slots < 3) return DCB_EUNSUPPORTED;

@@ -138,7 +138,8 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* r) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+// named barrier of one epilogue group (4 warps); group g uses barrier id 1 + g
+__device__ __forceinline__ void epi_bar(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile(
@@ -174,14 +175,14 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc_off(uint32_t smem_add
 //  1. cp.async prefetch of the whole residual tile (32 KB in flight per SM) into the swizzled staging tile
 //  2. thread-per-row: TMEM -> regs -> bias, rowvec, act, gate, +residual (smem), act_post -> bf16 in place
 //  3. coalesced copy-out: 16 threads cover one 256-byte output row
-// Called by the 4 epilogue warps (128 threads, named barrier 1).  stg8: TC_EPI_BYTES of smem.
+// Called by the 4 warps of one epilogue group (128 threads, named barrier bar_id).  stg8: TC_EPI_BYTES of smem per group.
 struct EpiGeom {
   int tiles_x, tiles_y, bw, bh, bn, OW, OH, NB, uniform;
 };
 
 __device__ __forceinline__ void staged_epilogue(const EpiGeom& gq, const EpiDev& e, uint8_t* stg8, int parity, int tm_lin,
                                                 int tn, int BN, uint32_t taddr, uint32_t full_bar, uint32_t full_parity,
-                                                bool do_wait, uint32_t empty_bar, bool do_release) {
+                                                bool do_wait, uint32_t empty_bar, bool do_release, int bar_id = 1) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q = warp & 3;
   const int r = q * 32 + lane;           // accumulator row (TMEM lane) owned in the thread-per-row pass
@@ -215,7 +216,7 @@ __device__ __forceinline__ void staged_epilogue(const EpiGeom& gq, const EpiDev&
         s_rowvec[et] = ok ? e.rowvec[(int64_t)(e.rowvec_idx ? e.rowvec_idx[grp0] : grp0) * e.rowvec_ld + ocol0 + et] : 0.f;
       if (e.gate) s_gate[et] = ok ? e.gate[(int64_t)grp0 * e.gate_ld + ocol0 + et] : 0.f;
     }
-    epi_bar();  // ids/constants visible; everybody has finished copying the previous tile out of the staging tile
+    epi_bar(bar_id);  // ids/constants visible; everybody has finished copying the previous tile out of the staging tile
     const int cc = et & 15, rr0 = et >> 4;            // coalesced role: 16-byte chunk cc of rows rr0, rr0+8, ...
     const bool cc_ok = cc * 8 < ncols_out && ocol0 + cc * 8 + 8 <= e.n_out;
     if (e.residual && cc_ok) {
@@ -237,7 +238,7 @@ __device__ __forceinline__ void staged_epilogue(const EpiGeom& gq, const EpiDev&
     }
     if (e.residual) {
       asm volatile("cp.async.wait_group 0;" ::: "memory");
-      epi_bar();
+      epi_bar(bar_id);
     }
     const int grp = (!gq.uniform && e.rows_per_group > 0 && row_ok) ? m / e.rows_per_group : 0;
     // ---- thread-per-row pass ----
@@ -301,7 +302,7 @@ __device__ __forceinline__ void staged_epilogue(const EpiGeom& gq, const EpiDev&
     tc_fence_before();
     __syncwarp();
     if (do_release && lane == 0) mbar_arrive(empty_bar);
-    epi_bar();
+    epi_bar(bar_id);
     // ---- coalesced copy-out ----
     if (cc_ok) {
       __nv_bfloat16* obase = (__nv_bfloat16*)e.out + ocol0 + cc * 8;

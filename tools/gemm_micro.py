@@ -8,15 +8,31 @@ from dcb200 import engine as E
 dev = torch.device("cuda:0")
 ctx = E.Ctx(device=dev, precision="bf16")
 
-def bench(fn, flops, n=10):
+import threading, time
+import pynvml
+pynvml.nvmlInit()
+_h = pynvml.nvmlDeviceGetHandleByIndex(0)
+
+def bench(fn, flops, n=int(os.environ.get("MICRO_ITERS", "300"))):
+    """n back-to-back launches (>= 100 ms so the power governor settles); SM clock / power sampled meanwhile."""
     for _ in range(3): fn()
     torch.cuda.synchronize()
+    samples, stop = [], [False]
+    def pump():
+        while not stop[0]:
+            samples.append((pynvml.nvmlDeviceGetClockInfo(_h, pynvml.NVML_CLOCK_SM), pynvml.nvmlDeviceGetPowerUsage(_h) / 1e3))
+            time.sleep(0.005)
+    th = threading.Thread(target=pump, daemon=True); th.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(n): fn()
     e1.record(); torch.cuda.synchronize()
+    stop[0] = True; th.join()
     ms = e0.elapsed_time(e1) / n
-    return ms, flops / ms / 1e9
+    half = samples[len(samples) // 2:] or [(0, 0)]
+    clk = sorted(c for c, _ in half)[len(half) // 2]
+    pw = sorted(w for _, w in half)[len(half) // 2]
+    return ms, flops / ms / 1e9, clk, pw
 
 cases = sys.argv[1:] or ["conv128", "conv256to128", "lin128", "lin256", "lin64"]
 NB, H, W = 100, 128, 128
@@ -37,5 +53,5 @@ for c in cases:
         fl = 2.0 * M * N * K
     for dbg in os.environ.get("DBG_SWEEP", "0").split(","):
       os.environ["DCB_TC2_DBG"] = dbg
-      ms, tf = bench(fn, fl)
-      print(f"{c:14s} env={os.environ.get('DCB_TC2_DBG','0')} notc2={os.environ.get('DCB_NO_TC2','')} nohalo={os.environ.get('DCB_TC2_NO_HALO','')}  {ms:7.3f} ms  {tf:7.1f} TF/s")
+      ms, tf, clk, pw = bench(fn, fl)
+      print(f"{c:14s} env={os.environ.get('DCB_TC2_DBG','0')} notc2={os.environ.get('DCB_NO_TC2','')} nohalo={os.environ.get('DCB_TC2_NO_HALO','')}  {ms:7.3f} ms  {tf:7.1f} TF/s  sm {clk} MHz {pw:.0f} W")
