@@ -21,7 +21,7 @@ c_void_p, c_int, c_i32, c_i64, c_u64, c_float = C.c_void_p, C.c_int, C.c_int32, 
 
 class Seg(C.Structure):
     _fields_ = [("src", c_void_p), ("C", c_i32), ("H", c_i32), ("W", c_i32), ("c_off", c_i32), ("kc", c_i32),
-                ("dy", c_i32), ("dx", c_i32), ("stride", c_i32), ("_r0", c_i32), ("_r1", c_i32)]
+                ("dy", c_i32), ("dx", c_i32), ("stride", c_i32), ("nb_div", c_i32), ("_r1", c_i32)]
 
 
 class GemmDesc(C.Structure):
@@ -51,6 +51,11 @@ _PROTOS = {
                                     c_void_p]),
     "dcb_groupnorm_apply": (c_int, [c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
                                     c_void_p, c_void_p, c_float, c_int, c_void_p, c_void_p]),
+    "dcb_groupnorm_stats_div": (c_int, [c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                                        c_void_p, c_void_p]),
+    "dcb_groupnorm_apply_div": (c_int, [c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                                        c_void_p, c_void_p, c_void_p, c_float, c_int, c_void_p, c_void_p]),
+    "dcb_expand_samples": (c_int, [c_int, c_void_p, c_int, c_int, c_i64, c_void_p, c_void_p]),
     "dcb_layernorm": (c_int, [c_int, c_void_p, c_i64, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int,
                               c_int, c_void_p, c_void_p]),
     "dcb_attention": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float,

@@ -57,11 +57,12 @@ class _GraphedDenoiser:
     graphs instead of a tracing compiler -- the captured launches are exactly the eager ones.)"""
     _pool = None
 
-    def __init__(self, net, ctx, pk, is_dit, U, nk, Cimg, H, W, patch, v_param, fused):
+    def __init__(self, net, ctx, pk, is_dit, U, nk, Cimg, H, W, patch, v_param, fused, share):
         dev = ctx.device
         rows = (H // patch) * (W // patch)
         S = U * nk
-        self.a_in = ctx.empty(S * rows, pk.kpad_in)
+        self.share = share
+        self.a_in = ctx.empty((U if share else S) * rows, pk.kpad_in)
         self.target = torch.empty(U * H * W * Cimg, device=dev, dtype=torch.float32)
         self.logsnr = torch.empty(U, device=dev, dtype=torch.float32)
         self.cls = torch.empty(S, device=dev, dtype=torch.int32)
@@ -78,7 +79,8 @@ class _GraphedDenoiser:
         if is_dit:
             net.run(ctx, pk, self.a_in, self.logsnr, U, nk, self.cls, mse=mse)
         else:
-            net.run(ctx, pk, self.a_in, self.logsnr, U, nk, H, W, self.table, xattn_idx=self.cls, mse=mse)
+            net.run(ctx, pk, self.a_in, self.logsnr, U, nk, H, W, self.table, xattn_idx=self.cls, mse=mse,
+                    share_prefix=self.share)
 
     def launch(self):
         if self.graph is not None:
@@ -244,6 +246,9 @@ class DiffusionClassifier(nn.Module):
             else:
                 eps_stage = None
             nk = classes.shape[1]
+            # U-Net: layers ahead of the first cross-attention are class-independent -> computed once per unit
+            share = (not is_dit) and nk > 1 and getattr(cfg, "dcb_share_prefix", None) is not False \
+                and os.environ.get("DCB_SHARE_PREFIX", "1") != "0"
             n_units = nj * BS
             lo, hi = shard_range(n_units, rank, world)
             chunk = max(1, max_s // nk)
@@ -259,16 +264,16 @@ class DiffusionClassifier(nn.Module):
                            unit_id0=start * BS + u0, alpha=alpha[u0:u0 + U], sigma=sigma[u0:u0 + U], img=img,
                            want_target=True, v_param=v_param)
                 if use_graph:
-                    key = (id(net), id(pk), is_dit, U, nk, Cimg, H, W, v_param, fused, str(dev))
+                    key = (id(net), id(pk), is_dit, U, nk, Cimg, H, W, v_param, fused, share, str(dev))
                     gr = self._graphs.get(key)
                     if gr is None:
                         if len(self._graphs) >= 6:      # stale shapes / repacked weights: drop old graphs
                             self._graphs.clear()
                         gr = self._graphs[key] = _GraphedDenoiser(net, ctx, pk, is_dit, U, nk, Cimg, H, W, patch,
-                                                                  v_param, fused)
+                                                                  v_param, fused, share)
                     gr.table = table
-                    E.prologue(ctx, 1 if is_dit else 0, xin, U, nk, Cimg, H, W, pk.kpad_in, a_out=gr.a_in,
-                               target_out=gr.target, **pro)
+                    E.prologue(ctx, 1 if is_dit else 0, xin, U, 1 if share else nk, Cimg, H, W, pk.kpad_in,
+                               a_out=gr.a_in, target_out=gr.target, **pro)
                     gr.logsnr.copy_(logsnr[u0:u0 + U])
                     gr.cls.copy_(cls32)
                     if v_param:
@@ -276,14 +281,16 @@ class DiffusionClassifier(nn.Module):
                     gr.launch()
                     err = gr.err
                 else:
-                    a_in, target = E.prologue(ctx, 1 if is_dit else 0, xin, U, nk, Cimg, H, W, pk.kpad_in, **pro)
+                    a_in, target = E.prologue(ctx, 1 if is_dit else 0, xin, U, 1 if share else nk, Cimg, H, W,
+                                              pk.kpad_in, **pro)
                     err = torch.empty(U * nk, device=dev, dtype=torch.float32)
                     mse = dict(target=target, div=nk, ld=No, err=err, fused=fused,
                                scale=alpha[u0:u0 + U].repeat_interleave(nk).contiguous() if v_param else None)
                     if is_dit:
                         net.run(ctx, pk, a_in, logsnr[u0:u0 + U], U, nk, cls32, mse=mse)
                     else:
-                        net.run(ctx, pk, a_in, logsnr[u0:u0 + U], U, nk, H, W, table, xattn_idx=cls32, mse=mse)
+                        net.run(ctx, pk, a_in, logsnr[u0:u0 + U], U, nk, H, W, table, xattn_idx=cls32, mse=mse,
+                                share_prefix=share)
                 b_idx = img.long().repeat_interleave(nk)
                 j_idx = jrel.repeat_interleave(nk)
                 if slab is None:

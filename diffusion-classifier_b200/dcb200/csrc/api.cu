@@ -50,6 +50,7 @@ static int to_dev(const dcb_gemm_desc* d, GemmDev* g) {
     SegDev& o = g->seg[i];
     o.src = s.src; o.C = s.C; o.H = s.H; o.W = s.W; o.c_off = s.c_off; o.kc = s.kc; o.dy = s.dy; o.dx = s.dx;
     o.stride = s.stride;
+    o.nb_div = s.nb_div > 1 ? s.nb_div : 1;
     K += s.kc;
   }
   g->K = K;

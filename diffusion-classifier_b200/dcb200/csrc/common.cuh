@@ -102,6 +102,7 @@ __device__ __forceinline__ uint4 pack_bf16x8(const float* f) {
 struct SegDev {
   const void* src;
   int C, H, W, c_off, kc, dy, dx, stride;
+  int nb_div;  // >= 1: source sample = output sample / nb_div
 };
 
 struct EpiDev {

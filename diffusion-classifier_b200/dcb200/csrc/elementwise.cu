@@ -165,6 +165,15 @@ __global__ void upsample2x_kernel(const T* __restrict__ x, int NB, int H, int W,
   }
 }
 
+// out[n] = x[n / div]: 16-byte vectors, grid-stride
+__global__ void expand_samples_kernel(const uint4* __restrict__ x, int64_t vec_per_sample, int64_t total, int div,
+                                      uint4* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t n = i / vec_per_sample, r = i - n * vec_per_sample;
+    out[i] = x[(n / div) * vec_per_sample + r];
+  }
+}
+
 // Haar analysis of one 2x2 block: cA=(a+b+c+d)/2, cH=(a+b-c-d)/2, cV=(a-b+c-d)/2, cD=(a-b-c+d)/2
 __global__ void haar_dwt_kernel(const float* __restrict__ x, int B, int C, int H, int W, float post, float* __restrict__ out) {
   const int h = H / 2, w = W / 2;
@@ -319,6 +328,16 @@ extern "C" int dcb_upsample2x(int dtype, const void* x, int NB, int H, int W, in
   else
     upsample2x_kernel<float><<<grid_for(total), 256, 0, st>>>((const float*)x, NB, H, W, C, (float*)out);
   DCB_CHECK_LAUNCH("upsample2x");
+  return DCB_OK;
+}
+
+extern "C" int dcb_expand_samples(int dtype, const void* x, int NB, int div, int64_t elems_per_sample, void* out,
+                                  dcb_stream stream) {
+  const int64_t bytes = elems_per_sample * (dtype == DCB_BF16 ? 2 : 4);
+  DCB_REQUIRE(bytes % 16 == 0 && div >= 1 && NB >= 1, "expand_samples: sample size must be a multiple of 16 bytes");
+  const int64_t vps = bytes / 16, total = vps * NB;
+  expand_samples_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>((const uint4*)x, vps, total, div, (uint4*)out);
+  DCB_CHECK_LAUNCH("expand_samples");
   return DCB_OK;
 }
 

@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmDev g) {
     const SegDev& sg = g.seg[s];
     const int iy = ay * sg.stride + sg.dy, ix = ax * sg.stride + sg.dx;
     const bool a_ok = am_ok && iy >= 0 && iy < sg.H && ix >= 0 && ix < sg.W;
-    const T* ap = (const T*)sg.src + (((int64_t)an * sg.H + iy) * sg.W + ix) * sg.C + sg.c_off;
+    const T* ap = (const T*)sg.src + (((int64_t)(an / sg.nb_div) * sg.H + iy) * sg.W + ix) * sg.C + sg.c_off;
     for (int kk = 0; kk < sg.kc; kk += SM_BK, kglob += SM_BK) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {

@@ -37,6 +37,7 @@ struct TcParams {
   int OW, OH, NB;
   int BN, stages, total_kb;
   uint32_t idesc;
+  int conv9, nkb_conv;  // segments 0..8 are the taps of one 3x3 conv (any stride): issue them (ky, channel block, kx)
   int staged;   // epilogue through the swizzled smem staging tile + coalesced second pass
   int uniform;  // every row of an M tile belongs to one rowvec/gate group (tile-constant vectors live in smem)
 };
@@ -176,22 +177,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       const int ty = tm % p.tiles_y;
       const int tb = tm / p.tiles_y;
       const int x0 = tx * p.bw, y0 = ty * p.bh, nb0 = tb * p.bn;
-      int kb_glob = 0;
-      for (int s = 0; s < p.nseg; ++s) {
-        const TcSeg sg = p.seg[s];
+      auto issue = [&](const TcSeg& sg, int nbs, int kb, int kb_glob) {
         const CUtensorMap* mp = sg.map == 0 ? &mapA0 : (sg.map == 1 ? &mapA1 : &mapA2);
-        for (int kb = 0; kb < sg.nkb; ++kb, ++kb_glob) {
-          mbar_wait(empty0 + stage * 8, phase ^ 1);
-          if (elect_one()) {
-            const uint32_t fb = full0 + stage * 8;
-            mbar_expect_tx(fb, (uint32_t)stage_bytes);
-            const uint32_t sa = smem_base + (uint32_t)(stage * stage_bytes);
-            tma_load_5d(sa, mp, fb, sg.c0 + kb * TC_BK, x0 + sg.dx, sg.p, y0 + sg.dy, nb0);
-            tma_load_2d(sa + TC_A_BYTES, &mapB, fb, kb_glob * TC_BK, tn * p.BN);
-          }
-          __syncwarp();
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        mbar_wait(empty0 + stage * 8, phase ^ 1);
+        if (elect_one()) {
+          const uint32_t fb = full0 + stage * 8;
+          mbar_expect_tx(fb, (uint32_t)stage_bytes);
+          const uint32_t sa = smem_base + (uint32_t)(stage * stage_bytes);
+          tma_load_5d(sa, mp, fb, sg.c0 + kb * TC_BK, x0 + sg.dx, sg.p, y0 + sg.dy, nbs);
+          tma_load_2d(sa + TC_A_BYTES, &mapB, fb, kb_glob * TC_BK, tn * p.BN);
         }
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      };
+      int s_first = 0, kb_glob = 0;
+      if (p.conv9) {
+        // 3x3 taps in (ky, channel block, kx) order -- the accumulation order of gemm_tc2's x-halo mode, so a layer's
+        // result does not depend on which of the two kernels the tile count selects (bit-stable across batch sizes)
+        const int nbs = p.seg[0].div > 1 ? nb0 / p.seg[0].div : nb0;
+        for (int ky = 0; ky < 3; ++ky)
+          for (int kb = 0; kb < p.nkb_conv; ++kb)
+            for (int kx = 0; kx < 3; ++kx) issue(p.seg[ky * 3 + kx], nbs, kb, (ky * 3 + kx) * p.nkb_conv + kb);
+        s_first = 9;
+        kb_glob = 9 * p.nkb_conv;
+      }
+      for (int s = s_first; s < p.nseg; ++s) {
+        const TcSeg sg = p.seg[s];
+        const int nbs = sg.div > 1 ? nb0 / sg.div : nb0;
+        for (int kb = 0; kb < sg.nkb; ++kb, ++kb_glob) issue(sg, nbs, kb, kb_glob);
       }
     }
   } else if (warp == 1) {
@@ -330,6 +343,19 @@ PFN_cuTensorMapEncodeTiled_v12000 tc_encode_fn() {
   return fn;
 }
 
+// segments 0..8 = the (ky, kx)-ordered taps of one 3x3 convolution over a single source
+bool is_conv9(const GemmDev& g) {
+  if (g.nseg < 9) return false;
+  const SegDev& a = g.seg[0];
+  for (int i = 0; i < 9; ++i) {
+    const SegDev& s = g.seg[i];
+    if (s.src != a.src || s.C != a.C || s.H != a.H || s.W != a.W || s.stride != a.stride || s.c_off != a.c_off ||
+        s.kc != a.kc || s.nb_div != a.nb_div || s.dy != i / 3 - 1 || s.dx != i % 3 - 1)
+      return false;
+  }
+  return true;
+}
+
 struct TcGeom {
   int bw, bh, bn, tiles_x, tiles_y, tiles_nb, BN, n_tiles;
 };
@@ -431,17 +457,19 @@ int launch_gemm_tc(const GemmDev& g, cudaStream_t st) {
     int mi = -1;
     for (int j = 0; j < nmaps; ++j)
       if (map_key[j].src == s.src && map_key[j].C == s.C && map_key[j].H == s.H && map_key[j].W == s.W &&
-          map_key[j].stride == s.stride)
+          map_key[j].stride == s.stride && map_key[j].nb_div == s.nb_div)
         mi = j;
+    DCB_REQUIRE(s.nb_div == 1 || t.bn == 1, "segment %d: nb_div needs tiles that lie inside one sample (OH*OW >= 128)", i);
     if (mi < 0) {
       DCB_REQUIRE(nmaps < 3, "at most 3 distinct A sources per GEMM");
       mi = nmaps++;
       map_key[mi] = s;
-      rc = encode_a_map(&maps[mi], s, g.NB, t);
+      rc = encode_a_map(&maps[mi], s, (g.NB + s.nb_div - 1) / s.nb_div, t);
       if (rc) return rc;
     }
     TcSeg& ts = p.seg[i];
     ts.map = mi;
+    ts.div = s.nb_div;
     ts.nkb = s.kc / TC_BK;
     if (s.stride == 1) {
       ts.c0 = s.c_off; ts.dx = s.dx; ts.p = 0; ts.dy = s.dy;
@@ -456,6 +484,8 @@ int launch_gemm_tc(const GemmDev& g, cudaStream_t st) {
     p.total_kb += ts.nkb;
   }
   for (int j = nmaps; j < 3; ++j) maps[j] = maps[0];
+  p.conv9 = is_conv9(g);
+  p.nkb_conv = p.conv9 ? g.seg[0].kc / TC_BK : 0;
 
   CUtensorMap mapB;
   {

@@ -25,6 +25,8 @@ struct Tc2Params {
   TcSeg seg[DCB_MAX_SEGS];
   int halo;      // segments 0..8 are a stride-1 3x3 conv served by x-halo boxes (map 0); segments 9.. are plain taps
   int nkb_conv;  // K blocks per tap of that conv (Cin / 64)
+  int halo_div;  // nb_div of the halo source
+  int conv9;     // segments 0..8 are one 3x3 conv (halo or not): K blocks are issued in (ky, channel block, kx) order
   int tiles_x, tiles_y, tiles_nb, m_tiles, n_tiles, total_tiles;  // m_tiles counts 128-row sub-tiles; a CTA tile = 2
   int bw, bh, bn, OW, OH, NB, BN;
   int a_slots, b_slots, a_slot_bytes;
@@ -115,6 +117,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
         if (++bi == p.b_slots) { bi = 0; bph ^= 1; }
       };
       if (p.halo) {
+        const int h0 = p.halo_div > 1 ? s0.nb0 / p.halo_div : s0.nb0, h1 = p.halo_div > 1 ? s1.nb0 / p.halo_div : s1.nb0;
         for (int ky = 0; ky < 3; ++ky)
           for (int kb = 0; kb < p.nkb_conv; ++kb) {
             mbar_wait(a_empty0 + ai * 8, aph ^ 1);
@@ -124,8 +127,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
               if (no_tma) mbar_arrive(fa);
               else {
                 mbar_expect_tx(fa, 2u * 130u * 128u);
-                tma_load_5d(sa, &mapA0, fa, kb * TC_BK, s0.x0 - 1, 0, s0.y0 + ky - 1, s0.nb0);
-                tma_load_5d(sa + T2_HALO_SUB, &mapA0, fa, kb * TC_BK, s1.x0 - 1, 0, s1.y0 + ky - 1, s1.nb0);
+                tma_load_5d(sa, &mapA0, fa, kb * TC_BK, s0.x0 - 1, 0, s0.y0 + ky - 1, h0);
+                tma_load_5d(sa + T2_HALO_SUB, &mapA0, fa, kb * TC_BK, s1.x0 - 1, 0, s1.y0 + ky - 1, h1);
               }
             }
             __syncwarp();
@@ -133,26 +136,36 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
             for (int kx = 0; kx < 3; ++kx) load_b((ky * 3 + kx) * p.nkb_conv + kb);
           }
       }
-      int kb_glob = p.halo ? 9 * p.nkb_conv : 0;
-      for (int s = first_tap_seg; s < p.nseg; ++s) {
-        const TcSeg sg = p.seg[s];
+      auto issue_tap = [&](const TcSeg& sg, int kb, int kb_glob) {
         const CUtensorMap* mp = sg.map == 0 ? &mapA0 : (sg.map == 1 ? &mapA1 : &mapA2);
-        for (int kb = 0; kb < sg.nkb; ++kb, ++kb_glob) {
-          mbar_wait(a_empty0 + ai * 8, aph ^ 1);
-          if (elect_one()) {
-            const uint32_t fa = a_full0 + ai * 8;
-            const uint32_t sa = a_ring0 + (uint32_t)(ai * p.a_slot_bytes);
-            if (no_tma) mbar_arrive(fa);
-            else {
-              mbar_expect_tx(fa, 2u * TC_A_BYTES);
-              tma_load_5d(sa, mp, fa, sg.c0 + kb * TC_BK, s0.x0 + sg.dx, sg.p, s0.y0 + sg.dy, s0.nb0);
-              tma_load_5d(sa + TC_A_BYTES, mp, fa, sg.c0 + kb * TC_BK, s1.x0 + sg.dx, sg.p, s1.y0 + sg.dy, s1.nb0);
-            }
+        const int n0s = sg.div > 1 ? s0.nb0 / sg.div : s0.nb0, n1s = sg.div > 1 ? s1.nb0 / sg.div : s1.nb0;
+        mbar_wait(a_empty0 + ai * 8, aph ^ 1);
+        if (elect_one()) {
+          const uint32_t fa = a_full0 + ai * 8;
+          const uint32_t sa = a_ring0 + (uint32_t)(ai * p.a_slot_bytes);
+          if (no_tma) mbar_arrive(fa);
+          else {
+            mbar_expect_tx(fa, 2u * TC_A_BYTES);
+            tma_load_5d(sa, mp, fa, sg.c0 + kb * TC_BK, s0.x0 + sg.dx, sg.p, s0.y0 + sg.dy, n0s);
+            tma_load_5d(sa + TC_A_BYTES, mp, fa, sg.c0 + kb * TC_BK, s1.x0 + sg.dx, sg.p, s1.y0 + sg.dy, n1s);
           }
-          __syncwarp();
-          if (++ai == p.a_slots) { ai = 0; aph ^= 1; }
-          load_b(kb_glob);
         }
+        __syncwarp();
+        if (++ai == p.a_slots) { ai = 0; aph ^= 1; }
+        load_b(kb_glob);
+      };
+      int kb_glob = p.halo ? 9 * p.nkb_conv : 0;
+      int s_first = first_tap_seg;
+      if (!p.halo && p.conv9) {   // same (ky, channel block, kx) accumulation order as the halo mode and gemm_tc
+        for (int ky = 0; ky < 3; ++ky)
+          for (int kb = 0; kb < p.nkb_conv; ++kb)
+            for (int kx = 0; kx < 3; ++kx) issue_tap(p.seg[ky * 3 + kx], kb, (ky * 3 + kx) * p.nkb_conv + kb);
+        s_first = 9;
+        kb_glob = 9 * p.nkb_conv;
+      }
+      for (int s = s_first; s < p.nseg; ++s) {
+        const TcSeg sg = p.seg[s];
+        for (int kb = 0; kb < sg.nkb; ++kb, ++kb_glob) issue_tap(sg, kb, kb_glob);
       }
     }
   } else if (warp == 1) {
@@ -245,6 +258,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
 
 // ---- host side ----------------------------------------------------------------------------------------------
 PFN_cuTensorMapEncodeTiled_v12000 tc_encode_fn();
+bool is_conv9(const GemmDev& g);
 
 static int encode_map(CUtensorMap* map, const SegDev& s, int NBsrc, int bx, int by, int bnb) {
   auto enc = tc_encode_fn();
@@ -291,11 +305,13 @@ int launch_gemm_tc2(const GemmDev& g, cudaStream_t st, int bw, int bh, int bn, i
   for (int i = 0; halo && i < 9; ++i) {
     const SegDev& s = g.seg[i];
     halo = s.src == g.seg[0].src && s.C == g.seg[0].C && s.H == g.OH && s.W == g.OW && s.stride == 1 && s.c_off == 0 &&
-           s.kc == s.C && s.dy == i / 3 - 1 && s.dx == i % 3 - 1;
+           s.kc == s.C && s.dy == i / 3 - 1 && s.dx == i % 3 - 1 && s.nb_div == g.seg[0].nb_div;
   }
   for (int i = 9; halo && i < g.nseg; ++i) halo = g.seg[i].src != g.seg[0].src;
   p.halo = halo;
-  p.nkb_conv = halo ? g.seg[0].kc / TC_BK : 0;
+  p.conv9 = is_conv9(g);
+  p.nkb_conv = (halo || p.conv9) ? g.seg[0].kc / TC_BK : 0;
+  p.halo_div = halo ? g.seg[0].nb_div : 1;
 
   CUtensorMap maps[3];
   memset(maps, 0, sizeof(maps));
@@ -303,7 +319,7 @@ int launch_gemm_tc2(const GemmDev& g, cudaStream_t st, int bw, int bh, int bn, i
   int nmaps = 0;
   int rc;
   if (halo) {
-    rc = encode_map(&maps[0], g.seg[0], g.NB, 130, 1, 1);
+    rc = encode_map(&maps[0], g.seg[0], (g.NB + g.seg[0].nb_div - 1) / g.seg[0].nb_div, 130, 1, 1);
     if (rc) return rc;
     map_key[0] = g.seg[0];
     map_key[0].src = nullptr;  // never matches a tap segment: the halo map has a different box
@@ -314,17 +330,19 @@ int launch_gemm_tc2(const GemmDev& g, cudaStream_t st, int bw, int bh, int bn, i
     int mi = -1;
     for (int j = 0; j < nmaps; ++j)
       if (map_key[j].src == s.src && map_key[j].C == s.C && map_key[j].H == s.H && map_key[j].W == s.W &&
-          map_key[j].stride == s.stride)
+          map_key[j].stride == s.stride && map_key[j].nb_div == s.nb_div)
         mi = j;
+    if (s.nb_div > 1 && bn != 1) return DCB_EUNSUPPORTED;
     if (mi < 0) {
       if (nmaps >= 3) return DCB_EUNSUPPORTED;
       mi = nmaps++;
       map_key[mi] = s;
-      rc = encode_map(&maps[mi], s, g.NB, bw, bh, bn);
+      rc = encode_map(&maps[mi], s, (g.NB + s.nb_div - 1) / s.nb_div, bw, bh, bn);
       if (rc) return rc;
     }
     TcSeg& ts = p.seg[i];
     ts.map = mi;
+    ts.div = s.nb_div;
     ts.nkb = s.kc / TC_BK;
     if (s.stride == 1) {
       ts.c0 = s.c_off; ts.dx = s.dx; ts.p = 0; ts.dy = s.dy;

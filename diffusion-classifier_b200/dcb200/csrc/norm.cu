@@ -38,7 +38,8 @@ constexpr int GN_THREADS = 256;
 // ---- GroupNorm statistics: part[((n*chunks + chunk)*G + g)*2 + {sum,sumsq}] -------------------------------
 template <typename T>
 __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const T* __restrict__ x0, int C0, const T* __restrict__ x1,
-                                                              int C1, int HW, int G, int chunks, float* __restrict__ part) {
+                                                              int C1, int HW, int G, int chunks, float* __restrict__ part,
+                                                              int div0, int div1) {
   constexpr int VN = Vec<T>::N;
   __shared__ float s_acc[GN_THREADS][VN][2];
   const int n = blockIdx.y, chunk = blockIdx.x;
@@ -60,8 +61,8 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const T* __restric
       const int c = v * VN;
       const T* base;
       int cs, cc;
-      if (c < C0) { base = x0 + (int64_t)n * HW * C0; cs = C0; cc = c; }
-      else { base = x1 + (int64_t)n * HW * C1; cs = C1; cc = c - C0; }
+      if (c < C0) { base = x0 + (int64_t)(n / div0) * HW * C0; cs = C0; cc = c; }
+      else { base = x1 + (int64_t)(n / div1) * HW * C1; cs = C1; cc = c - C0; }
       // 8 raw 16-byte loads in flight per thread (Little: ~66 KB/SM must be outstanding to saturate HBM3e)
       const T* bp = base + cc;
       for (int p = p0 + prow; p < p1; p += 8 * nrows) {
@@ -118,7 +119,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const T* __restric
                                                               int C1, int HW, int G, int chunks,
                                                               const float* __restrict__ part, const float* __restrict__ gamma,
                                                               const float* __restrict__ beta, float eps, int silu,
-                                                              T* __restrict__ out, int pix_per_block) {
+                                                              T* __restrict__ out, int pix_per_block, int div0, int div1) {
   constexpr int VN = Vec<T>::N;
   __shared__ float s_mean[64], s_rstd[64];
   const int n = blockIdx.y;
@@ -153,8 +154,8 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const T* __restric
     }
     const T* base;
     int cs;
-    if (c < C0) { base = x0 + (int64_t)n * HW * C0 + c; cs = C0; }
-    else { base = x1 + (int64_t)n * HW * C1 + (c - C0); cs = C1; }
+    if (c < C0) { base = x0 + (int64_t)(n / div0) * HW * C0 + c; cs = C0; }
+    else { base = x1 + (int64_t)(n / div1) * HW * C1 + (c - C0); cs = C1; }
     T* obase = ob + c;
     for (int p = p0 + prow; p < p1; p += 4 * nrows) {
       float f[4][VN];
@@ -180,17 +181,18 @@ static int gn_threads(int V) { return V >= GN_THREADS ? GN_THREADS : (GN_THREADS
 
 template <typename T>
 static int gn_stats_t(const void* x0, int C0, const void* x1, int C1, int NB, int HW, int G, int chunks, float* part,
-                      cudaStream_t st) {
+                      cudaStream_t st, int div0, int div1) {
   const int V = (C0 + C1) / Vec<T>::N;
   dim3 grid(chunks, NB);
-  gn_stats_kernel<T><<<grid, gn_threads(V), 0, st>>>((const T*)x0, C0, (const T*)x1, C1, HW, G, chunks, part);
+  gn_stats_kernel<T><<<grid, gn_threads(V), 0, st>>>((const T*)x0, C0, (const T*)x1, C1, HW, G, chunks, part, div0, div1);
   DCB_CHECK_LAUNCH("gn_stats");
   return DCB_OK;
 }
 
 template <typename T>
 static int gn_apply_t(const void* x0, int C0, const void* x1, int C1, int NB, int HW, int G, int chunks, const float* part,
-                      const float* gamma, const float* beta, float eps, int silu, void* out, cudaStream_t st) {
+                      const float* gamma, const float* beta, float eps, int silu, void* out, cudaStream_t st, int div0,
+                      int div1) {
   const int V = (C0 + C1) / Vec<T>::N;
   const int threads = gn_threads(V);
   const int nrows = threads / (V < threads ? V : threads);
@@ -199,7 +201,7 @@ static int gn_apply_t(const void* x0, int C0, const void* x1, int C1, int NB, in
   if (ppb < nrows) ppb = nrows;
   dim3 grid((HW + ppb - 1) / ppb, NB);
   gn_apply_kernel<T><<<grid, threads, 0, st>>>((const T*)x0, C0, (const T*)x1, C1, HW, G, chunks, part, gamma, beta, eps,
-                                               silu, (T*)out, ppb);
+                                               silu, (T*)out, ppb, div0, div1);
   DCB_CHECK_LAUNCH("gn_apply");
   return DCB_OK;
 }
@@ -271,26 +273,42 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const T* __restrict__ x,
 
 using namespace dcb;
 
-extern "C" int dcb_groupnorm_stats(int dtype, const void* x0, int C0, const void* x1, int C1, int NB, int HW, int G,
-                                   int chunks, float* part, dcb_stream stream) {
+extern "C" int dcb_groupnorm_stats_div(int dtype, const void* x0, int C0, int div0, const void* x1, int C1, int div1,
+                                       int NB, int HW, int G, int chunks, float* part, dcb_stream stream) {
   int rc = gn_check(dtype, C0, C1, G, x1);
   if (rc) return rc;
   DCB_REQUIRE(chunks >= 1 && NB >= 1 && NB <= 65535, "groupnorm: bad chunks/NB");
+  if (div0 < 1) div0 = 1;
+  if (div1 < 1) div1 = 1;
   cudaStream_t st = (cudaStream_t)stream;
-  return dtype == DCB_BF16 ? gn_stats_t<__nv_bfloat16>(x0, C0, x1, C1, NB, HW, G, chunks, part, st)
-                           : gn_stats_t<float>(x0, C0, x1, C1, NB, HW, G, chunks, part, st);
+  return dtype == DCB_BF16 ? gn_stats_t<__nv_bfloat16>(x0, C0, x1, C1, NB, HW, G, chunks, part, st, div0, div1)
+                           : gn_stats_t<float>(x0, C0, x1, C1, NB, HW, G, chunks, part, st, div0, div1);
+}
+
+extern "C" int dcb_groupnorm_apply_div(int dtype, const void* x0, int C0, int div0, const void* x1, int C1, int div1,
+                                       int NB, int HW, int G, int chunks, const float* part, const float* gamma,
+                                       const float* beta, float eps, int silu, void* out, dcb_stream stream) {
+  int rc = gn_check(dtype, C0, C1, G, x1);
+  if (rc) return rc;
+  DCB_REQUIRE(chunks >= 1 && NB >= 1 && NB <= 65535, "groupnorm: bad chunks/NB");
+  if (div0 < 1) div0 = 1;
+  if (div1 < 1) div1 = 1;
+  cudaStream_t st = (cudaStream_t)stream;
+  return dtype == DCB_BF16 ? gn_apply_t<__nv_bfloat16>(x0, C0, x1, C1, NB, HW, G, chunks, part, gamma, beta, eps, silu,
+                                                       out, st, div0, div1)
+                           : gn_apply_t<float>(x0, C0, x1, C1, NB, HW, G, chunks, part, gamma, beta, eps, silu, out, st,
+                                               div0, div1);
+}
+
+extern "C" int dcb_groupnorm_stats(int dtype, const void* x0, int C0, const void* x1, int C1, int NB, int HW, int G,
+                                   int chunks, float* part, dcb_stream stream) {
+  return dcb_groupnorm_stats_div(dtype, x0, C0, 1, x1, C1, 1, NB, HW, G, chunks, part, stream);
 }
 
 extern "C" int dcb_groupnorm_apply(int dtype, const void* x0, int C0, const void* x1, int C1, int NB, int HW, int G,
                                    int chunks, const float* part, const float* gamma, const float* beta, float eps,
                                    int silu, void* out, dcb_stream stream) {
-  int rc = gn_check(dtype, C0, C1, G, x1);
-  if (rc) return rc;
-  DCB_REQUIRE(chunks >= 1 && NB >= 1 && NB <= 65535, "groupnorm: bad chunks/NB");
-  cudaStream_t st = (cudaStream_t)stream;
-  return dtype == DCB_BF16
-             ? gn_apply_t<__nv_bfloat16>(x0, C0, x1, C1, NB, HW, G, chunks, part, gamma, beta, eps, silu, out, st)
-             : gn_apply_t<float>(x0, C0, x1, C1, NB, HW, G, chunks, part, gamma, beta, eps, silu, out, st);
+  return dcb_groupnorm_apply_div(dtype, x0, C0, 1, x1, C1, 1, NB, HW, G, chunks, part, gamma, beta, eps, silu, out, stream);
 }
 
 extern "C" int dcb_layernorm(int dtype, const void* x, int64_t rows, int C, const float* gamma, const float* beta,

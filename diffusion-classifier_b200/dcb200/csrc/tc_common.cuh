@@ -20,6 +20,7 @@ struct TcSeg {
   int c0;   // channel coordinate (dim 0) of the first K block (includes the x-parity offset for stride 2)
   int dx, p, dy;
   int nkb;  // K blocks (of 64) in this segment
+  int div;  // source sample = output sample / div (shared class-independent prefix), >= 1
 };
 
 

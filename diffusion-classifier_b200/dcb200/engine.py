@@ -63,12 +63,13 @@ def _p(t):
     return None if t is None else t.data_ptr()
 
 
-def seg(src, C_, H, W, c_off=0, kc=None, dy=0, dx=0, stride=1):
-    return (src, C_, H, W, c_off, C_ - c_off if kc is None else kc, dy, dx, stride)
+def seg(src, C_, H, W, c_off=0, kc=None, dy=0, dx=0, stride=1, nb_div=1):
+    """nb_div > 1: ``src`` holds one tensor per (image, timestep) unit and output sample n reads unit n // nb_div."""
+    return (src, C_, H, W, c_off, C_ - c_off if kc is None else kc, dy, dx, stride, nb_div)
 
 
-def conv3x3_segs(src, C_, H, W, stride=1):
-    return [seg(src, C_, H, W, 0, C_, ky - 1, kx - 1, stride) for ky in range(3) for kx in range(3)]
+def conv3x3_segs(src, C_, H, W, stride=1, nb_div=1):
+    return [seg(src, C_, H, W, 0, C_, ky - 1, kx - 1, stride, nb_div) for ky in range(3) for kx in range(3)]
 
 
 def gemm(ctx: Ctx, segs, W, N, NB, OH, OW, *, bias=None, rowvec=None, rowvec_ld=0, rowvec_idx=None, rows_per_group=0,
@@ -84,9 +85,10 @@ def gemm(ctx: Ctx, segs, W, N, NB, OH, OW, *, bias=None, rowvec=None, rowvec_ld=
     d.NB, d.OH, d.OW, d.N = NB, OH, OW, N
     d.nseg = len(segs)
     keep = []
-    for i, (src, C_, H, W_, c_off, kc, dy, dx, stride) in enumerate(segs):
+    for i, (src, C_, H, W_, c_off, kc, dy, dx, stride, nb_div) in enumerate(segs):
         s = d.seg[i]
         s.src, s.C, s.H, s.W, s.c_off, s.kc, s.dy, s.dx, s.stride = src.data_ptr(), C_, H, W_, c_off, kc, dy, dx, stride
+        s.nb_div = nb_div
         keep.append(src)
     M = NB * OH * OW
     n_out = N // 2 if act == L.ACT_GEGLU else N
@@ -140,16 +142,26 @@ def gn_chunks(NB, HW, Ctot):
     return max(1, min((HW * Ctot) // 131072, 64, HW))
 
 
-def groupnorm(ctx, x0, C0, x1, C1, NB, HW, gamma, beta, eps, silu, G=32):
+def groupnorm(ctx, x0, C0, x1, C1, NB, HW, gamma, beta, eps, silu, G=32, div0=1, div1=1):
+    """GroupNorm(+SiLU) over cat([x0, x1], channel) for NB samples; sample n reads x0[n // div0], x1[n // div1]."""
     lib = L.lib()
     chunks = gn_chunks(NB, HW, C0 + C1)
     part = torch.empty(NB * chunks * G * 2, device=ctx.device, dtype=torch.float32)
     out = ctx.empty(NB * HW, C0 + C1)
-    L.check(lib.dcb_groupnorm_stats(ctx.code, x0.data_ptr(), C0, _p(x1), C1, NB, HW, G, chunks, part.data_ptr(),
-                                    ctx.stream()), "groupnorm_stats")
-    L.check(lib.dcb_groupnorm_apply(ctx.code, x0.data_ptr(), C0, _p(x1), C1, NB, HW, G, chunks, part.data_ptr(),
-                                    gamma.data_ptr(), beta.data_ptr(), eps, int(silu), out.data_ptr(), ctx.stream()),
-            "groupnorm_apply")
+    L.check(lib.dcb_groupnorm_stats_div(ctx.code, x0.data_ptr(), C0, div0, _p(x1), C1, div1, NB, HW, G, chunks,
+                                        part.data_ptr(), ctx.stream()), "groupnorm_stats")
+    L.check(lib.dcb_groupnorm_apply_div(ctx.code, x0.data_ptr(), C0, div0, _p(x1), C1, div1, NB, HW, G, chunks,
+                                        part.data_ptr(), gamma.data_ptr(), beta.data_ptr(), eps, int(silu),
+                                        out.data_ptr(), ctx.stream()), "groupnorm_apply")
+    return out
+
+
+def expand_samples(ctx, x, NB, div, rows_per_sample):
+    """materialised class expansion [NB/div * rows, C] -> [NB * rows, C] (small low-resolution tensors only)."""
+    C_ = x.shape[1]
+    out = torch.empty(NB * rows_per_sample, C_, device=ctx.device, dtype=x.dtype)
+    L.check(L.lib().dcb_expand_samples(L.F32 if x.dtype == torch.float32 else L.BF16, x.data_ptr(), NB, div,
+                                       rows_per_sample * C_, out.data_ptr(), ctx.stream()), "expand_samples")
     return out
 
 

@@ -95,6 +95,14 @@ class _TimeEmb(_P):
         self.linear_2 = nn.Linear(tdim, tdim)
 
 
+class _Act:
+    """activation handle: tensor [nb*HW, C], channel count, sample divisor (1 = per sample, rep = per unit)."""
+    __slots__ = ("t", "C", "div")
+
+    def __init__(self, t, C, div):
+        self.t, self.C, self.div = t, C, div
+
+
 def _tup(v, n):
     return tuple(v) if isinstance(v, (tuple, list)) else (v,) * n
 
@@ -226,6 +234,7 @@ class UNetCondition2D(nn.Module):
         self.conv_norm_out = nn.GroupNorm(G, boc[0], eps=norm_eps)
         self.conv_out = nn.Conv2d(boc[0], out_channels, 3, padding=1)
         self._packs = {}
+        self._row_idx = {}
         self.precision = "bf16"  # "fp32" selects the CUDA-core verify engine (north star: 1e-4 mode)
 
     # ---- weight packing (layout plumbing, once per parameter version) --------------------------------------
@@ -333,36 +342,75 @@ class UNetCondition2D(nn.Module):
         return pk
 
     # ---- the denoiser program -------------------------------------------------------------------------------
-    def _resnet(self, ctx, q, temb, x0, C0, x1, C1, S, H, W):
+    # Activations travel as _Act(t, C, div): ``t`` is [nb*HW, C]; div == 1 -> one tensor per sample (nb = S = U*rep),
+    # div == rep > 1 -> one tensor per (image, timestep) UNIT (nb = U), shared by the unit's rep class-conditional
+    # samples.  Every layer whose inputs are per-unit and that does not see the class (everything up to the first
+    # attn1 out-projection, where the collapsed cross-attention vector enters) is computed once per unit; the reference
+    # recomputes it for every candidate class (diffusion_classifier.py:694-704 loops classes around the full forward).
+    # The arithmetic per sample is unchanged, so results are identical to the unshared program.
+    def _unit_rows(self, ctx, S, HW, rep):
+        """int32 [S*HW]: row of the per-unit tensor that sample-major row m reads (persistent: CUDA graphs hold it)."""
+        key = (S, HW, rep, str(ctx.device))
+        idx = self._row_idx.get(key)
+        if idx is None:
+            m = torch.arange(S * HW, device=ctx.device, dtype=torch.int64)
+            idx = ((m // (HW * rep)) * HW + m % HW).to(torch.int32).contiguous()
+            self._row_idx[key] = idx
+        return idx
+
+    def _resnet(self, ctx, q, temb, x0, x1, U, rep, H, W):
         HW = H * W
-        a1 = E.groupnorm(ctx, x0, C0, x1, C1, S, HW, q.g1, q.b1n, q.eps, True)
-        h1 = E.gemm(ctx, E.conv3x3_segs(a1, q.cin, H, W), q.w1, q.cout, S, H, W, bias=q.b1,
-                    rowvec=temb[:, q.temb_off:], rowvec_ld=temb.shape[1], rows_per_group=HW)
-        a2 = E.groupnorm(ctx, h1, q.cout, None, 0, S, HW, q.g2, q.b2n, q.eps, True)
+        S = U * rep
+        unit = x0.div > 1 and (x1 is None or x1.div > 1)
+        NB = U if unit else S
+        d0 = 1 if unit else x0.div
+        assert d0 == 1, "the running activation is per-sample once any class-dependent layer has run"
+        d1 = 1 if (unit or x1 is None) else x1.div
+        if d1 > 1 and HW < 128:      # a GEMM tile would span samples: materialise the (tiny) expanded skip
+            x1 = _Act(E.expand_samples(ctx, x1.t, S, d1, HW), x1.C, 1)
+            d1 = 1
+        t1, C0 = (x1.t if x1 is not None else None), x0.C
+        C1 = x1.C if x1 is not None else 0
+        tld = temb.shape[1] * (rep if unit else 1)   # per-unit layers read the unit's first sample row of temb
+        a1 = E.groupnorm(ctx, x0.t, C0, t1, C1, NB, HW, q.g1, q.b1n, q.eps, True, div1=d1)
+        h1 = E.gemm(ctx, E.conv3x3_segs(a1, q.cin, H, W), q.w1, q.cout, NB, H, W, bias=q.b1,
+                    rowvec=temb[:, q.temb_off:], rowvec_ld=tld, rows_per_group=HW)
+        a2 = E.groupnorm(ctx, h1, q.cout, None, 0, NB, HW, q.g2, q.b2n, q.eps, True)
         segs = E.conv3x3_segs(a2, q.cout, H, W)
         if q.shortcut:
-            segs.append(E.seg(x0, C0, H, W))
+            segs.append(E.seg(x0.t, C0, H, W))
             if x1 is not None:
-                segs.append(E.seg(x1, C1, H, W))
-            return E.gemm(ctx, segs, q.w2, q.cout, S, H, W, bias=q.b2)
-        return E.gemm(ctx, segs, q.w2, q.cout, S, H, W, bias=q.b2, residual=x0, res_ld=C0)
+                segs.append(E.seg(t1, C1, H, W, nb_div=d1))
+            out = E.gemm(ctx, segs, q.w2, q.cout, NB, H, W, bias=q.b2)
+        else:
+            out = E.gemm(ctx, segs, q.w2, q.cout, NB, H, W, bias=q.b2, residual=x0.t, res_ld=C0)
+        return _Act(out, q.cout, rep if unit else 1)
 
-    def _transformer(self, ctx, q, xattn, xattn_idx, x, S, H, W):
+    def _transformer(self, ctx, q, xattn, xattn_idx, x, U, rep, H, W):
         HW, Cc = H * W, q.ch
-        M = S * HW
-        a = E.groupnorm(ctx, x, Cc, None, 0, S, HW, q.gn_g, q.gn_b, 1e-6, False)
+        S = U * rep
+        shared = x.div > 1 and HW >= 128          # attention core once per unit
+        NB = U if shared else S
+        ridx = self._unit_rows(ctx, S, HW, rep) if x.div > 1 else None
+        a = E.groupnorm(ctx, x.t, Cc, None, 0, NB, HW, q.gn_g, q.gn_b, 1e-6, False, div0=1 if shared else x.div)
         h = E.linear(ctx, a, q.pin_w, Cc, bias=q.pin_b)
         n1 = E.layernorm(ctx, h, q.ln1_g, q.ln1_b, 1e-5)
         qkv = E.linear(ctx, n1, q.qkv_w, 3 * Cc)
-        att = E.attention(ctx, qkv, S, HW, q.heads, Cc // q.heads)
-        # attn1 out-proj + residual + collapsed single-token cross-attention (attn2) in one epilogue
-        h = E.linear(ctx, att, q.o1_w, Cc, bias=q.o1_b, residual=h, res_ld=Cc, rowvec=xattn[:, q.xv_off:],
-                     rowvec_ld=xattn.shape[1], rowvec_idx=xattn_idx, rows_per_group=HW)
+        att = E.attention(ctx, qkv, NB, HW, q.heads, Cc // q.heads)
+        # attn1 out-proj + residual + collapsed single-token cross-attention (attn2) in one epilogue: the first place a
+        # sample sees its class.  With a shared core the A operand / residual rows come from the unit's tensors.
+        epi = dict(bias=q.o1_b, residual=h, res_ld=Cc, rowvec=xattn[:, q.xv_off:], rowvec_ld=xattn.shape[1],
+                   rowvec_idx=xattn_idx, rows_per_group=HW)
+        if shared:
+            h = E.gemm(ctx, [E.seg(att, Cc, H, W, nb_div=rep)], q.o1_w, Cc, S, H, W, res_idx=ridx, **epi)
+        else:
+            h = E.linear(ctx, att, q.o1_w, Cc, **epi)
         n3 = E.layernorm(ctx, h, q.ln3_g, q.ln3_b, 1e-5)
         ff = E.linear(ctx, n3, q.gg_w, 8 * Cc, bias=q.gg_b, act=L.ACT_GEGLU)
         h = E.linear(ctx, ff, q.ff2_w, Cc, bias=q.ff2_b, residual=h, res_ld=Cc)
-        assert M == h.shape[0]
-        return E.linear(ctx, h, q.pout_w, Cc, bias=q.pout_b, residual=x, res_ld=Cc)
+        assert S * HW == h.shape[0]
+        out = E.linear(ctx, h, q.pout_w, Cc, bias=q.pout_b, residual=x.t, res_ld=Cc, res_idx=ridx)
+        return _Act(out, Cc, 1)
 
     def cross_attn_table(self, ctx, pk, ehs):
         """ehs [R, hid] (engine dtype) -> fp32 [R, sum C_layer]: attn2 output per row (class or sample)."""
@@ -376,52 +424,53 @@ class UNetCondition2D(nn.Module):
                      out=table[:, q.xv_off:], out_ld=pk.xv_total)
         return table
 
-    def run(self, ctx, pk, a_in, t, U, rep, H, W, xattn, xattn_idx=None, mse=None):
-        """a_in: staged conv_in operand [S*H*W, kpad]; t: [U] fp32 noise labels (sample s = u*rep + r).
-        Returns the NHWC prediction [S*H*W, Cout] (fp32) or, with ``mse``, fills mse['err'] and returns None."""
+    def run(self, ctx, pk, a_in, t, U, rep, H, W, xattn, xattn_idx=None, mse=None, share_prefix=False):
+        """a_in: staged conv_in operand [S*H*W, kpad] ([U*H*W, kpad] with ``share_prefix``); t: [U] fp32 noise labels
+        (sample s = u*rep + r).  Returns the NHWC prediction [S*H*W, Cout] (fp32) or, with ``mse``, fills mse['err']
+        and returns None."""
         S = U * rep
         boc = self.config.block_out_channels
-        n = len(boc)
+        div = rep if (share_prefix and rep > 1) else 1
+        assert a_in.shape[0] == (U if div > 1 else S) * H * W
         # time embedding: sincos -> MLP -> SiLU (every consumer applies SiLU first) -> all resnets' projections
         te = E.timestep_embed(ctx, t, U, rep, boc[0], self.config.freq_shift)
         e1 = E.linear(ctx, te, pk.te1_w, pk.te1_w.shape[0], bias=pk.te1_b, act=L.ACT_SILU)
         e2 = E.linear(ctx, e1, pk.te2_w, pk.te2_w.shape[0], bias=pk.te2_b, act=L.ACT_SILU)
         temb = E.linear(ctx, e2, pk.temb_w, pk.temb_total, bias=pk.temb_b, out_dtype=torch.float32)
 
-        h = E.linear(ctx, a_in, pk.conv_in_w, boc[0], bias=pk.conv_in_b, k_alg=9 * self.config.in_channels)
-        Ch = boc[0]
-        skips = [(h, Ch)]
+        h = _Act(E.linear(ctx, a_in, pk.conv_in_w, boc[0], bias=pk.conv_in_b, k_alg=9 * self.config.in_channels),
+                 boc[0], div)
+        skips = [h]
         for i, blk in enumerate(self.down_blocks):
             for j, r in enumerate(blk.resnets):
-                q = pk.res[id(r)]
-                h = self._resnet(ctx, q, temb, h, Ch, None, 0, S, H, W)
-                Ch = q.cout
+                h = self._resnet(ctx, pk.res[id(r)], temb, h, None, U, rep, H, W)
                 if hasattr(blk, "attentions"):
-                    h = self._transformer(ctx, pk.tr[id(blk.attentions[j])], xattn, xattn_idx, h, S, H, W)
-                skips.append((h, Ch))
+                    h = self._transformer(ctx, pk.tr[id(blk.attentions[j])], xattn, xattn_idx, h, U, rep, H, W)
+                skips.append(h)
             if hasattr(blk, "downsamplers"):
                 sp = pk.samp[id(blk.downsamplers[0])]
-                h = E.gemm(ctx, E.conv3x3_segs(h, Ch, H, W, stride=2), sp.w, Ch, S, H // 2, W // 2, bias=sp.b)
+                NB = U if h.div > 1 else S
+                h = _Act(E.gemm(ctx, E.conv3x3_segs(h.t, h.C, H, W, stride=2), sp.w, h.C, NB, H // 2, W // 2, bias=sp.b),
+                         h.C, h.div)
                 H, W = H // 2, W // 2
-                skips.append((h, Ch))
+                skips.append(h)
         mb = self.mid_block
-        h = self._resnet(ctx, pk.res[id(mb.resnets[0])], temb, h, Ch, None, 0, S, H, W)
-        h = self._transformer(ctx, pk.tr[id(mb.attentions[0])], xattn, xattn_idx, h, S, H, W)
-        h = self._resnet(ctx, pk.res[id(mb.resnets[1])], temb, h, Ch, None, 0, S, H, W)
+        h = self._resnet(ctx, pk.res[id(mb.resnets[0])], temb, h, None, U, rep, H, W)
+        h = self._transformer(ctx, pk.tr[id(mb.attentions[0])], xattn, xattn_idx, h, U, rep, H, W)
+        h = self._resnet(ctx, pk.res[id(mb.resnets[1])], temb, h, None, U, rep, H, W)
         for i, blk in enumerate(self.up_blocks):
             for j, r in enumerate(blk.resnets):
-                sk, Cs = skips.pop()
-                q = pk.res[id(r)]
-                h = self._resnet(ctx, q, temb, h, Ch, sk, Cs, S, H, W)  # torch.cat folded into GN + K segments
-                Ch = q.cout
+                h = self._resnet(ctx, pk.res[id(r)], temb, h, skips.pop(), U, rep, H, W)  # cat folded into GN + K segs
                 if hasattr(blk, "attentions"):
-                    h = self._transformer(ctx, pk.tr[id(blk.attentions[j])], xattn, xattn_idx, h, S, H, W)
+                    h = self._transformer(ctx, pk.tr[id(blk.attentions[j])], xattn, xattn_idx, h, U, rep, H, W)
             if hasattr(blk, "upsamplers"):
                 sp = pk.samp[id(blk.upsamplers[0])]
-                up = E.upsample2x(ctx, h, S, H, W, Ch)
+                up = E.upsample2x(ctx, h.t, S, H, W, h.C)
                 H, W = 2 * H, 2 * W
-                h = E.gemm(ctx, E.conv3x3_segs(up, Ch, H, W), sp.w, Ch, S, H, W, bias=sp.b)
-        a = E.groupnorm(ctx, h, Ch, None, 0, S, H * W, pk.out_g, pk.out_bn, self.config.norm_eps, True)
+                h = _Act(E.gemm(ctx, E.conv3x3_segs(up, h.C, H, W), sp.w, h.C, S, H, W, bias=sp.b), h.C, 1)
+        assert h.div == 1
+        Ch = h.C
+        a = E.groupnorm(ctx, h.t, Ch, None, 0, S, H * W, pk.out_g, pk.out_bn, self.config.norm_eps, True)
         Co = self.config.out_channels
         if mse is not None and mse.get("fused", False):
             E.gemm(ctx, E.conv3x3_segs(a, Ch, H, W), pk.out_w, Co, S, H, W, bias=pk.out_b, mse=mse, want_out=False)

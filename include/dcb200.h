@@ -61,7 +61,9 @@ typedef struct dcb_seg {
   int32_t kc;       /* channels consumed (K extent); multiple of 64 (tcgen05) / 16 (SIMT) */
   int32_t dy, dx;   /* input pixel = (oy*stride + dy, ox*stride + dx); out-of-range reads as 0 (padding) */
   int32_t stride;   /* 1 or 2 */
-  int32_t _r0, _r1;
+  int32_t nb_div;   /* 0/1: src sample = n;  d > 1: src sample = n / d -- a tensor computed once per (image, timestep)
+                       unit is read by all d class-conditional samples of that unit (shared class-independent prefix) */
+  int32_t _r1;
 } dcb_seg;
 
 typedef struct dcb_gemm_desc {
@@ -106,6 +108,12 @@ int dcb_groupnorm_stats(int dtype, const void* x0, int C0, const void* x1, int C
 int dcb_groupnorm_apply(int dtype, const void* x0, int C0, const void* x1, int C1, int NB, int HW, int G, int chunks,
                         const float* part, const float* gamma, const float* beta, float eps, int silu, void* out,
                         dcb_stream stream);
+/* same, with per-source sample divisors: sample n reads x0[n / div0] and x1[n / div1] (see dcb_seg.nb_div) */
+int dcb_groupnorm_stats_div(int dtype, const void* x0, int C0, int div0, const void* x1, int C1, int div1, int NB, int HW,
+                            int G, int chunks, float* part, dcb_stream stream);
+int dcb_groupnorm_apply_div(int dtype, const void* x0, int C0, int div0, const void* x1, int C1, int div1, int NB, int HW,
+                            int G, int chunks, const float* part, const float* gamma, const float* beta, float eps,
+                            int silu, void* out, dcb_stream stream);
 /* LayerNorm over C with optional affine (gamma,beta) and optional adaLN modulation
  * y = LN(x)*(1 + scale[g]) + shift[g], g = row / rows_per_group */
 int dcb_layernorm(int dtype, const void* x, int64_t rows, int C, const float* gamma, const float* beta, float eps,
@@ -123,7 +131,9 @@ int dcb_haar_idwt(const float* w, int B, int C4, int h, int wd, float pre_scale,
 
 /* ---- data movement helpers ------------------------------------------------------------------------------ */
 int dcb_upsample2x(int dtype, const void* x, int NB, int H, int W, int C, void* out, dcb_stream stream);
-/* out[m][n] = x[m/div][n] + vec[m / rows_per_group][n]  (class expansion of a shared prefix; reserved) */
+/* out[n] = x[n / div]: materialised class expansion of a per-unit tensor [NB/div, HW, C] -> [NB, HW, C] (only for
+ * geometries where a GEMM tile spans several samples and dcb_seg.nb_div cannot be used) */
+int dcb_expand_samples(int dtype, const void* x, int NB, int div, int64_t elems_per_sample, void* out, dcb_stream stream);
 int dcb_nhwc_to_nchw(int dtype, const void* x, int NB, int HW, int C, int ld, float* out, dcb_stream stream);
 /* DiT unpatchify: tok [B, g*g, p*p*C] (dtype) -> [B,C,g*p,g*p] fp32  ("nhwpqc->nchpwq") */
 int dcb_unpatchify(int dtype, const void* tok, int B, int g, int p, int C, int ld, float* out, dcb_stream stream);

@@ -228,3 +228,25 @@ def test_attention(dev, d, N):
     assert rel_err(out, ref) < 1e-2
     out = E.attention(_ctx(dev, "bf16"), qb, B, N, heads, d, simt=True).float()
     assert rel_err(out, ref) < 1e-2
+
+
+@pytest.mark.parametrize("dt", ["bf16", "fp32"])
+def test_groupnorm_unit_divisor_and_expand(dev, dt):
+    """GroupNorm over cat([per-sample h, per-unit skip]) with a sample divisor == GroupNorm over the materialised
+    expansion; dcb_expand_samples == repeat_interleave."""
+    from dcb200 import engine as E
+    torch.manual_seed(0)
+    ctx = E.Ctx(device=dev, precision=dt)
+    U, rep, HW, C0, C1 = 3, 4, 256, 128, 64
+    S = U * rep
+    h = torch.randn(S * HW, C0, device=dev).to(ctx.tdtype)
+    sk = torch.randn(U * HW, C1, device=dev).to(ctx.tdtype)
+    g, b = torch.randn(C0 + C1, device=dev), torch.randn(C0 + C1, device=dev)
+    ex = E.expand_samples(ctx, sk, S, rep, HW)
+    assert torch.equal(ex, sk.reshape(U, HW, C1).repeat_interleave(rep, 0).reshape(-1, C1))
+    a = E.groupnorm(ctx, h, C0, sk, C1, S, HW, g, b, 1e-5, True, div1=rep)
+    r = E.groupnorm(ctx, h, C0, ex, C1, S, HW, g, b, 1e-5, True)
+    assert torch.equal(a, r)
+    a = E.groupnorm(ctx, sk, C1, None, 0, S, HW, g[:C1].contiguous(), b[:C1].contiguous(), 1e-6, False, div0=rep)
+    r = E.groupnorm(ctx, ex, C1, None, 0, S, HW, g[:C1].contiguous(), b[:C1].contiguous(), 1e-6, False)
+    assert torch.equal(a, r)

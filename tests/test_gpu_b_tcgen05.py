@@ -218,3 +218,51 @@ def test_tc2_linear_odd_tiles(dev):
     r = _bf(M, N, dev=dev)
     out = E.linear(_ctx(dev), x, w, N, bias=b, residual=r, res_ld=N)
     assert rel_err(out, x.float() @ w.float().t() + b + r.float()) < 5e-3
+
+
+@pytest.mark.parametrize("U,rep,H,W,Ci,Co,big", [
+    (3, 2, 16, 16, 128, 128, False),    # gemm_tc (few tiles), 1x1 + 3x3 over a per-unit source
+    (5, 3, 128, 128, 64, 128, True),    # gemm_tc2 incl. the x-halo path: many tiles
+    (2, 10, 32, 32, 64, 64, False),     # CIFAR-like: 10 classes per unit
+])
+def test_tc_unit_shared_sources(dev, U, rep, H, W, Ci, Co, big):
+    """dcb_seg.nb_div: a per-(image, timestep) unit tensor read by all of the unit's class-conditional samples equals
+    the GEMM over the materialised repeat_interleave'd tensor, bit for bit, in both tcgen05 kernels and the SIMT engine."""
+    from dcb200 import _lib as L
+    from dcb200 import engine as E
+    torch.manual_seed(0)
+    S = U * rep
+    xu = _bf(U, H, W, Ci, dev=dev)
+    xs = xu.repeat_interleave(rep, 0).contiguous()
+    ys = _bf(S, H, W, Ci, dev=dev)                                # a genuinely per-sample second source
+    w = (torch.randn(Co, 10 * Ci, device=dev) * 0.05).to(torch.bfloat16)
+    b = torch.randn(Co, device=dev)
+    for eng in (0, L.ENGINE_SIMT):
+        segs_u = E.conv3x3_segs(ys, Ci, H, W) + [E.seg(xu, Ci, H, W, nb_div=rep)]
+        segs_s = E.conv3x3_segs(ys, Ci, H, W) + [E.seg(xs, Ci, H, W)]
+        o_u = E.gemm(_ctx(dev, eng), segs_u, w, Co, S, H, W, bias=b)
+        o_s = E.gemm(_ctx(dev, eng), segs_s, w, Co, S, H, W, bias=b)
+        assert torch.equal(o_u, o_s), f"1x1 unit source, engine {eng}"
+        w9 = w[:, :9 * Ci].contiguous()
+        o_u = E.gemm(_ctx(dev, eng), E.conv3x3_segs(xu, Ci, H, W, nb_div=rep), w9, Co, S, H, W, bias=b)
+        o_s = E.gemm(_ctx(dev, eng), E.conv3x3_segs(xs, Ci, H, W), w9, Co, S, H, W, bias=b)
+        assert torch.equal(o_u, o_s), f"3x3 unit source, engine {eng}"
+    # residual rows gathered from the unit tensor (attn1 out-projection of a shared attention core)
+    HW = H * W
+    m = torch.arange(S * HW, device=dev)
+    ridx = ((m // (HW * rep)) * HW + m % HW).to(torch.int32)
+    r_u = _bf(U * HW, Co, dev=dev)
+    w1 = w[:, :Ci].contiguous()
+    o_u = E.gemm(_ctx(dev), [E.seg(xu, Ci, H, W, nb_div=rep)], w1, Co, S, H, W, bias=b, residual=r_u, res_ld=Co, res_idx=ridx)
+    o_s = E.gemm(_ctx(dev), [E.seg(xs, Ci, H, W)], w1, Co, S, H, W, bias=b,
+                 residual=r_u.reshape(U, HW, Co).repeat_interleave(rep, 0).reshape(-1, Co).contiguous(), res_ld=Co)
+    assert torch.equal(o_u, o_s)
+
+
+def test_tc_unit_source_needs_single_sample_tiles(dev):
+    from dcb200 import _lib as L
+    from dcb200 import engine as E
+    x = _bf(2, 8, 8, 64, dev=dev)   # 64 pixels per sample: a 128-row tile spans two samples
+    w = _bf(64, 64, dev=dev)
+    with pytest.raises(L.DcbError):
+        E.gemm(_ctx(dev, L.ENGINE_TCGEN05), [E.seg(x, 64, 8, 8, nb_div=2)], w, 64, 4, 8, 8)

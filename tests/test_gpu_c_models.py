@@ -178,6 +178,12 @@ def test_classify_cifar_config_vs_oracle_loop(dev, precision):
         cfg.dcb_max_batch = 1000  # different chunking must not change anything (per-sample fixed-order math)
         dc.classify(x.to(dev), t_all=t_all, eps_all=eps_all)
         assert torch.equal(dc.last_errors, e1)
+    # class-independent prefix computed once per (image, timestep) unit vs once per class (the reference's order):
+    # the per-sample arithmetic is the same, so the error table must not change by a single bit
+    cfg.dcb_share_prefix = False
+    dc.classify(x.to(dev), t_all=t_all, eps_all=eps_all)
+    assert torch.equal(dc.last_errors, e1), "shared-prefix program differs from the per-class program"
+    cfg.dcb_share_prefix = None
 
 
 def test_classify_reference_rng_semantics(dev):

@@ -36,6 +36,12 @@ def _run(dev, kind, arch, cfg, x, T, BS, amplify):
     dc = dc.to(dev).eval()
     labels = dc.classify(x.to(dev), t_all=t_all, eps_all=eps_all)
     _check_classify(labels.cpu(), dc.last_errors, ref_labels.numpy(), ref_err.mean(dim=2).numpy(), 1e-2)
+    if kind == "unet":   # shared class-independent prefix (default) vs the reference's per-class recomputation
+        e1 = dc.last_errors.clone()
+        cfg.dcb_share_prefix = False
+        dc.classify(x.to(dev), t_all=t_all, eps_all=eps_all)
+        assert torch.equal(dc.last_errors, e1)
+        cfg.dcb_share_prefix = None
     return dc
 
 
