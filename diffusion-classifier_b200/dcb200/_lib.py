@@ -29,7 +29,7 @@ class GemmDesc(C.Structure):
                 ("nseg", c_i32), ("_r0", c_i32), ("seg", Seg * MAX_SEGS),
                 ("W", c_void_p), ("bias", c_void_p), ("rowvec", c_void_p), ("rowvec_idx", c_void_p),
                 ("gate", c_void_p), ("residual", c_void_p), ("res_idx", c_void_p), ("out", c_void_p),
-                ("mse_target", c_void_p), ("mse_scale", c_void_p), ("mse_part", c_void_p),
+                ("mse_target", c_void_p), ("mse_scale", c_void_p), ("mse_part", c_void_p), ("gn_part", c_void_p),
                 ("rowvec_ld", c_i32), ("gate_ld", c_i32), ("rows_per_group", c_i32), ("act", c_i32),
                 ("act_post", c_i32), ("res_ld", c_i32), ("res_mod", c_i32), ("res_dtype", c_i32),
                 ("out_ld", c_i32), ("out_dtype", c_i32), ("mse_div", c_i32), ("mse_ld", c_i32)]
@@ -45,6 +45,9 @@ _PROTOS = {
     "dcb_timestep_embed": (c_int, [c_int, c_void_p, c_int, c_int, c_int, c_float, c_float, c_void_p, c_void_p]),
     "dcb_gemm": (c_int, [C.POINTER(GemmDesc), c_void_p]),
     "dcb_gemm_mse_layout": (c_int, [C.POINTER(GemmDesc), C.POINTER(c_i32), C.POINTER(c_i32)]),
+    "dcb_gemm_gn_layout": (c_int, [C.POINTER(GemmDesc), C.POINTER(c_i32)]),
+    "dcb_groupnorm_stats_from_tiles": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                               c_void_p, c_void_p]),
     "dcb_mse_finalize": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
     "dcb_eps_mse": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_i64, c_void_p, c_int, c_void_p]),
     "dcb_groupnorm_stats": (c_int, [c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,

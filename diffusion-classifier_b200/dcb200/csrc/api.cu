@@ -60,7 +60,7 @@ static int to_dev(const dcb_gemm_desc* d, GemmDev* g) {
   e.n_out = d->act == DCB_ACT_GEGLU ? d->N / 2 : d->N;
   e.rows_per_sample = d->OH * d->OW;
   e.bias = d->bias; e.rowvec = d->rowvec; e.rowvec_idx = d->rowvec_idx; e.gate = d->gate; e.residual = d->residual; e.res_idx = d->res_idx;
-  e.out = d->out; e.mse_target = d->mse_target; e.mse_scale = d->mse_scale; e.mse_part = d->mse_part;
+  e.out = d->out; e.mse_target = d->mse_target; e.mse_scale = d->mse_scale; e.mse_part = d->mse_part; e.gn_part = d->gn_part;
   e.rowvec_ld = d->rowvec_ld; e.gate_ld = d->gate_ld; e.rows_per_group = d->rows_per_group;
   e.act = d->act; e.act_post = d->act_post;
   e.res_ld = d->res_ld; e.res_mod = d->res_mod; e.res_dtype = d->res_dtype;
@@ -94,6 +94,14 @@ extern "C" int dcb_gemm(const dcb_gemm_desc* d, dcb_stream stream) {
   const int eng = pick_engine(d);
   if (eng == DCB_ENGINE_TCGEN05) return launch_gemm_tc(g, (cudaStream_t)stream);
   return launch_gemm_simt(g, (cudaStream_t)stream);
+}
+
+extern "C" int dcb_gemm_gn_layout(const dcb_gemm_desc* d, int32_t* supported) {
+  GemmDev g;
+  int rc = to_dev(d, &g);
+  if (rc) return rc;
+  *supported = (pick_engine(d) == DCB_ENGINE_TCGEN05 && g.K % 64 == 0 && tc_staged(g)) ? 1 : 0;
+  return DCB_OK;
 }
 
 extern "C" int dcb_gemm_mse_layout(const dcb_gemm_desc* d, int32_t* rows_per_part, int32_t* n_tiles) {

@@ -118,6 +118,7 @@ struct EpiDev {
   const float* mse_target;
   const float* mse_scale;
   float* mse_part;
+  float* gn_part;  // per-tile per-column (sum, sumsq) of the written bf16 values, or null
   int rowvec_ld, gate_ld, rows_per_group;
   int act, act_post;
   int res_ld, res_mod, res_dtype;
@@ -152,5 +153,6 @@ __device__ __forceinline__ float epi_scalar(const EpiDev& e, int m, int n, float
 int launch_gemm_simt(const GemmDev& g, cudaStream_t st);
 int launch_gemm_tc(const GemmDev& g, cudaStream_t st);
 int tc_geometry(const GemmDev& g, int* m_tiles, int* n_tiles, int* BN);
+bool tc_staged(const GemmDev& g);
 
 }  // namespace dcb

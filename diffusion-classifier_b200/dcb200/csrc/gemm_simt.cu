@@ -106,6 +106,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmDev g) {
 
 int launch_gemm_simt(const GemmDev& g, cudaStream_t st) {
   DCB_REQUIRE(g.epi.mse_part == nullptr, "SIMT engine has no fused MSE epilogue; use dcb_eps_mse");
+  DCB_REQUIRE(g.epi.gn_part == nullptr, "SIMT engine does not produce GroupNorm tile statistics");
   for (int s = 0; s < g.nseg; ++s) DCB_REQUIRE(g.seg[s].kc % SM_BK == 0, "SIMT engine needs kc %% 16 == 0");
   dim3 grid((g.epi.M + SM_BM - 1) / SM_BM, (g.epi.n_out + SM_BN - 1) / SM_BN);
   if (g.dtype == DCB_BF16) gemm_simt_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(g);

@@ -398,6 +398,21 @@ static int choose_geometry(const GemmDev& g, TcGeom* t) {
   return DCB_OK;
 }
 
+// bf16 outputs with <= 128 output columns per tile (BN <= 128, or GEGLU's 256 -> 128); 16-byte aligned rows
+static bool staged_for(const GemmDev& g, const TcGeom& t) {
+  const EpiDev& e = g.epi;
+  if (getenv("DCB_TC_DIRECT_EPILOGUE")) return false;
+  return e.out != nullptr && e.out_dtype == DCB_BF16 && e.mse_part == nullptr && e.n_out % 8 == 0 && e.out_ld % 8 == 0 &&
+         ((uintptr_t)e.out % 16) == 0 && (t.BN <= 128 || e.act == DCB_ACT_GEGLU) &&
+         (e.residual == nullptr || (e.res_dtype == DCB_BF16 && e.res_ld % 8 == 0 && ((uintptr_t)e.residual % 16) == 0));
+}
+
+bool tc_staged(const GemmDev& g) {
+  TcGeom t;
+  if (g.dtype != DCB_BF16 || choose_geometry(g, &t)) return false;
+  return staged_for(g, t);
+}
+
 int tc_geometry(const GemmDev& g, int* m_tiles, int* n_tiles, int* BN) {
   TcGeom t;
   int rc = choose_geometry(g, &t);
@@ -509,11 +524,8 @@ int launch_gemm_tc(const GemmDev& g, cudaStream_t st) {
   {
     const EpiDev& e = g.epi;
     // bf16 outputs with <= 128 output columns per tile (BN <= 128, or GEGLU's 256 -> 128); 16-byte aligned rows
-    p.staged = e.out != nullptr && e.out_dtype == DCB_BF16 && e.mse_part == nullptr && e.n_out % 8 == 0 &&
-               e.out_ld % 8 == 0 && ((uintptr_t)e.out % 16) == 0 && (t.BN <= 128 || e.act == DCB_ACT_GEGLU) &&
-               (e.residual == nullptr ||
-                (e.res_dtype == DCB_BF16 && e.res_ld % 8 == 0 && ((uintptr_t)e.residual % 16) == 0));
-    if (getenv("DCB_TC_DIRECT_EPILOGUE")) p.staged = 0;
+    p.staged = staged_for(g, t);
+    DCB_REQUIRE(e.gn_part == nullptr || p.staged, "gn_part needs the staged bf16 epilogue (ask dcb_gemm_gn_layout first)");
     // all rows of an M tile fall into one rowvec/gate group?
     if (e.rows_per_group <= 0) p.uniform = 1;
     else if (g.OH == 1 && g.NB == 1) p.uniform = e.rows_per_group % TC_BM == 0;

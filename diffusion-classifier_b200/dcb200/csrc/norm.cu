@@ -177,6 +177,36 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const T* __restric
   }
 }
 
+// ---- GroupNorm statistics from the producer GEMM's tile partials (dcb_gemm_desc.gn_part) -------------------
+// one block per sample; thread (slice, g) walks every 8th tile of group g's channels, fixed-order combine
+__global__ void __launch_bounds__(512) gn_tiles_finalize_kernel(const float* __restrict__ p0, int C0, int div0,
+                                                                const float* __restrict__ p1, int C1, int div1, int tps,
+                                                                int G, float* __restrict__ out) {
+  __shared__ double sh[8][64][2];
+  const int n = blockIdx.x, g = threadIdx.x % G, slice = threadIdx.x / G;
+  const int cpg = (C0 + C1) / G;
+  double s = 0.0, q = 0.0;
+  for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+    const float* src;
+    int stride;
+    if (c < C0) { src = p0 + ((int64_t)(n / div0) * tps * C0 + c) * 2; stride = C0 * 2; }
+    else { src = p1 + ((int64_t)(n / div1) * tps * C1 + (c - C0)) * 2; stride = C1 * 2; }
+    for (int t = slice; t < tps; t += 8) {
+      const float2 v = *reinterpret_cast<const float2*>(src + (int64_t)t * stride);
+      s += v.x;
+      q += v.y;
+    }
+  }
+  sh[slice][g][0] = s;
+  sh[slice][g][1] = q;
+  __syncthreads();
+  if (slice == 0) {
+    for (int k = 1; k < 8; ++k) { s += sh[k][g][0]; q += sh[k][g][1]; }
+    out[((int64_t)n * G + g) * 2] = (float)s;
+    out[((int64_t)n * G + g) * 2 + 1] = (float)q;
+  }
+}
+
 static int gn_threads(int V) { return V >= GN_THREADS ? GN_THREADS : (GN_THREADS / V) * V; }
 
 template <typename T>
@@ -298,6 +328,17 @@ extern "C" int dcb_groupnorm_apply_div(int dtype, const void* x0, int C0, int di
                                                        out, st, div0, div1)
                            : gn_apply_t<float>(x0, C0, x1, C1, NB, HW, G, chunks, part, gamma, beta, eps, silu, out, st,
                                                div0, div1);
+}
+
+extern "C" int dcb_groupnorm_stats_from_tiles(const float* part0, int C0, int div0, const float* part1, int C1, int div1,
+                                              int NB, int tiles_per_sample, int G, float* part_out, dcb_stream stream) {
+  DCB_REQUIRE(G > 0 && G <= 64 && (C0 + C1) % G == 0, "groupnorm: C=%d not divisible by G=%d (G<=64)", C0 + C1, G);
+  DCB_REQUIRE(part0 != nullptr && (C1 == 0) == (part1 == nullptr) && tiles_per_sample >= 1 && NB >= 1,
+              "groupnorm_stats_from_tiles: bad arguments");
+  gn_tiles_finalize_kernel<<<NB, 8 * G, 0, (cudaStream_t)stream>>>(part0, C0, div0 < 1 ? 1 : div0, part1, C1,
+                                                                  div1 < 1 ? 1 : div1, tiles_per_sample, G, part_out);
+  DCB_CHECK_LAUNCH("gn_tiles_finalize");
+  return DCB_OK;
 }
 
 extern "C" int dcb_groupnorm_stats(int dtype, const void* x0, int C0, const void* x1, int C1, int NB, int HW, int G,

@@ -304,16 +304,53 @@ __device__ __forceinline__ void staged_epilogue(const EpiGeom& gq, const EpiDev&
     __syncwarp();
     if (do_release && lane == 0) mbar_arrive(empty_bar);
     epi_bar(bar_id);
-    // ---- coalesced copy-out ----
+    // ---- coalesced copy-out (+ per-column sum / sum of squares of the stored values for the next GroupNorm) ----
+    float cs[8], cq[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) cs[i] = cq[i] = 0.f;
     if (cc_ok) {
       __nv_bfloat16* obase = (__nv_bfloat16*)e.out + ocol0 + cc * 8;
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         const int row = rr0 + 8 * i;
         const int mm = s_m[row];
-        if (mm >= 0)
-          *reinterpret_cast<uint4*>(obase + (int64_t)mm * e.out_ld) =
-              *reinterpret_cast<const uint4*>(stg8 + row * 256 + ((cc ^ (row & 7)) << 4));
+        if (mm >= 0) {
+          const uint4 val = *reinterpret_cast<const uint4*>(stg8 + row * 256 + ((cc ^ (row & 7)) << 4));
+          *reinterpret_cast<uint4*>(obase + (int64_t)mm * e.out_ld) = val;
+          if (e.gn_part) {
+            float f[8];
+            unpack_bf16x8(val, f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { cs[j] += f[j]; cq[j] = fmaf(f[j], f[j], cq[j]); }
+          }
+        }
+      }
+    }
+    if (e.gn_part) {
+      // fixed-order reduction over the 8 row-slices: lanes cc / cc+16 by shuffle, the 4 warps through the (now free)
+      // staging tile; thread c then owns output column c of this tile
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        cs[j] += __shfl_xor_sync(0xffffffffu, cs[j], 16);
+        cq[j] += __shfl_xor_sync(0xffffffffu, cq[j], 16);
+      }
+      epi_bar(bar_id);  // every thread has read its rows out of the staging tile
+      float* red = reinterpret_cast<float*>(stg8);  // [4 warps][128 columns][2]
+      const int wq = et >> 5;
+      if ((et & 16) == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          red[(wq * 128 + cc * 8 + j) * 2] = cs[j];
+          red[(wq * 128 + cc * 8 + j) * 2 + 1] = cq[j];
+        }
+      }
+      epi_bar(bar_id);
+      if (et < ncols_out && ocol0 + et < e.n_out && tb * gq.bn < gq.NB) {  // (tc2's odd tail sub-tile has no slot)
+        const float s4 = (red[et * 2] + red[(128 + et) * 2]) + (red[(256 + et) * 2] + red[(384 + et) * 2]);
+        const float q4 = (red[et * 2 + 1] + red[(128 + et) * 2 + 1]) + (red[(256 + et) * 2 + 1] + red[(384 + et) * 2 + 1]);
+        float* gp = e.gn_part + ((int64_t)tm_lin * e.n_out + ocol0 + et) * 2;
+        gp[0] = s4;
+        gp[1] = q4;
       }
     }
 }

@@ -57,6 +57,7 @@ class GemmProfile:
 
 
 PROFILE = None
+USE_TILE_STATS = __import__("os").environ.get("DCB_TILE_STATS", "1") != "0"
 
 
 def _p(t):
@@ -74,10 +75,13 @@ def conv3x3_segs(src, C_, H, W, stride=1, nb_div=1):
 
 def gemm(ctx: Ctx, segs, W, N, NB, OH, OW, *, bias=None, rowvec=None, rowvec_ld=0, rowvec_idx=None, rows_per_group=0,
          gate=None, gate_ld=0, residual=None, res_ld=0, res_mod=0, res_idx=None, act=L.ACT_NONE, act_post=L.ACT_NONE,
-         out=None, out_dtype=None, out_ld=None, mse=None, want_out=True, k_alg=None):
+         out=None, out_dtype=None, out_ld=None, mse=None, want_out=True, k_alg=None, gn_stats=False):
     """D = sum_seg A_seg . W^T with the fused epilogue; returns the [M, n_out] output (or None if want_out=False).
 
     mse = dict(target=, scale=, div=, ld=, err=[S] fp32 out) enables the fused eps-MSE epilogue (tcgen05 only).
+    gn_stats=True returns ``(out, part)``: part [ceil(M/128), n_out, 2] fp32 holds per-128-row-tile, per-column
+    (sum, sumsq) of the written values -- the next GroupNorm's statistics -- or None when this launch cannot
+    produce them (fp32 verify engine, 256-wide direct-epilogue tiles).
     """
     lib = L.lib()
     d = L.GemmDesc()
@@ -105,6 +109,13 @@ def gemm(ctx: Ctx, segs, W, N, NB, OH, OW, *, bias=None, rowvec=None, rowvec_ld=
         d.out = out.data_ptr()
         d.out_ld = out_ld if out_ld is not None else (out.shape[-1] if out.dim() == 2 else n_out)
         d.out_dtype = L.F32 if out.dtype == torch.float32 else L.BF16
+    gpart = None
+    if gn_stats and ctx.code == L.BF16 and out is not None:
+        ok = C.c_int32()
+        L.check(lib.dcb_gemm_gn_layout(C.byref(d), C.byref(ok)), "gemm_gn_layout")
+        if ok.value:
+            gpart = torch.empty((M + 127) // 128, n_out, 2, device=ctx.device, dtype=torch.float32)
+            d.gn_part = gpart.data_ptr()
     part = None
     if mse is not None:
         d.mse_target, d.mse_scale = mse["target"].data_ptr(), _p(mse.get("scale"))
@@ -127,6 +138,8 @@ def gemm(ctx: Ctx, segs, W, N, NB, OH, OW, *, bias=None, rowvec=None, rowvec_ld=
         prof.rows.append((e0, e1, 2.0 * M * N * (k_alg or K), f"M{M}_N{N}_K{K}_seg{len(segs)}"))
     if mse is not None:
         L.check(lib.dcb_mse_finalize(part.data_ptr(), pps, NB, mse["err"].data_ptr(), 1, ctx.stream()), "mse_finalize")
+    if gn_stats:
+        return out, gpart
     return out
 
 
@@ -142,14 +155,22 @@ def gn_chunks(NB, HW, Ctot):
     return max(1, min((HW * Ctot) // 131072, 64, HW))
 
 
-def groupnorm(ctx, x0, C0, x1, C1, NB, HW, gamma, beta, eps, silu, G=32, div0=1, div1=1):
-    """GroupNorm(+SiLU) over cat([x0, x1], channel) for NB samples; sample n reads x0[n // div0], x1[n // div1]."""
+def groupnorm(ctx, x0, C0, x1, C1, NB, HW, gamma, beta, eps, silu, G=32, div0=1, div1=1, st0=None, st1=None):
+    """GroupNorm(+SiLU) over cat([x0, x1], channel) for NB samples; sample n reads x0[n // div0], x1[n // div1].
+    st0 / st1: tile statistics written by the GEMMs that produced x0 / x1 (``gemm(gn_stats=True)``); when every source
+    has them the statistics pass -- a full re-read of the tensors -- is replaced by a reduction of those partials."""
     lib = L.lib()
-    chunks = gn_chunks(NB, HW, C0 + C1)
-    part = torch.empty(NB * chunks * G * 2, device=ctx.device, dtype=torch.float32)
     out = ctx.empty(NB * HW, C0 + C1)
-    L.check(lib.dcb_groupnorm_stats_div(ctx.code, x0.data_ptr(), C0, div0, _p(x1), C1, div1, NB, HW, G, chunks,
-                                        part.data_ptr(), ctx.stream()), "groupnorm_stats")
+    if st0 is not None and (x1 is None or st1 is not None) and HW % 128 == 0 and USE_TILE_STATS:
+        chunks = 1
+        part = torch.empty(NB * G * 2, device=ctx.device, dtype=torch.float32)
+        L.check(lib.dcb_groupnorm_stats_from_tiles(st0.data_ptr(), C0, div0, _p(st1), C1, div1, NB, HW // 128, G,
+                                                   part.data_ptr(), ctx.stream()), "groupnorm_stats_from_tiles")
+    else:
+        chunks = gn_chunks(NB, HW, C0 + C1)
+        part = torch.empty(NB * chunks * G * 2, device=ctx.device, dtype=torch.float32)
+        L.check(lib.dcb_groupnorm_stats_div(ctx.code, x0.data_ptr(), C0, div0, _p(x1), C1, div1, NB, HW, G, chunks,
+                                            part.data_ptr(), ctx.stream()), "groupnorm_stats")
     L.check(lib.dcb_groupnorm_apply_div(ctx.code, x0.data_ptr(), C0, div0, _p(x1), C1, div1, NB, HW, G, chunks,
                                         part.data_ptr(), gamma.data_ptr(), beta.data_ptr(), eps, int(silu),
                                         out.data_ptr(), ctx.stream()), "groupnorm_apply")

@@ -97,10 +97,12 @@ class _TimeEmb(_P):
 
 class _Act:
     """activation handle: tensor [nb*HW, C], channel count, sample divisor (1 = per sample, rep = per unit)."""
-    __slots__ = ("t", "C", "div")
+    __slots__ = ("t", "C", "div", "st")
 
-    def __init__(self, t, C, div):
-        self.t, self.C, self.div = t, C, div
+    def __init__(self, t, C, div, st=None):
+        if isinstance(t, tuple):      # (tensor, GroupNorm tile statistics) from gemm(gn_stats=True)
+            t, st = t
+        self.t, self.C, self.div, self.st = t, C, div, st
 
 
 def _tup(v, n):
@@ -370,20 +372,21 @@ class UNetCondition2D(nn.Module):
             x1 = _Act(E.expand_samples(ctx, x1.t, S, d1, HW), x1.C, 1)
             d1 = 1
         t1, C0 = (x1.t if x1 is not None else None), x0.C
+        s1 = x1.st if x1 is not None else None
         C1 = x1.C if x1 is not None else 0
         tld = temb.shape[1] * (rep if unit else 1)   # per-unit layers read the unit's first sample row of temb
-        a1 = E.groupnorm(ctx, x0.t, C0, t1, C1, NB, HW, q.g1, q.b1n, q.eps, True, div1=d1)
-        h1 = E.gemm(ctx, E.conv3x3_segs(a1, q.cin, H, W), q.w1, q.cout, NB, H, W, bias=q.b1,
-                    rowvec=temb[:, q.temb_off:], rowvec_ld=tld, rows_per_group=HW)
-        a2 = E.groupnorm(ctx, h1, q.cout, None, 0, NB, HW, q.g2, q.b2n, q.eps, True)
+        a1 = E.groupnorm(ctx, x0.t, C0, t1, C1, NB, HW, q.g1, q.b1n, q.eps, True, div1=d1, st0=x0.st, st1=s1)
+        h1, hs = E.gemm(ctx, E.conv3x3_segs(a1, q.cin, H, W), q.w1, q.cout, NB, H, W, bias=q.b1,
+                        rowvec=temb[:, q.temb_off:], rowvec_ld=tld, rows_per_group=HW, gn_stats=True)
+        a2 = E.groupnorm(ctx, h1, q.cout, None, 0, NB, HW, q.g2, q.b2n, q.eps, True, st0=hs)
         segs = E.conv3x3_segs(a2, q.cout, H, W)
         if q.shortcut:
             segs.append(E.seg(x0.t, C0, H, W))
             if x1 is not None:
                 segs.append(E.seg(t1, C1, H, W, nb_div=d1))
-            out = E.gemm(ctx, segs, q.w2, q.cout, NB, H, W, bias=q.b2)
+            out = E.gemm(ctx, segs, q.w2, q.cout, NB, H, W, bias=q.b2, gn_stats=True)
         else:
-            out = E.gemm(ctx, segs, q.w2, q.cout, NB, H, W, bias=q.b2, residual=x0.t, res_ld=C0)
+            out = E.gemm(ctx, segs, q.w2, q.cout, NB, H, W, bias=q.b2, residual=x0.t, res_ld=C0, gn_stats=True)
         return _Act(out, q.cout, rep if unit else 1)
 
     def _transformer(self, ctx, q, xattn, xattn_idx, x, U, rep, H, W):
@@ -392,7 +395,7 @@ class UNetCondition2D(nn.Module):
         shared = x.div > 1 and HW >= 128          # attention core once per unit
         NB = U if shared else S
         ridx = self._unit_rows(ctx, S, HW, rep) if x.div > 1 else None
-        a = E.groupnorm(ctx, x.t, Cc, None, 0, NB, HW, q.gn_g, q.gn_b, 1e-6, False, div0=1 if shared else x.div)
+        a = E.groupnorm(ctx, x.t, Cc, None, 0, NB, HW, q.gn_g, q.gn_b, 1e-6, False, div0=1 if shared else x.div, st0=x.st)
         h = E.linear(ctx, a, q.pin_w, Cc, bias=q.pin_b)
         n1 = E.layernorm(ctx, h, q.ln1_g, q.ln1_b, 1e-5)
         qkv = E.linear(ctx, n1, q.qkv_w, 3 * Cc)
@@ -409,7 +412,7 @@ class UNetCondition2D(nn.Module):
         ff = E.linear(ctx, n3, q.gg_w, 8 * Cc, bias=q.gg_b, act=L.ACT_GEGLU)
         h = E.linear(ctx, ff, q.ff2_w, Cc, bias=q.ff2_b, residual=h, res_ld=Cc)
         assert S * HW == h.shape[0]
-        out = E.linear(ctx, h, q.pout_w, Cc, bias=q.pout_b, residual=x.t, res_ld=Cc, res_idx=ridx)
+        out = E.linear(ctx, h, q.pout_w, Cc, bias=q.pout_b, residual=x.t, res_ld=Cc, res_idx=ridx, gn_stats=True)
         return _Act(out, Cc, 1)
 
     def cross_attn_table(self, ctx, pk, ehs):
@@ -438,8 +441,8 @@ class UNetCondition2D(nn.Module):
         e2 = E.linear(ctx, e1, pk.te2_w, pk.te2_w.shape[0], bias=pk.te2_b, act=L.ACT_SILU)
         temb = E.linear(ctx, e2, pk.temb_w, pk.temb_total, bias=pk.temb_b, out_dtype=torch.float32)
 
-        h = _Act(E.linear(ctx, a_in, pk.conv_in_w, boc[0], bias=pk.conv_in_b, k_alg=9 * self.config.in_channels),
-                 boc[0], div)
+        h = _Act(E.linear(ctx, a_in, pk.conv_in_w, boc[0], bias=pk.conv_in_b, k_alg=9 * self.config.in_channels,
+                          gn_stats=True), boc[0], div)
         skips = [h]
         for i, blk in enumerate(self.down_blocks):
             for j, r in enumerate(blk.resnets):
@@ -450,8 +453,8 @@ class UNetCondition2D(nn.Module):
             if hasattr(blk, "downsamplers"):
                 sp = pk.samp[id(blk.downsamplers[0])]
                 NB = U if h.div > 1 else S
-                h = _Act(E.gemm(ctx, E.conv3x3_segs(h.t, h.C, H, W, stride=2), sp.w, h.C, NB, H // 2, W // 2, bias=sp.b),
-                         h.C, h.div)
+                h = _Act(E.gemm(ctx, E.conv3x3_segs(h.t, h.C, H, W, stride=2), sp.w, h.C, NB, H // 2, W // 2, bias=sp.b,
+                                gn_stats=True), h.C, h.div)
                 H, W = H // 2, W // 2
                 skips.append(h)
         mb = self.mid_block
@@ -467,10 +470,10 @@ class UNetCondition2D(nn.Module):
                 sp = pk.samp[id(blk.upsamplers[0])]
                 up = E.upsample2x(ctx, h.t, S, H, W, h.C)
                 H, W = 2 * H, 2 * W
-                h = _Act(E.gemm(ctx, E.conv3x3_segs(up, h.C, H, W), sp.w, h.C, S, H, W, bias=sp.b), h.C, 1)
+                h = _Act(E.gemm(ctx, E.conv3x3_segs(up, h.C, H, W), sp.w, h.C, S, H, W, bias=sp.b, gn_stats=True), h.C, 1)
         assert h.div == 1
         Ch = h.C
-        a = E.groupnorm(ctx, h.t, Ch, None, 0, S, H * W, pk.out_g, pk.out_bn, self.config.norm_eps, True)
+        a = E.groupnorm(ctx, h.t, Ch, None, 0, S, H * W, pk.out_g, pk.out_bn, self.config.norm_eps, True, st0=h.st)
         Co = self.config.out_channels
         if mse is not None and mse.get("fused", False):
             E.gemm(ctx, E.conv3x3_segs(a, Ch, H, W), pk.out_w, Co, S, H, W, bias=pk.out_b, mse=mse, want_out=False)

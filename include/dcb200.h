@@ -84,6 +84,9 @@ typedef struct dcb_gemm_desc {
   const float* mse_target;   /* fused eps-MSE: part[tile] = sum_{rows,cols}(mse_scale[s]*v - target[(s/mse_div)*rps + pix][n])^2 */
   const float* mse_scale;    /* [NB] or NULL (=1) */
   float* mse_part;           /* [m_tiles * n_tiles] partial sums, reduced by dcb_mse_finalize */
+  float* gn_part;            /* optional [ceil(M/128)][n_out][2]: per-128-row-tile, per-column (sum, sum of squares) of the
+                                bf16 values just written -- the GroupNorm statistics of the NEXT layer, so its stats
+                                pass (a full re-read of this tensor) disappears; dcb_gemm_gn_layout says if supported */
   int32_t rowvec_ld, gate_ld, rows_per_group;
   int32_t act, act_post;     /* act before gate/residual, act_post after */
   int32_t res_ld, res_mod, res_dtype;
@@ -92,6 +95,8 @@ typedef struct dcb_gemm_desc {
 } dcb_gemm_desc;
 
 int dcb_gemm(const dcb_gemm_desc* d, dcb_stream stream);
+/* *supported = 1 when dcb_gemm(d) would fill d->gn_part (tcgen05 engine, staged bf16 epilogue); rows per tile = 128 */
+int dcb_gemm_gn_layout(const dcb_gemm_desc* d, int32_t* supported);
 /* rows covered by one mse_part entry for descriptor d (128 for tcgen05, 64 for SIMT), and n-tile count */
 int dcb_gemm_mse_layout(const dcb_gemm_desc* d, int32_t* rows_per_part, int32_t* n_tiles);
 /* err[s] (+)= sum of parts_per_sample consecutive partials (fixed order => deterministic) */
@@ -108,6 +113,11 @@ int dcb_groupnorm_stats(int dtype, const void* x0, int C0, const void* x1, int C
 int dcb_groupnorm_apply(int dtype, const void* x0, int C0, const void* x1, int C1, int NB, int HW, int G, int chunks,
                         const float* part, const float* gamma, const float* beta, float eps, int silu, void* out,
                         dcb_stream stream);
+/* statistics pass replaced by a reduction of producer-written tile partials (dcb_gemm_desc.gn_part):
+ * part0/part1: [n_src*tiles_per_sample][C][2] per source (part1 NULL when C1 == 0), sample n reads source sample n/div;
+ * writes part_out[NB][1][G][2] = (sum, sumsq) per group, i.e. the `part` of dcb_groupnorm_apply with chunks = 1 */
+int dcb_groupnorm_stats_from_tiles(const float* part0, int C0, int div0, const float* part1, int C1, int div1, int NB,
+                                   int tiles_per_sample, int G, float* part_out, dcb_stream stream);
 /* same, with per-source sample divisors: sample n reads x0[n / div0] and x1[n / div1] (see dcb_seg.nb_div) */
 int dcb_groupnorm_stats_div(int dtype, const void* x0, int C0, int div0, const void* x1, int C1, int div1, int NB, int HW,
                             int G, int chunks, float* part, dcb_stream stream);

@@ -266,3 +266,39 @@ def test_tc_unit_source_needs_single_sample_tiles(dev):
     w = _bf(64, 64, dev=dev)
     with pytest.raises(L.DcbError):
         E.gemm(_ctx(dev, L.ENGINE_TCGEN05), [E.seg(x, 64, 8, 8, nb_div=2)], w, 64, 4, 8, 8)
+
+
+@pytest.mark.parametrize("NB,H,W,Ci,Co,res", [(3, 16, 16, 128, 128, True), (2, 128, 128, 64, 128, False),
+                                              (5, 32, 32, 64, 256, True), (9, 128, 128, 64, 64, False)])
+def test_tc_epilogue_groupnorm_tile_statistics(dev, NB, H, W, Ci, Co, res):
+    """dcb_gemm_desc.gn_part: the staged epilogue's per-tile (sum, sumsq) of the bf16 values it stores, and GroupNorm
+    fed from them (dcb_groupnorm_stats_from_tiles) vs GroupNorm with its own statistics pass over the same tensor."""
+    from dcb200 import engine as E
+    torch.manual_seed(0)
+    ctx = _ctx(dev)
+    HW = H * W
+    x = _bf(NB, H, W, Ci, dev=dev)
+    w = (torch.randn(Co, 9 * Ci, device=dev) * 0.05).to(torch.bfloat16)
+    b = torch.randn(Co, device=dev)
+    r = _bf(NB * HW, Co, dev=dev) if res else None
+    out, part = E.gemm(ctx, E.conv3x3_segs(x, Ci, H, W), w, Co, NB, H, W, bias=b, residual=r, res_ld=Co, gn_stats=True)
+    plain = E.gemm(ctx, E.conv3x3_segs(x, Ci, H, W), w, Co, NB, H, W, bias=b, residual=r, res_ld=Co)
+    assert torch.equal(out, plain), "asking for statistics must not change the output"
+    assert part is not None and part.shape == (NB * HW // 128, Co, 2)
+    tps = HW // 128
+    # per-sample, per-channel totals (tile -> pixel assignment is a box, so compare after summing a sample's tiles)
+    got = part.reshape(NB, tps, Co, 2).double().sum(1)
+    o = out.reshape(NB, HW, Co).double()
+    assert rel_err(got[..., 0], o.sum(1)) < 1e-5 and rel_err(got[..., 1], (o * o).sum(1)) < 1e-5
+    g, be = torch.randn(Co, device=dev), torch.randn(Co, device=dev)
+    a = E.groupnorm(ctx, out, Co, None, 0, NB, HW, g, be, 1e-5, True, st0=part)
+    ref = E.groupnorm(ctx, out, Co, None, 0, NB, HW, g, be, 1e-5, True)
+    assert rel_err(a, ref) < 2e-3 and (a.float() - ref.float()).abs().max() < 0.07   # bf16 ulps where rounding flips
+    # concatenated sources, one of them per unit
+    rep = 1 if NB % 3 else 3
+    sk = _bf(NB // rep, H, W, Ci, dev=dev)
+    sk_out, sk_part = E.gemm(ctx, [E.seg(sk, Ci, H, W)], w[:, :Ci].contiguous(), Co, NB // rep, H, W, bias=b, gn_stats=True)
+    g2, b2 = torch.randn(2 * Co, device=dev), torch.randn(2 * Co, device=dev)
+    a = E.groupnorm(ctx, out, Co, sk_out, Co, NB, HW, g2, b2, 1e-5, True, div1=rep, st0=part, st1=sk_part)
+    ref = E.groupnorm(ctx, out, Co, sk_out, Co, NB, HW, g2, b2, 1e-5, True, div1=rep)
+    assert rel_err(a, ref) < 2e-3
