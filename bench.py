@@ -34,6 +34,7 @@ WORKLOADS = {
     # name: (arch key in tests/helpers.py, classes, timesteps, GFLOP/eval, images per GPU per step)
     "unet128": ("UNET128", 2, 100, 175.79, 4),
     "cifar": ("CIFAR_UNET", 10, 32, 10.454, 16),
+    "dit": ("DIT_B4_256", 2, 25, 1315.0, 1),     # BASELINE configs[3]: CheXpert-256 DiT-B/4 (attention + adaLN kernels)
 }
 
 
@@ -44,6 +45,8 @@ def build_workload(name):
     S = arch["sample_size"]
     cfg = helpers.base_cfg(classes=classes, evaluation_per_stage=[T], n_stages=1, n_keep_per_stage=[1], noise_d=S,
                            image_size=S, schedule="cosine", pred_param="eps")
+    if name == "dit":
+        cfg.encoder_type = "DiT"
     return arch, cfg, classes, T, gflop, ipg
 
 
@@ -119,7 +122,7 @@ def run_reference(args):
         return
     arch, cfg, classes, T, gflop, ipg = build_workload(args.workload)
     threads = len(os.sched_getaffinity(0))
-    n_t = 4 if args.workload == "unet128" else 8
+    n_t = 16 if args.workload == "unet128" else 8
     for _ in range(args.warmup):
         cpu_port_run(arch, cfg, 1, 1, threads)
     vals, times = [], []
@@ -145,7 +148,9 @@ def workload_name(w, classes, T):
     return {"unet128": f"unet-128 class-conditional U-Net (models/unet-128.py) ELBO scoring, {classes} classes x {T} "
                        f"timesteps, 3x128x128",
             "cifar": f"CIFAR-10 32x32 class-conditional U-Net (experiments/cifar10) ELBO classification, {classes} "
-                     f"classes x {T} timesteps"}[w]
+                     f"classes x {T} timesteps",
+            "dit": f"CheXpert 256x256 DiT-B/4 (models/chexpert-256-dit-b4) ELBO classification, {classes} classes x {T} "
+                   f"timesteps"}[w]
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -168,7 +173,7 @@ def run_ours(args):
     if args.max_batch:
         cfg.dcb_max_batch = args.max_batch
     torch.manual_seed(0)
-    net = dcb200.UNetCondition2D(**arch)
+    net = (dcb200.DiT if args.workload == "dit" else dcb200.UNetCondition2D)(**arch)
     dc = dcb200.DiffusionClassifier(net, cfg).to(dev).eval()
     S, C = arch["sample_size"], arch["in_channels"]
     g = torch.Generator().manual_seed(0)
@@ -253,7 +258,7 @@ def run_ours(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         threads = len(os.sched_getaffinity(0))
-        n_t = 4 if args.workload == "unet128" else 8
+        n_t = 32 if args.workload == "unet128" else 8
         cpu_port_run(arch, cfg, 1, 1, threads)
         v, dt = cpu_port_run(arch, cfg, 1, n_t, threads)
         cpu = {"value": v, "unit": "evals/s", "cores": threads, "kind": "port", "seconds": dt,

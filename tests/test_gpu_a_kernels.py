@@ -250,3 +250,24 @@ def test_groupnorm_unit_divisor_and_expand(dev, dt):
     a = E.groupnorm(ctx, sk, C1, None, 0, S, HW, g[:C1].contiguous(), b[:C1].contiguous(), 1e-6, False, div0=rep)
     r = E.groupnorm(ctx, ex, C1, None, 0, S, HW, g[:C1].contiguous(), b[:C1].contiguous(), 1e-6, False)
     assert torch.equal(a, r)
+
+
+@pytest.mark.parametrize("B,heads,N", [(2, 3, 128), (1, 2, 256), (2, 12, 300), (1, 8, 4096), (3, 1, 1000)])
+def test_attention_tcgen05_head64(dev, B, heads, N):
+    """the tcgen05/TMEM flash kernel (d = 64, N >= 128: DiT-B/4 and the C/8 = 64 U-Net blocks) against torch SDPA in
+    fp32 on the same bf16 inputs, against the mma.sync kernel it replaces, and for ragged N (masked last key block,
+    partially empty query tiles).  Inputs with large logits exercise the running-max rescale."""
+    import os
+    from dcb200 import engine as E
+    torch.manual_seed(N)
+    d = 64
+    qkv = torch.randn(B * N, 3 * heads * d, device=dev)
+    qkv[:, : heads * d] *= 3.0          # sharper softmax: the maximum moves between key blocks
+    qb = qkv.to(torch.bfloat16)
+    q, k, v = (t.float().reshape(B, N, heads, d).transpose(1, 2) for t in qb.chunk(3, -1))
+    ref = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B * N, heads * d)
+    out = E.attention(_ctx(dev, "bf16"), qb, B, N, heads, d).float()
+    assert torch.isfinite(out).all()
+    assert rel_err(out, ref) < 1e-2
+    simt = E.attention(_ctx(dev, "bf16"), qb, B, N, heads, d, simt=True).float()
+    assert rel_err(out, simt) < 1e-2
