@@ -9,14 +9,19 @@
 //                 S_t = Q_t K_j^T      tcgen05.mma SS, M=128 N=128 K=64   -> TMEM S_t (fp32)
 //                 O_t = P_t V_j        tcgen05.mma TS: A = P_t straight from TMEM (bf16 pairs), B = V_j as an MN-major
 //                                      128B-swizzled smem operand (the [token][channel] box TMA delivers), N=64 K=128
-//   warps 2-9 / 10-17 softmax group of tile 0 / 1: one TMEM lane = one query row, shared by TWO threads (warps w, w+4:
-//                 keys 0-63 / 64-127 of the block, channels 0-31 / 32-63 of O) so that 4 warps per scheduler overlap
-//                 their MUFU, FMA and tcgen05.ld phases; the halves exchange their block maximum through smem:
-//                 one pass over S per key block: P = exp2((S - R) c) against the lagged running maximum R -> bf16 pairs ->
-//                 tcgen05.st into TMEM; the PV product of the previous block is folded into fp32 register accumulators
-//                 while the tensor pipe already runs the next QK^T, so nothing is ever rescaled in TMEM and the N x N
-//                 scores never exist in HBM.
+//   warps 2-5 / 6-9   softmax group of tile 0 / 1, one TMEM lane = one query row per thread (no shuffles):
+//                 pass 1 row max of S, pass 2 P = exp2(S*c - m*c) -> bf16 -> tcgen05.st into TMEM; the PV product of the
+//                 previous block is folded into fp32 register accumulators (O = O*alpha + O_j) while the tensor pipe
+//                 already runs the next QK^T, so nothing is ever rescaled in TMEM and the N x N scores never exist in HBM.
 // TMEM columns: S0 [0,128) S1 [128,256) P0 [256,320) P1 [320,384) O0 [384,448) O1 [448,512).
+//
+// Roofline at d = 64: 128 x 128 exponentials per key block and tile = 1024 cycles of MUFU (16 ex2/clk/SM) against 768
+// cycles of tensor pipe (QK^T 256 + PV 512 at the N = 64 half rate), and ~4 issue slots per score on the 4 schedulers
+// (~1000 cycles): the kernel is bound by the softmax warps, not by the tensor pipe or by L2.  Measured (ncu, DiT-B/4
+// shape): MUFU pipe 55 %, issue slots 41 %, tensor pipe 26 % busy -> 614 TF/s.  Variants tried and measured NOT faster
+// (tools/attn_micro.py, git history): single-pass softmax with a lagged running maximum; 2 or 4 threads per query row
+// (needs a per-block max exchange, which locks the warps of a scheduler in step); one tile per CTA with S, P and O all
+// double buffered; K/V shared by 2 / 4 CTAs through TMA multicast (L2 -> SMEM is not the limit: 9.7 TB/s measured).
 #include <cudaTypedefs.h>
 
 #include <mutex>
@@ -25,7 +30,7 @@
 
 namespace dcb {
 
-constexpr int AT_THREADS = 576;  // TMA warp, MMA warp, 2 query tiles x 2 column halves x 4 softmax warps
+constexpr int AT_THREADS = 320;
 constexpr int AT_KV_STAGES = 4;
 constexpr int AT_TILE_BYTES = 128 * 64 * 2;  // one [128 tokens x 64 ch] bf16 box
 
@@ -66,11 +71,6 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
         "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
-__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
-               "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
-               : "memory");
-}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ float ex2f(float x) {
   float y;
@@ -103,7 +103,6 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
   uint64_t* p_full = s_full + 2;                 // [2]  softmax -> MMA: P_t(j) written, S_t and O_t free again
   uint64_t* o_full = p_full + 2;                 // [2]  MMA -> softmax: O_t(j) = P_t(j) V_j complete
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
-  float* xch = reinterpret_cast<float*>(bars + 32);   // [2 parities + 1][2 tiles][2 halves][128 rows] block maxima / row sums
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
@@ -123,7 +122,7 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
     }
     for (int t = 0; t < 2; ++t) {
       mbar_init(smem_u32(&s_full[t]), 1);
-      mbar_init(smem_u32(&p_full[t]), 8);  // one arrive per softmax warp of the group
+      mbar_init(smem_u32(&p_full[t]), 4);  // one arrive per softmax warp of the group
       mbar_init(smem_u32(&o_full[t]), 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -229,116 +228,100 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
     }
   } else {
     // ===================== softmax groups =====================
-    const int t = (warp - 2) >> 3;          // query tile of this group
-    const int hf = ((warp - 2) >> 2) & 1;   // column half: keys [64 hf, 64 hf + 64) of a block, channels [32 hf, 32 hf + 32)
+    const int t = (warp - 2) >> 2;          // query tile of this group
     const int qd = warp & 3;                // TMEM lane quarter
     const int r = qd * 32 + lane;           // query row inside the tile == TMEM lane
-    const int bar_id = 1 + t;               // named barrier of the group (256 threads)
     const uint32_t lane_addr = tmem_base + ((uint32_t)(qd * 32) << 16);
-    const uint32_t s_addr = lane_addr + (uint32_t)(t * 128 + hf * 64);
-    const uint32_t p_addr = lane_addr + (uint32_t)(256 + t * 64 + hf * 32);
-    const uint32_t o_addr = lane_addr + (uint32_t)(384 + t * 64 + hf * 32);
-    float* my_x = xch + (t * 2 + hf) * 128 + r;            // this thread's exchange slot
-    const float* other_x = xch + (t * 2 + (hf ^ 1)) * 128 + r;
-    float o[32];
+    const uint32_t s_addr = lane_addr + (uint32_t)(t * 128);
+    const uint32_t p_addr = lane_addr + (uint32_t)(256 + t * 64);
+    const uint32_t o_addr = lane_addr + (uint32_t)(384 + t * 64);
+    float o[64];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) o[i] = 0.f;
-    // Single pass per key block with a LAGGED reference maximum R (the running max of the previous blocks):
-    //   P_j = exp2((S_j - R_j) c),  O_j = P_j V_j,  then  R_{j+1} = max(R_j, max S_j),  beta_j = exp2((R_j - R_{j+1}) c)
-    //   l <- (l + rowsum P_j) beta_j      o <- (o + O_{j-1}) beta_{j-1}   (O is folded one block late, see the header)
-    // which is the online softmax with every quantity of block j expressed relative to R_j instead of R_{j+1}; P may
-    // exceed 1 by 2^(max S_j - R_j) -- harmless in bf16/fp32 below 2^40, and if a row would exceed that (always the case
-    // for the first block, where R = -inf) both halves first move R up to the block maximum and redo the block.
-    float R = -1e30f, l = 0.f, beta_prev = 1.f;
+    for (int i = 0; i < 64; ++i) o[i] = 0.f;
+    float m = -1e30f, l = 0.f, alpha_prev = 1.f;
     const float sc = p.sc;
     for (int j = 0; j < p.nblk; ++j) {
       mbar_wait(s_full0 + t * 8, (uint32_t)(j & 1));
       tc_fence_after();
-      const int valid = p.N - j * 128 - hf * 64;   // keys of this half block that exist (>= 64: all)
-      uint32_t sv[16];
-      // ---- fold the previous block's P V into the register accumulators; also frees P_t and O_t for this block ----
+      const int valid = p.N - j * 128;       // keys of this block that exist (>= 128: all)
+      // ---- pass 1: row max ----
+      float mx = -1e30f;
+#pragma unroll
+      for (int c = 0; c < 128; c += 32) {
+        uint32_t sv[32];
+        tmem_ld32_nowait(s_addr + (uint32_t)c, sv);
+        tmem_ld_wait();
+        if (valid >= 128) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(sv[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c + i < valid) mx = fmaxf(mx, __uint_as_float(sv[i]));
+        }
+      }
+      const float m_new = fmaxf(m, mx);
+      const float alpha = ex2f((m - m_new) * sc);
+      const float msc = m_new * sc;
+      m = m_new;
+      // ---- fold the previous block's P V into the register accumulators (its MMAs finished long ago) ----
       if (j > 0) {
         mbar_wait(o_full0 + t * 8, (uint32_t)((j - 1) & 1));
         tc_fence_after();
 #pragma unroll
-        for (int c = 0; c < 32; c += 16) {
-          tmem_ld16_nowait(o_addr + (uint32_t)c, sv);
+        for (int c = 0; c < 64; c += 32) {
+          uint32_t ov[32];
+          tmem_ld32_nowait(o_addr + (uint32_t)c, ov);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 16; ++i) o[c + i] = (o[c + i] + __uint_as_float(sv[i])) * beta_prev;
+          for (int i = 0; i < 32; ++i) o[c + i] = fmaf(o[c + i], alpha_prev, __uint_as_float(ov[i]));
         }
       }
-      float rs = 0.f, mx = -1e30f;
-      auto pass = [&](float rsc) {
-        rs = 0.f;
-        mx = -1e30f;
+      alpha_prev = alpha;
+      // ---- pass 2: P = exp2(S*c - m*c) -> bf16 pairs -> TMEM ----
+      float rs = 0.f;
 #pragma unroll
-        for (int c = 0; c < 64; c += 16) {
-          tmem_ld16_nowait(s_addr + (uint32_t)c, sv);
-          tmem_ld_wait();
-          uint32_t pk[8];
+      for (int c = 0; c < 128; c += 32) {
+        uint32_t sv[32];
+        tmem_ld32_nowait(s_addr + (uint32_t)c, sv);
+        tmem_ld_wait();
+        uint32_t pk[16];
 #pragma unroll
-          for (int i = 0; i < 16; i += 2) {
-            const float s0 = __uint_as_float(sv[i]), s1 = __uint_as_float(sv[i + 1]);
-            float p0 = ex2f(fmaf(s0, sc, -rsc));
-            float p1 = ex2f(fmaf(s1, sc, -rsc));
-            if (valid >= 64) {
-              mx = fmaxf(mx, fmaxf(s0, s1));
-            } else {
-              if (c + i < valid) mx = fmaxf(mx, s0); else p0 = 0.f;
-              if (c + i + 1 < valid) mx = fmaxf(mx, s1); else p1 = 0.f;
-            }
-            rs += p0 + p1;
-            pk[i >> 1] = pack_bf16x2(p0, p1);
+        for (int i = 0; i < 32; i += 2) {
+          float p0 = ex2f(fmaf(__uint_as_float(sv[i]), sc, -msc));
+          float p1 = ex2f(fmaf(__uint_as_float(sv[i + 1]), sc, -msc));
+          if (valid < 128) {
+            if (c + i >= valid) p0 = 0.f;
+            if (c + i + 1 >= valid) p1 = 0.f;
           }
-          tmem_st8(p_addr + (uint32_t)(c >> 1), pk);
+          rs += p0 + p1;
+          pk[i >> 1] = pack_bf16x2(p0, p1);
         }
-      };
-      pass(R * sc);
-      // the two halves of a row agree on the block maximum (and therefore on R and on the redo decision)
-      my_x[(j & 1) * 512] = mx;
-      asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
-      float bm = fmaxf(mx, other_x[(j & 1) * 512]);
-      if (__any_sync(0xffffffffu, (bm - R) * sc > 40.f)) {
-        const float Rn = fmaxf(R, bm);
-        const float g = ex2f((R - Rn) * sc);
-        l *= g;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[i] *= g;
-        R = Rn;
-        tmem_st_wait();
-        pass(R * sc);
+        tmem_st16(p_addr + (uint32_t)(c >> 1), pk);
       }
-      const float Rn = fmaxf(R, bm);
-      const float beta = ex2f((R - Rn) * sc);
-      l = (l + rs) * beta;
-      beta_prev = beta;
-      R = Rn;
+      l = fmaf(l, alpha, rs);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full0 + t * 8);
     }
-    // last block's product, and the other half's share of the row sum
-    my_x[1024] = l;
-    asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
-    l += other_x[1024];
+    // last block's product
     mbar_wait(o_full0 + t * 8, (uint32_t)((p.nblk - 1) & 1));
     tc_fence_after();
     const float inv = 1.f / l;
     const int qrow = q0 + t * 128 + r;
-    __nv_bfloat16* orow = out + ((int64_t)b * p.N + qrow) * p.out_ld + h * 64 + hf * 32;
+    __nv_bfloat16* orow = out + ((int64_t)b * p.N + qrow) * p.out_ld + h * 64;
 #pragma unroll
-    for (int c = 0; c < 32; c += 16) {
-      uint32_t ov[16];
-      tmem_ld16_nowait(o_addr + (uint32_t)c, ov);
+    for (int c = 0; c < 64; c += 32) {
+      uint32_t ov[32];
+      tmem_ld32_nowait(o_addr + (uint32_t)c, ov);
       tmem_ld_wait();
-      float v[16];
+      float v[32];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = (o[c + i] + __uint_as_float(ov[i])) * beta_prev * inv;
+      for (int i = 0; i < 32; ++i) v[i] = fmaf(o[c + i], alpha_prev, __uint_as_float(ov[i])) * inv;
       if (qrow < p.N) {
-        *reinterpret_cast<uint4*>(orow + c) = pack_bf16x8(v);
-        *reinterpret_cast<uint4*>(orow + c + 8) = pack_bf16x8(v + 8);
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) *reinterpret_cast<uint4*>(orow + c + i) = pack_bf16x8(v + i);
       }
     }
   }
@@ -379,7 +362,7 @@ int launch_flash_tc(const void* q, const void* k, const void* v, int ld, int B, 
   p.nblk = (N + 127) / 128;
   p.sc = scale * 1.4426950408889634f;
   p.out_ld = out_ld;
-  const size_t smem = 1024 + (2 + 2 * AT_KV_STAGES) * AT_TILE_BYTES + 256 + 3 * 512 * 4;
+  const size_t smem = 1024 + (2 + 2 * AT_KV_STAGES) * AT_TILE_BYTES + 256;
   static std::once_flag once;
   std::call_once(once, [] {
     cudaFuncSetAttribute(flash_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT);

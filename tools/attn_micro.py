@@ -1,0 +1,22 @@
+"""micro-benchmark of the attention kernel at the DiT-B/4 shape (B x 12 heads x 4096 tokens x 64) through the C ABI."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "diffusion-classifier_b200"), os.path.join(ROOT, "tests")):
+    sys.path.insert(0, p)
+import torch
+from dcb200 import engine as E
+dev = torch.device("cuda:0")
+ctx = E.Ctx(device=dev, precision="bf16")
+B, heads, N, d = int(os.environ.get("AB", 16)), 12, int(os.environ.get("AN", 4096)), 64
+qkv = torch.randn(B * N, 3 * heads * d, device=dev).to(torch.bfloat16)
+fl = 4.0 * B * heads * N * N * d
+for dbg in os.environ.get("DBG_SWEEP", "0").split(","):
+    os.environ["DCB_ATTN_DBG"] = dbg
+    for _ in range(3): E.attention(ctx, qkv, B, N, heads, d)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10): E.attention(ctx, qkv, B, N, heads, d)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    print(f"attention B={B} N={N} dbg={dbg} tc={os.environ.get('DCB_ATTN_TC','1')}: {ms:.3f} ms  {fl/ms/1e9:.1f} TF/s")
