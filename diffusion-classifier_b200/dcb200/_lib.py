@@ -44,6 +44,7 @@ _PROTOS = {
                              c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "dcb_timestep_embed": (c_int, [c_int, c_void_p, c_int, c_int, c_int, c_float, c_float, c_void_p, c_void_p]),
     "dcb_gemm": (c_int, [C.POINTER(GemmDesc), c_void_p]),
+    "dcb_struct_size": (c_int, [c_int]),
     "dcb_gemm_mse_layout": (c_int, [C.POINTER(GemmDesc), C.POINTER(c_i32), C.POINTER(c_i32)]),
     "dcb_gemm_gn_layout": (c_int, [C.POINTER(GemmDesc), C.POINTER(c_i32)]),
     "dcb_groupnorm_stats_from_tiles": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
@@ -91,6 +92,8 @@ def lib():
         for name, (res, args) in _PROTOS.items():
             fn = getattr(L, name)  # AttributeError here == ABI drift
             fn.restype, fn.argtypes = res, args
+        if L.dcb_struct_size(0) != C.sizeof(Seg) or L.dcb_struct_size(1) != C.sizeof(GemmDesc):
+            raise ImportError("dcb200: ctypes struct layout does not match libdcb200.so (rebuild the extension)")
         _lib = L
     return _lib
 

@@ -87,6 +87,8 @@ extern "C" const char* dcb_last_error(void) { return g_err; }
 extern "C" int64_t dcb_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 extern "C" void dcb_note_graph_replay(int64_t n_kernels) { g_launches.fetch_add(n_kernels, std::memory_order_relaxed); }
 
+extern "C" int dcb_struct_size(int which) { return which == 0 ? (int)sizeof(dcb_seg) : (int)sizeof(dcb_gemm_desc); }
+
 extern "C" int dcb_gemm(const dcb_gemm_desc* d, dcb_stream stream) {
   GemmDev g;
   int rc = to_dev(d, &g);

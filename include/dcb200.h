@@ -95,6 +95,8 @@ typedef struct dcb_gemm_desc {
 } dcb_gemm_desc;
 
 int dcb_gemm(const dcb_gemm_desc* d, dcb_stream stream);
+/* sizeof(dcb_seg) (which = 0) / sizeof(dcb_gemm_desc) (which = 1) as compiled: lets a binding check its struct layout */
+int dcb_struct_size(int which);
 /* *supported = 1 when dcb_gemm(d) would fill d->gn_part (tcgen05 engine, staged bf16 epilogue); rows per tile = 128 */
 int dcb_gemm_gn_layout(const dcb_gemm_desc* d, int32_t* supported);
 /* rows covered by one mse_part entry for descriptor d (128 for tcgen05, 64 for SIMT), and n-tile count */
