@@ -48,6 +48,39 @@ __device__ __forceinline__ float apply_act(int act, float v) {
   return v;
 }
 
+// ---- activations of the bf16 staged epilogue: one MUFU op each.  Their approximation error (tanh.approx: 2^-11
+// relative; erf: Abramowitz-Stegun 7.1.26, 1.5e-7 absolute) is far below the bf16 rounding of the stored result; the
+// fp32-verify engine keeps the exact forms above.
+__device__ __forceinline__ float tanh_approx_f(float x) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x));
+  return t;
+}
+__device__ __forceinline__ float silu_fast_f(float x) { return x * fmaf(0.5f, tanh_approx_f(0.5f * x), 0.5f); }
+__device__ __forceinline__ float gelu_tanh_fast_f(float x) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f * 0.7978845608028654f;
+  const float u = x * fmaf(k1, x * x, k0);
+  const float hx = 0.5f * x;
+  return fmaf(hx, tanh_approx_f(u), hx);
+}
+__device__ __forceinline__ float gelu_erf_fast_f(float x) {
+  // erf(|z|) = 1 - (a1 t + a2 t^2 + a3 t^3 + a4 t^4 + a5 t^5) exp(-z^2),  t = 1 / (1 + 0.3275911 |z|)
+  const float z = fabsf(x) * 0.7071067811865476f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float e = poly * t * __expf(-z * z);          // 1 - erf(|z|)
+  const float erf_abs = 1.0f - e;
+  return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+}
+__device__ __forceinline__ float apply_act_fast(int act, float v) {
+  if (act == DCB_ACT_SILU) return silu_fast_f(v);
+  if (act == DCB_ACT_GELU_TANH) return gelu_tanh_fast_f(v);
+  return v;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

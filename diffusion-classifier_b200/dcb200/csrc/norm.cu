@@ -244,7 +244,9 @@ static int gn_check(int dtype, int C0, int C1, int G, const void* x1) {
   return DCB_OK;
 }
 
-// ---- LayerNorm: one warp per row, row cached in registers ---------------------------------------------------
+// ---- LayerNorm: one warp per row, row cached in registers; per-channel coefficients by 16-byte loads -------------
+// (measured: keeping the coefficients in registers across several rows per warp costs occupancy and is slower)
+constexpr int LN_ROWS = 1;
 template <typename T>
 __global__ void __launch_bounds__(256) layernorm_kernel(const T* __restrict__ x, int64_t rows, int C,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -257,6 +259,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const T* __restrict__ x,
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int V = C / VN;
+  const float inv_c = 1.f / (float)C;
   const T* xr = x + row * C;
   float buf[MAXV][VN];
   float s = 0.f;
@@ -269,7 +272,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const T* __restrict__ x,
       for (int i = 0; i < VN; ++i) s += buf[j][i];
     }
   }
-  const float mean = warp_sum(s) / (float)C;
+  const float mean = warp_sum(s) * inv_c;
   float q = 0.f;
 #pragma unroll
   for (int j = 0; j < MAXV; ++j) {
@@ -279,8 +282,10 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const T* __restrict__ x,
       for (int i = 0; i < VN; ++i) { float d = buf[j][i] - mean; q = fmaf(d, d, q); }
     }
   }
-  const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+  const float rstd = rsqrtf(warp_sum(q) * inv_c + eps);
   const int64_t grp = rows_per_group > 0 ? row / rows_per_group : 0;
+  const float* sp = scale ? scale + grp * mod_ld : nullptr;
+  const float* hp = scale ? shift + grp * mod_ld : nullptr;
   T* orow = out + row * C;
 #pragma unroll
   for (int j = 0; j < MAXV; ++j) {
@@ -288,11 +293,24 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const T* __restrict__ x,
     if (v < V) {
       const int c = v * VN;
 #pragma unroll
-      for (int i = 0; i < VN; ++i) {
-        float y = (buf[j][i] - mean) * rstd;
-        if (gamma) y = y * gamma[c + i] + (beta ? beta[c + i] : 0.f);
-        if (scale) y = y * (1.f + scale[grp * mod_ld + c + i]) + shift[grp * mod_ld + c + i];
-        buf[j][i] = y;
+      for (int i = 0; i < VN; i += 4) {
+        float y[4] = {(buf[j][i] - mean) * rstd, (buf[j][i + 1] - mean) * rstd, (buf[j][i + 2] - mean) * rstd,
+                      (buf[j][i + 3] - mean) * rstd};
+        if (gamma) {
+          const float4 g4 = *reinterpret_cast<const float4*>(gamma + c + i);
+          y[0] *= g4.x; y[1] *= g4.y; y[2] *= g4.z; y[3] *= g4.w;
+        }
+        if (beta) {
+          const float4 b4 = *reinterpret_cast<const float4*>(beta + c + i);
+          y[0] += b4.x; y[1] += b4.y; y[2] += b4.z; y[3] += b4.w;
+        }
+        if (sp) {
+          const float4 s4 = *reinterpret_cast<const float4*>(sp + c + i);
+          const float4 h4 = *reinterpret_cast<const float4*>(hp + c + i);
+          y[0] = fmaf(y[0], 1.f + s4.x, h4.x); y[1] = fmaf(y[1], 1.f + s4.y, h4.y);
+          y[2] = fmaf(y[2], 1.f + s4.z, h4.z); y[3] = fmaf(y[3], 1.f + s4.w, h4.w);
+        }
+        buf[j][i] = y[0]; buf[j][i + 1] = y[1]; buf[j][i + 2] = y[2]; buf[j][i + 3] = y[3];
       }
       Vec<T>::store(orow + c, buf[j]);
     }
@@ -358,9 +376,13 @@ extern "C" int dcb_layernorm(int dtype, const void* x, int64_t rows, int C, cons
   const int vn = dtype == DCB_BF16 ? 8 : 4;
   DCB_REQUIRE(C % vn == 0 && C <= 1024, "layernorm: need C %% %d == 0 and C <= 1024 (C=%d)", vn, C);
   DCB_REQUIRE((scale == nullptr) == (shift == nullptr), "layernorm: scale/shift must come together");
+  DCB_REQUIRE((((uintptr_t)gamma | (uintptr_t)beta | (uintptr_t)scale | (uintptr_t)shift) & 15) == 0 &&
+                  (scale == nullptr || mod_ld % 4 == 0),
+              "layernorm: gamma/beta/scale/shift must be 16-byte aligned (mod_ld %% 4 == 0)");
   cudaStream_t st = (cudaStream_t)stream;
   const int wpb = 8;
-  const unsigned grid = (unsigned)((rows + wpb - 1) / wpb);
+  const int64_t warps = (rows + LN_ROWS - 1) / LN_ROWS;
+  const unsigned grid = (unsigned)((warps + wpb - 1) / wpb);
   if (dtype == DCB_BF16)
     layernorm_kernel<__nv_bfloat16><<<grid, wpb * 32, 0, st>>>((const __nv_bfloat16*)x, rows, C, gamma, beta, eps, scale,
                                                                shift, mod_ld, rows_per_group, (__nv_bfloat16*)out);

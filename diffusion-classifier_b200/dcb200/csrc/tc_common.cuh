@@ -252,7 +252,7 @@ __device__ __forceinline__ void staged_epilogue(const EpiGeom& gq, const EpiDev&
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         float a = __uint_as_float(ra[i]) + s_bias[c + i];
-        if (geglu) a *= gelu_erf_f(__uint_as_float(rg[i]) + s_bias[128 + c + i]);
+        if (geglu) a *= gelu_erf_fast_f(__uint_as_float(rg[i]) + s_bias[128 + c + i]);
         v[i] = a;
       }
       if (e.rowvec) {
@@ -268,7 +268,7 @@ __device__ __forceinline__ void staged_epilogue(const EpiGeom& gq, const EpiDev&
       }
       if (e.act == DCB_ACT_SILU || e.act == DCB_ACT_GELU_TANH) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = apply_act(e.act, v[i]);
+        for (int i = 0; i < 16; ++i) v[i] = apply_act_fast(e.act, v[i]);
       }
       if (e.gate) {
         if (gq.uniform) {
@@ -294,7 +294,7 @@ __device__ __forceinline__ void staged_epilogue(const EpiGeom& gq, const EpiDev&
       }
       if (e.act_post != DCB_ACT_NONE) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = apply_act(e.act_post, v[i]);
+        for (int i = 0; i < 16; ++i) v[i] = apply_act_fast(e.act_post, v[i]);
       }
       *s0 = pack_bf16x8(v);
       *s1 = pack_bf16x8(v + 8);

@@ -43,6 +43,14 @@ for c in cases:
         w = (torch.randn(Co, 9 * Ci, device=dev) * 0.05).to(torch.bfloat16)
         fn = lambda: E.gemm(ctx, E.conv3x3_segs(x, Ci, H, W), w, Co, NB, H, W)
         fl = 2.0 * NB * H * W * Co * 9 * Ci
+    elif c.startswith("mkn"):       # mkn<M>x<K>x<N>[:act]  generic linear layer
+        M, K, N = (int(v) for v in c[3:].split(":")[0].split("x"))
+        x = torch.randn(M, K, device=dev).to(torch.bfloat16)
+        w = (torch.randn(N, K, device=dev) * 0.05).to(torch.bfloat16)
+        b = torch.randn(N, device=dev)
+        act = 2 if c.endswith(":gelu") else 0
+        fn = lambda: E.linear(ctx, x, w, N, bias=b, act=act)
+        fl = 2.0 * M * N * K
     else:
         N = int(c[3:])
         K = 1152
