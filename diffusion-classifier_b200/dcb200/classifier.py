@@ -166,7 +166,9 @@ class DiffusionClassifier(nn.Module):
         v = getattr(self.config, "dcb_max_batch", None)
         if v:
             return int(v)
-        return int(os.environ.get("DCB_MAX_BATCH", max(1, min(1024, (1 << 22) // (H * W)))))
+        # ~16 M pixels of denoiser batch per launch sequence (1024 samples at 128^2: the 8^2 / 16^2 layers then fill all 148
+        # SMs; peak activation footprint ~40 GB of the 180 GB)
+        return int(os.environ.get("DCB_MAX_BATCH", max(1, min(2048, (1 << 24) // (H * W)))))
 
     # ---- the hot path ---------------------------------------------------------------------------------------------
     @torch.no_grad()
