@@ -16,7 +16,7 @@
 
 namespace dcb {
 
-constexpr int T2_THREADS = 320;  // TMA warp, MMA warp, 2 epilogue groups x 4 warps (group g drains sub-tile g)
+constexpr int T2_THREADS = 352;  // TMA warp, 2 MMA warps (one per sub-tile), 2 epilogue groups x 4 warps (group g drains sub-tile g)
 constexpr int T2_MAX_SLOTS = 8;
 constexpr int T2_HALO_SUB = 17 * 1024;  // 130 rows x 128 B = 16640 B, padded to the 1024-B swizzle repeat
 
@@ -66,9 +66,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
   uint64_t* a_empty = bars + T2_MAX_SLOTS;
   uint64_t* b_full = bars + 2 * T2_MAX_SLOTS;
   uint64_t* b_empty = bars + 3 * T2_MAX_SLOTS;
-  uint64_t* tfull_bar = bars + 4 * T2_MAX_SLOTS;
-  uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* tfull_bar = bars + 4 * T2_MAX_SLOTS;   // [2 TMEM stages][2 sub-tiles]
+  uint64_t* tempty_bar = tfull_bar + 4;            // [2 TMEM stages][2 sub-tiles]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 4);
   uint8_t* stg8 = reinterpret_cast<uint8_t*>(bars) + 512;
 
   // warp-uniform role dispatch (see gemm_tc.cu): loop state and descriptors stay in uniform registers
@@ -76,9 +76,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&mapA0);
     prefetch_tmap(&mapB);
-    for (int i = 0; i < p.a_slots; ++i) { mbar_init(smem_u32(&a_full[i]), 1); mbar_init(smem_u32(&a_empty[i]), 1); }
-    for (int i = 0; i < p.b_slots; ++i) { mbar_init(smem_u32(&b_full[i]), 1); mbar_init(smem_u32(&b_empty[i]), 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&tfull_bar[i]), 1); mbar_init(smem_u32(&tempty_bar[i]), 8); }
+    // every smem slot is read by BOTH MMA warps (one commit each); accumulators are per (stage, sub-tile)
+    for (int i = 0; i < p.a_slots; ++i) { mbar_init(smem_u32(&a_full[i]), 1); mbar_init(smem_u32(&a_empty[i]), 2); }
+    for (int i = 0; i < p.b_slots; ++i) { mbar_init(smem_u32(&b_full[i]), 1); mbar_init(smem_u32(&b_empty[i]), 2); }
+    for (int i = 0; i < 4; ++i) { mbar_init(smem_u32(&tfull_bar[i]), 1); mbar_init(smem_u32(&tempty_bar[i]), 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -100,11 +101,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
     int ai = 0, bi = 0;
     uint32_t aph = 0, bph = 0;
     const bool no_tma = (p.dbg & 1) != 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x; tile < ((p.dbg & 8) ? 0 : p.total_tiles); tile += gridDim.x) {
       const int tn = tile % p.n_tiles, tp = tile / p.n_tiles;
       const SubTile s0 = decode_sub(p, 2 * tp), s1 = decode_sub(p, 2 * tp + 1);
       auto load_b = [&](int kb_glob) {
-        mbar_wait(b_empty0 + bi * 8, bph ^ 1);
+        if (p.dbg & 64) mbar_spin(b_empty0 + bi * 8, bph ^ 1); else mbar_wait(b_empty0 + bi * 8, bph ^ 1);
         if (elect_one()) {
           const uint32_t fb = b_full0 + bi * 8;
           if (no_tma) mbar_arrive(fb);
@@ -120,7 +121,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
         const int h0 = p.halo_div > 1 ? s0.nb0 / p.halo_div : s0.nb0, h1 = p.halo_div > 1 ? s1.nb0 / p.halo_div : s1.nb0;
         for (int ky = 0; ky < 3; ++ky)
           for (int kb = 0; kb < p.nkb_conv; ++kb) {
-            mbar_wait(a_empty0 + ai * 8, aph ^ 1);
+            if (p.dbg & 64) mbar_spin(a_empty0 + ai * 8, aph ^ 1); else mbar_wait(a_empty0 + ai * 8, aph ^ 1);
             if (elect_one()) {
               const uint32_t fa = a_full0 + ai * 8;
               const uint32_t sa = a_ring0 + (uint32_t)(ai * p.a_slot_bytes);
@@ -168,8 +169,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
         for (int kb = 0; kb < sg.nkb; ++kb, ++kb_glob) issue_tap(sg, kb, kb_glob);
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer (warp-uniform bookkeeping, one elected lane issues) =====================
+  } else if (warp <= 2) {
+    // ===================== two MMA issuers: warp 1 -> sub-tile 0, warp 2 -> sub-tile 1 =====================
+    // One issuing thread cannot hide its per-K-block bookkeeping (two try_waits, three commits, descriptor words) behind
+    // four or eight 64-cycle MMAs -- the MMA queue is ~2 deep (profiles/r01_mma_issue_probes.txt: one warp 75-98 %,
+    // two warps 100 % of the pipe).  With one warp per accumulator the bookkeeping of one overlaps the MMAs of the other.
+    const int sub = warp - 1;
     int ai = 0, bi = 0, as = 0;
     uint32_t aph = 0, bph = 0, aphase = 0;
     const int halo_items = p.halo ? 3 * p.nkb_conv : 0;
@@ -178,41 +183,44 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
     const int items = halo_items + tap_items;
     const uint32_t desc_hi = (uint32_t)(make_kmajor_sw128_desc(0) >> 32);
     const bool no_mma = (p.dbg & 4) != 0;
+    const bool no_ring = (p.dbg & 8) != 0;   // experiment: no smem-ring handshakes at all (pure MMA issue + tile handshake)
+    const bool prof = (p.dbg & 128) != 0;    // experiment: cycle accounting of this warp's waits (block 0 prints)
+    long long w_te = 0, w_a = 0, w_b = 0, t_all = prof ? clock64() : 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      mbar_wait(smem_u32(&tempty_bar[as]), aphase ^ 1);
+      { long long c0 = prof ? clock64() : 0; mbar_wait(smem_u32(&tempty_bar[as * 2 + sub]), aphase ^ 1); if (prof) w_te += clock64() - c0; }
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(as * 256);
+      const uint32_t d_tmem = tmem_base + (uint32_t)(as * 256 + sub * 128);
       uint32_t accumulate = 0;
       for (int item = 0; item < items; ++item) {
         const bool is_halo = item < halo_items;
         const int nb_blocks = is_halo ? 3 : 1;
-        mbar_wait(a_full0 + ai * 8, aph);
+        if (!no_ring) { long long c0 = prof ? clock64() : 0; mbar_wait(a_full0 + ai * 8, aph); if (prof) w_a += clock64() - c0; }
         tc_fence_after();
-        const uint32_t sa = a_ring0 + (uint32_t)(ai * p.a_slot_bytes);
-        const uint32_t sub_stride = is_halo ? (uint32_t)T2_HALO_SUB : (uint32_t)TC_A_BYTES;
+        const uint32_t sa = a_ring0 + (uint32_t)(ai * p.a_slot_bytes) +
+                            (uint32_t)sub * (is_halo ? (uint32_t)T2_HALO_SUB : (uint32_t)TC_A_BYTES);
         for (int j = 0; j < nb_blocks; ++j) {
-          mbar_wait(b_full0 + bi * 8, bph);
+          if (!no_ring) { long long c0 = prof ? clock64() : 0; mbar_wait(b_full0 + bi * 8, bph); if (prof) w_b += clock64() - c0; }
           tc_fence_after();
           // halo box: output pixel xl with tap kx=j reads smem row xl + j  ->  start the operand j rows (128 B) in
-          const uint32_t a_addr0 = sa + (uint32_t)(j * 128);
-          const uint32_t alo0 = ((a_addr0 & 0x3FFFFu) >> 4) | (1u << 16);
-          const uint32_t alo1 = (((a_addr0 + sub_stride) & 0x3FFFFu) >> 4) | (1u << 16);
+          const uint32_t a_addr = sa + (uint32_t)(j * 128);
+          const uint32_t alo = ((a_addr & 0x3FFFFu) >> 4) | (1u << 16);
           const uint32_t blo = (((b_ring0 + (uint32_t)(bi * b_bytes)) & 0x3FFFFu) >> 4) | (1u << 16);
           // base_offset (descriptor bits 49-51) experiment knob; 0 is what the hardware wants here (see launch code)
-          const uint32_t ahi = desc_hi | ((is_halo && p.base_off_mode) ? (((a_addr0 >> 7) & 7u) << 17) : 0u);
+          const uint32_t ahi = desc_hi | ((is_halo && p.base_off_mode) ? (((a_addr >> 7) & 7u) << 17) : 0u);
           if (elect_one()) {
             if (!no_mma) {
-              // k outer / sub-tile inner: consecutive MMAs alternate between the two TMEM accumulators
 #pragma unroll
-              for (int k = 0; k < TC_BK / 16; ++k) {
-                const uint32_t acc = k == 0 ? accumulate : 1u;
-                umma_f16_lohi2(d_tmem, alo0 + 2 * k, ahi, blo + 2 * k, desc_hi, p.idesc, acc);
-                umma_f16_lohi2(d_tmem + 128u, alo1 + 2 * k, ahi, blo + 2 * k, desc_hi, p.idesc, acc);
-              }
+              for (int k = 0; k < TC_BK / 16; ++k)
+                umma_f16_lohi2(d_tmem, alo + 2 * k, ahi, blo + 2 * k, desc_hi, p.idesc, k == 0 ? accumulate : 1u);
             }
-            umma_commit(b_empty0 + bi * 8);
-            if (j == nb_blocks - 1) umma_commit(a_empty0 + ai * 8);
-            if (item == items - 1 && j == nb_blocks - 1) umma_commit(smem_u32(&tfull_bar[as]));
+            if (p.dbg & 32) {          // experiment: release the slots at ISSUE time (plain arrive), not at MMA completion
+              mbar_arrive(b_empty0 + bi * 8);
+              if (j == nb_blocks - 1) mbar_arrive(a_empty0 + ai * 8);
+            } else if (!no_ring) {
+              umma_commit(b_empty0 + bi * 8);
+              if (j == nb_blocks - 1) umma_commit(a_empty0 + ai * 8);
+            }
+            if (item == items - 1 && j == nb_blocks - 1) umma_commit(smem_u32(&tfull_bar[as * 2 + sub]));
           }
           __syncwarp();
           accumulate = 1;
@@ -222,10 +230,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
       }
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
+    if (prof && blockIdx.x == 0 && lane == 0)
+      printf("tc2 mma warp %d: total %lld cycles, waits: tempty %lld a_full %lld b_full %lld (tiles %d, k-blocks/tile %d)\n", sub,
+             clock64() - t_all, w_te, w_a, w_b, (p.total_tiles + (int)gridDim.x - 1) / (int)gridDim.x, items + 2 * halo_items);
   } else {
-    // ===================== epilogue: warps 2..5 drain sub-tile 0, warps 6..9 sub-tile 1, concurrently =====================
+    // ===================== epilogue: warps 3..6 drain sub-tile 0, warps 7..10 sub-tile 1, concurrently =====================
     const int q = warp & 3;             // TMEM lane quarter this warp may access
-    const int grp = (warp - 2) >> 2;    // epilogue group == sub-tile == accumulator half
+    const int grp = (warp - 3) >> 2;    // epilogue group == sub-tile == accumulator half
     uint8_t* my_stg = stg8 + grp * TC_EPI_BYTES;
     EpiGeom gq{p.tiles_x, p.tiles_y, p.bw, p.bh, p.bn, p.OW, p.OH, p.NB, p.uniform};
     int as = 0;
@@ -234,16 +245,16 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
       const int tn = tile % p.n_tiles, tp = tile / p.n_tiles;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 256 + grp * 128);
       if (p.dbg & 2) {
-        mbar_wait(smem_u32(&tfull_bar[as]), aphase);
+        mbar_wait(smem_u32(&tfull_bar[as * 2 + grp]), aphase);
         tc_fence_after();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[as]));
+        if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[as * 2 + grp]));
         if (++as == 2) { as = 0; aphase ^= 1; }
         continue;
       }
-      staged_epilogue(gq, e, my_stg, it & 1, 2 * tp + grp, tn, p.BN, taddr, smem_u32(&tfull_bar[as]), aphase, true,
-                      smem_u32(&tempty_bar[as]), true, 1 + grp);
+      staged_epilogue(gq, e, my_stg, it & 1, 2 * tp + grp, tn, p.BN, taddr, smem_u32(&tfull_bar[as * 2 + grp]), aphase, true,
+                      smem_u32(&tempty_bar[as * 2 + grp]), true, 1 + grp);
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
   }
@@ -371,10 +382,11 @@ int launch_gemm_tc2(const GemmDev& g, cudaStream_t st, int bw, int bh, int bn, i
 
   const int b_bytes = BN * TC_BK * 2;
   p.a_slot_bytes = halo ? 2 * T2_HALO_SUB : 2 * TC_A_BYTES;
-  p.a_slots = 2;
+  p.a_slots = getenv("DCB_TC2_ASLOTS") ? atoi(getenv("DCB_TC2_ASLOTS")) : 2;
   const int fixed = 1024 + 512 + 2 * TC_EPI_BYTES + p.a_slots * p.a_slot_bytes;
   int b_slots = (TC_SMEM_LIMIT - fixed) / b_bytes;
   if (b_slots > T2_MAX_SLOTS) b_slots = T2_MAX_SLOTS;
+  if (getenv("DCB_TC2_BSLOTS") && atoi(getenv("DCB_TC2_BSLOTS")) < b_slots) b_slots = atoi(getenv("DCB_TC2_BSLOTS"));
   if (b_slots < 3) return DCB_EUNSUPPORTED;
   p.b_slots = b_slots;
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
