@@ -63,17 +63,27 @@ __device__ __forceinline__ float gelu_tanh_fast_f(float x) {
   const float hx = 0.5f * x;
   return fmaf(hx, tanh_approx_f(u), hx);
 }
+__device__ __forceinline__ float rcp_approx_f(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float ex2_approx_f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float gelu_erf_fast_f(float x) {
-  // erf(|z|) = 1 - (a1 t + a2 t^2 + a3 t^3 + a4 t^4 + a5 t^5) exp(-z^2),  t = 1 / (1 + 0.3275911 |z|)
+  // erf(|z|) = 1 - (a1 t + a2 t^2 + a3 t^3 + a4 t^4 + a5 t^5) exp(-z^2),  t = 1 / (1 + 0.3275911 |z|)   (two MUFU ops)
   const float z = fabsf(x) * 0.7071067811865476f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  const float t = rcp_approx_f(fmaf(0.3275911f, z, 1.0f));
   float poly = fmaf(1.061405429f, t, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);
   poly = fmaf(poly, t, 0.254829592f);
-  const float e = poly * t * __expf(-z * z);          // 1 - erf(|z|)
-  const float erf_abs = 1.0f - e;
-  return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+  const float e = poly * t * ex2_approx_f(z * z * -1.4426950408889634f);   // 1 - erf(|z|)
+  const float hx = 0.5f * x;
+  return fmaf(hx, copysignf(1.0f - e, x), hx);
 }
 __device__ __forceinline__ float apply_act_fast(int act, float v) {
   if (act == DCB_ACT_SILU) return silu_fast_f(v);

@@ -194,6 +194,15 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc_off(uint32_t smem_add
   return d;
 }
 
+// 16 consecutive floats from shared memory (16-byte aligned address)
+__device__ __forceinline__ void lds16f(uint32_t addr, float* f) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(f[4 * i]), "=f"(f[4 * i + 1]), "=f"(f[4 * i + 2]), "=f"(f[4 * i + 3])
+                 : "r"(addr + 16 * i));
+}
+
 // ---- staged epilogue of one 128-row accumulator sub-tile (bf16 outputs, <= 128 output columns per tile) --------
 //  0. per-row ids + tile-constant bias/rowvec/gate vectors -> smem
 //  1. cp.async prefetch of the whole residual tile (32 KB in flight per SM) into the swizzled staging tile
@@ -271,17 +280,21 @@ __device__ __forceinline__ void staged_epilogue(const EpiGeom& gq, const EpiDev&
       tmem_ld16_nowait(taddr + (uint32_t)c, ra);
       if (geglu) tmem_ld16_nowait(taddr + (uint32_t)(128 + c), rg);
       tmem_ld_wait();
-      float v[16];
+      float v[16], bz[16], bg[16];
+      // tile-constant vectors through explicit 16-byte shared loads (the generic-pointer form compiles to LD.E)
+      lds16f(smem_u32(s_bias + c), bz);
+      if (geglu) lds16f(smem_u32(s_bias + 128 + c), bg);
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        float a = __uint_as_float(ra[i]) + s_bias[c + i];
-        if (geglu) a *= gelu_erf_fast_f(__uint_as_float(rg[i]) + s_bias[128 + c + i]);
+        float a = __uint_as_float(ra[i]) + bz[i];
+        if (geglu) a *= gelu_erf_fast_f(__uint_as_float(rg[i]) + bg[i]);
         v[i] = a;
       }
       if (e.rowvec) {
         if (gq.uniform) {
+          { float rvv[16]; lds16f(smem_u32(s_rowvec + c), rvv);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] += s_rowvec[c + i];
+            for (int i = 0; i < 16; ++i) v[i] += rvv[i]; }
         } else if (row_ok) {
           const float* rv = e.rowvec + (int64_t)(e.rowvec_idx ? e.rowvec_idx[grp] : grp) * e.rowvec_ld + ocol0 + c;
 #pragma unroll
@@ -295,8 +308,9 @@ __device__ __forceinline__ void staged_epilogue(const EpiGeom& gq, const EpiDev&
       }
       if (e.gate) {
         if (gq.uniform) {
+          { float gvv[16]; lds16f(smem_u32(s_gate + c), gvv);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] *= s_gate[c + i];
+            for (int i = 0; i < 16; ++i) v[i] *= gvv[i]; }
         } else if (row_ok) {
           const float* gt = e.gate + (int64_t)grp * e.gate_ld + ocol0 + c;
 #pragma unroll

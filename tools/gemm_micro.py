@@ -48,7 +48,7 @@ for c in cases:
         x = torch.randn(M, K, device=dev).to(torch.bfloat16)
         w = (torch.randn(N, K, device=dev) * 0.05).to(torch.bfloat16)
         b = torch.randn(N, device=dev)
-        act = 2 if c.endswith(":gelu") else 0
+        act = 2 if c.endswith(":gelu") else (3 if c.endswith(":geglu") else 0)
         fn = lambda: E.linear(ctx, x, w, N, bias=b, act=act)
         fl = 2.0 * M * N * K
     else:
