@@ -185,54 +185,63 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
     const bool no_mma = (p.dbg & 4) != 0;
     const bool no_ring = (p.dbg & 8) != 0;   // experiment: no smem-ring handshakes at all (pure MMA issue + tile handshake)
     const bool prof = (p.dbg & 128) != 0;    // experiment: cycle accounting of this warp's waits (block 0 prints)
-    long long w_te = 0, w_a = 0, w_b = 0, t_all = prof ? clock64() : 0;
+    long long w_te = 0, w_a = 0, w_b = 0, w_iss = 0, w_com = 0, t_all = prof ? clock64() : 0;
+    // running descriptor words / barrier addresses of the current slots (no multiplications in the K loop)
+    const uint32_t a_step = (uint32_t)p.a_slot_bytes >> 4, b_step = (uint32_t)b_bytes >> 4;
+    const uint32_t a_lo_base = (((a_ring0 + (uint32_t)sub * (p.halo ? (uint32_t)T2_HALO_SUB : (uint32_t)TC_A_BYTES)) & 0x3FFFFu) >> 4) | (1u << 16);
+    const uint32_t a_lo_tap_base = (((a_ring0 + (uint32_t)sub * (uint32_t)TC_A_BYTES) & 0x3FFFFu) >> 4) | (1u << 16);
+    const uint32_t b_lo_base = ((b_ring0 & 0x3FFFFu) >> 4) | (1u << 16);
+    uint32_t a_off = 0, b_lo = b_lo_base;           // a_off: (slot index * slot bytes) >> 4
+    uint32_t a_fb = a_full0, a_eb = a_empty0, b_fb = b_full0, b_eb = b_empty0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       { long long c0 = prof ? clock64() : 0; mbar_wait(smem_u32(&tempty_bar[as * 2 + sub]), aphase ^ 1); if (prof) w_te += clock64() - c0; }
-      tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(as * 256 + sub * 128);
+      const uint32_t tfull_addr = smem_u32(&tfull_bar[as * 2 + sub]);
       uint32_t accumulate = 0;
       for (int item = 0; item < items; ++item) {
         const bool is_halo = item < halo_items;
         const int nb_blocks = is_halo ? 3 : 1;
-        if (!no_ring) { long long c0 = prof ? clock64() : 0; mbar_wait(a_full0 + ai * 8, aph); if (prof) w_a += clock64() - c0; }
-        tc_fence_after();
-        const uint32_t sa = a_ring0 + (uint32_t)(ai * p.a_slot_bytes) +
-                            (uint32_t)sub * (is_halo ? (uint32_t)T2_HALO_SUB : (uint32_t)TC_A_BYTES);
+        if (!no_ring) { long long c0 = prof ? clock64() : 0; mbar_wait(a_fb, aph); if (prof) w_a += clock64() - c0; }
+        const uint32_t alo_item = (is_halo ? a_lo_base : a_lo_tap_base) + a_off;
+        const bool last_item = item == items - 1;
         for (int j = 0; j < nb_blocks; ++j) {
-          if (!no_ring) { long long c0 = prof ? clock64() : 0; mbar_wait(b_full0 + bi * 8, bph); if (prof) w_b += clock64() - c0; }
+          if (!no_ring) { long long c0 = prof ? clock64() : 0; mbar_wait(b_fb, bph); if (prof) w_b += clock64() - c0; }
           tc_fence_after();
           // halo box: output pixel xl with tap kx=j reads smem row xl + j  ->  start the operand j rows (128 B) in
-          const uint32_t a_addr = sa + (uint32_t)(j * 128);
-          const uint32_t alo = ((a_addr & 0x3FFFFu) >> 4) | (1u << 16);
-          const uint32_t blo = (((b_ring0 + (uint32_t)(bi * b_bytes)) & 0x3FFFFu) >> 4) | (1u << 16);
-          // base_offset (descriptor bits 49-51) experiment knob; 0 is what the hardware wants here (see launch code)
-          const uint32_t ahi = desc_hi | ((is_halo && p.base_off_mode) ? (((a_addr >> 7) & 7u) << 17) : 0u);
+          const uint32_t alo = alo_item + (uint32_t)(j * 8);
+          const bool last_j = j == nb_blocks - 1;
           if (elect_one()) {
+            const long long c_i0 = prof ? clock64() : 0;
             if (!no_mma) {
 #pragma unroll
               for (int k = 0; k < TC_BK / 16; ++k)
-                umma_f16_lohi2(d_tmem, alo + 2 * k, ahi, blo + 2 * k, desc_hi, p.idesc, k == 0 ? accumulate : 1u);
+                umma_f16_lohi2(d_tmem, alo + 2 * k, desc_hi, b_lo + 2 * k, desc_hi, p.idesc, k == 0 ? accumulate : 1u);
             }
+            const long long c_i1 = prof ? clock64() : 0;
+            if (prof) w_iss += c_i1 - c_i0;
             if (p.dbg & 32) {          // experiment: release the slots at ISSUE time (plain arrive), not at MMA completion
-              mbar_arrive(b_empty0 + bi * 8);
-              if (j == nb_blocks - 1) mbar_arrive(a_empty0 + ai * 8);
+              mbar_arrive(b_eb);
+              if (last_j) mbar_arrive(a_eb);
             } else if (!no_ring) {
-              umma_commit(b_empty0 + bi * 8);
-              if (j == nb_blocks - 1) umma_commit(a_empty0 + ai * 8);
+              umma_commit(b_eb);
+              if (last_j) umma_commit(a_eb);
             }
-            if (item == items - 1 && j == nb_blocks - 1) umma_commit(smem_u32(&tfull_bar[as * 2 + sub]));
+            if (last_item && last_j) umma_commit(tfull_addr);
+            if (prof) w_com += clock64() - c_i1;
           }
           __syncwarp();
           accumulate = 1;
-          if (++bi == p.b_slots) { bi = 0; bph ^= 1; }
+          b_lo += b_step; b_fb += 8; b_eb += 8;
+          if (++bi == p.b_slots) { bi = 0; bph ^= 1; b_lo = b_lo_base; b_fb = b_full0; b_eb = b_empty0; }
         }
-        if (++ai == p.a_slots) { ai = 0; aph ^= 1; }
+        a_off += a_step; a_fb += 8; a_eb += 8;
+        if (++ai == p.a_slots) { ai = 0; aph ^= 1; a_off = 0; a_fb = a_full0; a_eb = a_empty0; }
       }
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
-    if (prof && blockIdx.x == 0 && lane == 0)
-      printf("tc2 mma warp %d: total %lld cycles, waits: tempty %lld a_full %lld b_full %lld (tiles %d, k-blocks/tile %d)\n", sub,
-             clock64() - t_all, w_te, w_a, w_b, (p.total_tiles + (int)gridDim.x - 1) / (int)gridDim.x, items + 2 * halo_items);
+    if (prof && (blockIdx.x % 21 == 0) && lane == 0)
+      printf("tc2 block %d mma warp %d: total %lld cycles, waits: tempty %lld a_full %lld b_full %lld; mma issue %lld commits %lld (tiles %d, k-blocks/tile %d)\n", (int)blockIdx.x, sub,
+             clock64() - t_all, w_te, w_a, w_b, w_iss, w_com, (p.total_tiles + (int)gridDim.x - 1) / (int)gridDim.x, items + 2 * halo_items);
   } else {
     // ===================== epilogue: warps 3..6 drain sub-tile 0, warps 7..10 sub-tile 1, concurrently =====================
     const int q = warp & 3;             // TMEM lane quarter this warp may access

@@ -29,3 +29,11 @@ if [ "$1" = "attn" ]; then
   $ACMD > gpurun_out/plain.log 2>&1 &&
   ncu --set full --clock-control none --import-source on -k regex:flash_attn_tc -s 14 -c 2 -f -o gpurun_out/prof_attn $ACMD > gpurun_out/ncu_attn.log 2>&1
 fi
+# tools/profile.sh domgemm -> gpurun_out/prof_domgemm.ncu-rep: --set full of the dominant conv shape (256 -> 128 ch 3x3 @128^2, x-halo gemm_tc2) and
+#                             gpurun_out/prof_attn.ncu-rep: the tcgen05 attention kernel at the DiT-B/4 shape
+if [ "$1" = "domgemm" ]; then
+  G="python tools/gemm_micro.py conv256to128"; A="python tools/attn_micro.py"
+  export MICRO_ITERS=3
+  $G > gpurun_out/plain.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:gemm_tc2_kernel -s 4 -c 1 -f -o gpurun_out/prof_domgemm $G > gpurun_out/ncu_domgemm.log 2>&1
+  $A > gpurun_out/plain2.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:flash_attn_tc -s 4 -c 1 -f -o gpurun_out/prof_attn $A > gpurun_out/ncu_attn.log 2>&1
+fi
