@@ -214,25 +214,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     int as = 0;
     uint32_t aphase = 0;
     const uint32_t desc_hi = (uint32_t)(make_kmajor_sw128_desc(0) >> 32);
+    // running descriptor word / barrier addresses of the current stage (no multiplications in the K loop)
+    const uint32_t lo_base = ((smem_base & 0x3FFFFu) >> 4) | (1u << 16), lo_step = (uint32_t)stage_bytes >> 4;
+    uint32_t alo = lo_base, fb = full0, eb = empty0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       mbar_wait(smem_u32(&tempty_bar[as]), aphase ^ 1);
-      tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(as * 256);
+      const uint32_t tfull_addr = smem_u32(&tfull_bar[as]);
       for (int kb = 0; kb < p.total_kb; ++kb) {
-        mbar_wait(full0 + stage * 8, phase);
+        mbar_wait(fb, phase);
         tc_fence_after();
         // descriptor low words: (address >> 4); +2 advances 16 elements (32 B) along K inside the swizzle atom
-        const uint32_t alo = ((smem_base + (uint32_t)(stage * stage_bytes)) & 0x3FFFFu) >> 4 | (1u << 16);
         const uint32_t blo = alo + (TC_A_BYTES >> 4);
         if (elect_one()) {
           umma_f16_lohi(d_tmem, alo, blo, desc_hi, p.idesc, (uint32_t)kb);
 #pragma unroll
           for (int k = 1; k < TC_BK / 16; ++k) umma_f16_lohi(d_tmem, alo + 2 * k, blo + 2 * k, desc_hi, p.idesc, 1u);
-          umma_commit(empty0 + stage * 8);                                  // frees the smem stage when the MMAs retire
-          if (kb == p.total_kb - 1) umma_commit(smem_u32(&tfull_bar[as]));  // accumulator complete
+          umma_commit(eb);                                   // frees the smem stage when the MMAs retire
+          if (kb == p.total_kb - 1) umma_commit(tfull_addr);  // accumulator complete
         }
         __syncwarp();
-        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        alo += lo_step; fb += 8; eb += 8;
+        if (++stage == p.stages) { stage = 0; phase ^= 1; alo = lo_base; fb = full0; eb = empty0; }
       }
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
