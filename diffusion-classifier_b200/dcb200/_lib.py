@@ -64,6 +64,8 @@ _PROTOS = {
                               c_int, c_void_p, c_void_p]),
     "dcb_attention": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float,
                               c_void_p, c_int, c_void_p]),
+    "dcb_attention_ws": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float,
+                                 c_void_p, c_int, c_void_p, c_void_p]),
     "dcb_haar_dwt": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
     "dcb_haar_idwt": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
     "dcb_upsample2x": (c_int, [c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),

@@ -271,15 +271,15 @@ static int launch_simt(const void* q, const void* k, const void* v, int ld, int 
 }
 
 int launch_flash_tc(const void* q, const void* k, const void* v, int ld, int B, int N, int heads, float scale, void* out,
-                    int out_ld, cudaStream_t st);
+                    int out_ld, float* norms_ws, cudaStream_t st);
 
 }  // namespace dcb
 
 using namespace dcb;
 
 // dtype DCB_BF16 -> tensor-core flash kernel; DCB_F32 -> fp32 verify kernel; (DCB_BF16 | 0x100) -> SIMT on bf16 data
-extern "C" int dcb_attention(int dtype, const void* q, const void* k, const void* v, int ld, int B, int Ntok, int heads,
-                             int d, float scale, void* out, int out_ld, dcb_stream stream) {
+extern "C" int dcb_attention_ws(int dtype, const void* q, const void* k, const void* v, int ld, int B, int Ntok, int heads,
+                                int d, float scale, void* out, int out_ld, float* ws, dcb_stream stream) {
   cudaStream_t st = (cudaStream_t)stream;
   DCB_REQUIRE(B >= 1 && B <= 65535 && heads >= 1 && Ntok >= 1, "attention: bad sizes");
   DCB_REQUIRE(d == 32 || d == 64 || d == 96 || d == 128, "attention: head dim %d not in {32,64,96,128}", d);
@@ -297,7 +297,7 @@ extern "C" int dcb_attention(int dtype, const void* q, const void* k, const void
     // the small-N / other-head-dim cases (d = 32, 96, 128 are a few per cent of the U-Net configs' FLOPs)
     static const bool tc_on = !(getenv("DCB_ATTN_TC") && atoi(getenv("DCB_ATTN_TC")) == 0);
     if (d == 64 && Ntok >= 128 && tc_on && out_ld % 8 == 0 && ((uintptr_t)out & 15) == 0)
-      return launch_flash_tc(q, k, v, ld, B, Ntok, heads, scale, out, out_ld, st);
+      return launch_flash_tc(q, k, v, ld, B, Ntok, heads, scale, out, out_ld, ws, st);
     DCB_ATTN_DISPATCH(launch_flash, )
   } else if (dtype == DCB_F32) {
     DCB_ATTN_DISPATCH(launch_simt, float, )
@@ -307,4 +307,9 @@ extern "C" int dcb_attention(int dtype, const void* q, const void* k, const void
 #undef DCB_ATTN_DISPATCH
   set_error("attention: unknown dtype %d", dtype);
   return DCB_EINVAL;
+}
+
+extern "C" int dcb_attention(int dtype, const void* q, const void* k, const void* v, int ld, int B, int Ntok, int heads,
+                             int d, float scale, void* out, int out_ld, dcb_stream stream) {
+  return dcb_attention_ws(dtype, q, k, v, ld, B, Ntok, heads, d, scale, out, out_ld, nullptr, stream);
 }

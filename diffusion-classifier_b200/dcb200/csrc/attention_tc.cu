@@ -78,10 +78,14 @@ __device__ __forceinline__ float ex2f(float x) {
   return y;
 }
 
+// the single-pass kernel is exact iff nothing underflows: max|q| max|k| c <= 50 bounds every (M_i - s_ij) c by 100 < 126
+__device__ __forceinline__ bool at_fast_ok(const float* norms, float sc) { return sqrtf(norms[0] * norms[1]) * sc <= 50.f; }
+
 struct AtParams {
   int N, nblk;        // tokens per (batch, head); ceil(N / 128)
   float sc;           // softmax scale * log2(e)
   int out_ld;
+  const float* norms;   // [2 + B*heads*2] fp32: global max|q|^2, max|k|^2, then the same per (batch, head); NULL = none
 };
 
 __global__ void __launch_bounds__(AT_THREADS, 1)
@@ -104,6 +108,8 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
   uint64_t* o_full = p_full + 2;                 // [2]  MMA -> softmax: O_t(j) = P_t(j) V_j complete
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
 
+  // when the single-pass kernel (attention_tc_fast.cu) can take this launch, this one has nothing to do
+  if (p.norms != nullptr && at_fast_ok(p.norms, p.sc)) return;
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const int h = blockIdx.y, b = blockIdx.z;
@@ -334,6 +340,303 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
   }
 }
 
+
+// =====================================================================================================================
+// Single-pass kernel.  Softmax is shift invariant, so any per-row M_i >= max_j s_ij serves as the reference:
+// M_i = |q_i| max_j |k_j| (Cauchy-Schwarz, norms from attn_norms_kernel) is known before the first key block.  That removes
+// the running maximum, its extra pass over S, every rescale and the per-block fold of O:  P = exp2((S - M_i) c) <= 1 in
+// ONE pass over S, and the tensor core accumulates O in TMEM over all key blocks.  Without a running maximum the two halves
+// of a score row are independent, so each query row is shared by TWO threads (warps w and w+8: keys 0-63 / 64-127, O
+// channels 0-31 / 32-63) with no exchange until the final row sum -- 16 softmax warps, four per scheduler, keep the MUFU
+// pipe fed.  Exact as long as nothing underflows; the launch falls back to flash_attn_tc_kernel by itself otherwise
+// (at_fast_ok, evaluated on the device: both kernels are always enqueued and one of them returns at once).
+// =====================================================================================================================
+constexpr int ATF_THREADS = 64 + 512;   // TMA warp, MMA warp, 2 tiles x 2 halves x 4 softmax warps
+
+__global__ void __launch_bounds__(ATF_THREADS, 1)
+flash_attn_tc_fast_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
+                          const __grid_constant__ CUtensorMap mapV, const __grid_constant__ AtParams p,
+                          __nv_bfloat16* __restrict__ out) {
+  if (!at_fast_ok(p.norms, p.sc)) return;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* q_s = smem;                                    // 2 tiles
+  uint8_t* k_s = q_s + 2 * AT_TILE_BYTES;                 // ring
+  uint8_t* v_s = k_s + AT_KV_STAGES * AT_TILE_BYTES;      // ring
+  uint64_t* bars = reinterpret_cast<uint64_t*>(v_s + AT_KV_STAGES * AT_TILE_BYTES);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = bars + 1;
+  uint64_t* k_empty = k_full + AT_KV_STAGES;
+  uint64_t* v_full = k_empty + AT_KV_STAGES;
+  uint64_t* v_empty = v_full + AT_KV_STAGES;
+  uint64_t* s_full = v_empty + AT_KV_STAGES;     // [2]  MMA -> softmax: S_t(j) complete
+  uint64_t* s_free = s_full + 2;                 // [2]  softmax -> MMA: S_t(j) is in registers
+  uint64_t* p_full = s_free + 2;                 // [2]  softmax -> MMA: P_t(j) written
+  uint64_t* o_full = p_full + 2;                 // [2]  MMA -> softmax: P_t(j) V_j accumulated (P_t free again)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+  float* lsum = reinterpret_cast<float*>(bars + 32);     // [2 tiles][2 halves][128 rows]
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int q0 = blockIdx.x * 256;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&mapQ);
+    prefetch_tmap(&mapK);
+    prefetch_tmap(&mapV);
+    mbar_init(smem_u32(q_full), 1);
+    for (int i = 0; i < AT_KV_STAGES; ++i) {
+      mbar_init(smem_u32(&k_full[i]), 1);
+      mbar_init(smem_u32(&k_empty[i]), 1);
+      mbar_init(smem_u32(&v_full[i]), 1);
+      mbar_init(smem_u32(&v_empty[i]), 1);
+    }
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(smem_u32(&s_full[t]), 1);
+      mbar_init(smem_u32(&s_free[t]), 8);   // one arrive per softmax warp of the tile
+      mbar_init(smem_u32(&p_full[t]), 8);
+      mbar_init(smem_u32(&o_full[t]), 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t k_full0 = smem_u32(k_full), k_empty0 = smem_u32(k_empty), v_full0 = smem_u32(v_full),
+                 v_empty0 = smem_u32(v_empty);
+  const uint32_t s_full0 = smem_u32(s_full), s_free0 = smem_u32(s_free), p_full0 = smem_u32(p_full),
+                 o_full0 = smem_u32(o_full);
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      const uint32_t fq = smem_u32(q_full);
+      mbar_expect_tx(fq, 2u * AT_TILE_BYTES);
+      tma_load_3d(smem_u32(q_s), &mapQ, fq, h * 64, q0, b);
+      tma_load_3d(smem_u32(q_s + AT_TILE_BYTES), &mapQ, fq, h * 64, q0 + 128, b);
+    }
+    __syncwarp();
+    int st = 0;
+    uint32_t ph = 0;
+    for (int j = 0; j < p.nblk; ++j) {
+      mbar_wait(k_empty0 + st * 8, ph ^ 1);
+      if (elect_one()) {
+        mbar_expect_tx(k_full0 + st * 8, (uint32_t)AT_TILE_BYTES);
+        tma_load_3d(smem_u32(k_s + st * AT_TILE_BYTES), &mapK, k_full0 + st * 8, h * 64, j * 128, b);
+      }
+      __syncwarp();
+      mbar_wait(v_empty0 + st * 8, ph ^ 1);
+      if (elect_one()) {
+        mbar_expect_tx(v_full0 + st * 8, (uint32_t)AT_TILE_BYTES);
+        tma_load_3d(smem_u32(v_s + st * AT_TILE_BYTES), &mapV, v_full0 + st * 8, h * 64, j * 128, b);
+      }
+      __syncwarp();
+      if (++st == AT_KV_STAGES) { st = 0; ph ^= 1; }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc_qk = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t idesc_pv = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t hi_k = (uint32_t)(make_kmajor_sw128_desc(0) >> 32);
+    const uint32_t q_lo = ((smem_u32(q_s) & 0x3FFFFu) >> 4) | (1u << 16);
+    const uint32_t k_lo0 = ((smem_u32(k_s) & 0x3FFFFu) >> 4) | (1u << 16);
+    const uint32_t v_lo0 = ((smem_u32(v_s) & 0x3FFFFu) >> 4) | (1u << 16);
+    auto issue_qk = [&](int t, int st_) {
+      const uint32_t a = q_lo + (uint32_t)t * (AT_TILE_BYTES >> 4), bq = k_lo0 + (uint32_t)st_ * (AT_TILE_BYTES >> 4);
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_f16_lohi(tmem_base + (uint32_t)(t * 128), a + 2 * k, bq + 2 * k, hi_k, idesc_qk, k ? 1u : 0u);
+        umma_commit(s_full0 + t * 8);
+      }
+      __syncwarp();
+    };
+    auto issue_pv = [&](int t, int st_, uint32_t acc0) {
+      const uint32_t bv = v_lo0 + (uint32_t)st_ * (AT_TILE_BYTES >> 4);
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)   // 16 keys per step: 8 TMEM columns of packed bf16 pairs, 2 x 1024 B of V rows
+          umma_f16_ts(tmem_base + (uint32_t)(384 + t * 64), tmem_base + (uint32_t)(256 + t * 64 + k * 8),
+                      bv + (uint32_t)k * (2048 >> 4), hi_k, idesc_pv, k ? 1u : acc0);
+        umma_commit(o_full0 + t * 8);
+      }
+      __syncwarp();
+    };
+    mbar_wait(smem_u32(q_full), 0);
+    mbar_wait(k_full0, 0);
+    tc_fence_after();
+    issue_qk(0, 0);
+    issue_qk(1, 0);
+    if (elect_one()) umma_commit(k_empty0);
+    __syncwarp();
+    int st = 0, stn = 1 % AT_KV_STAGES;
+    uint32_t ph = 0, phn = (AT_KV_STAGES == 1) ? 1u : 0u;
+    for (int j = 0; j < p.nblk; ++j) {
+      if (j + 1 < p.nblk) {
+        mbar_wait(k_full0 + stn * 8, phn);
+        for (int t = 0; t < 2; ++t) {
+          mbar_wait(s_free0 + t * 8, (uint32_t)(j & 1));   // S_t(j) is in the softmax warps' registers
+          tc_fence_after();
+          issue_qk(t, stn);
+        }
+        if (elect_one()) umma_commit(k_empty0 + stn * 8);
+        __syncwarp();
+      }
+      mbar_wait(v_full0 + st * 8, ph);
+      for (int t = 0; t < 2; ++t) {
+        mbar_wait(p_full0 + t * 8, (uint32_t)(j & 1));
+        tc_fence_after();
+        issue_pv(t, st, j ? 1u : 0u);                      // O_t accumulates in TMEM over all key blocks
+      }
+      if (elect_one()) umma_commit(v_empty0 + st * 8);
+      __syncwarp();
+      st = stn; ph = phn;
+      if (++stn == AT_KV_STAGES) { stn = 0; phn ^= 1; }
+    }
+  } else {
+    // ===================== softmax warps =====================
+    const int t = (warp - 2) >> 3;          // query tile
+    const int hf = ((warp - 2) >> 2) & 1;   // keys [64 hf, +64) of every block, O channels [32 hf, +32)
+    const int qd = warp & 3;                // TMEM lane quarter
+    const int r = qd * 32 + lane;           // query row inside the tile == TMEM lane
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(qd * 32) << 16);
+    const uint32_t s_addr = lane_addr + (uint32_t)(t * 128 + hf * 64);
+    const uint32_t p_addr = lane_addr + (uint32_t)(256 + t * 64 + hf * 32);
+    const uint32_t o_addr = lane_addr + (uint32_t)(384 + t * 64 + hf * 32);
+    // |q_r|^2 from the swizzled Q tile (16-byte chunk c of row r sits at chunk c ^ (r & 7))
+    mbar_wait(smem_u32(q_full), 0);
+    float qn2 = 0.f;
+    {
+      const uint8_t* qrow = q_s + t * AT_TILE_BYTES + r * 128;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float f[8];
+        unpack_bf16x8(*reinterpret_cast<const uint4*>(qrow + ((c ^ (r & 7)) << 4)), f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) qn2 = fmaf(f[i], f[i], qn2);
+      }
+    }
+    const float kn2 = p.norms[2 + (b * gridDim.y + h) * 2 + 1];
+    const float sc = p.sc;
+    const float msc = sqrtf(qn2 * kn2) * 1.002f * sc;   // M_i c (log2 units), a hair above the Cauchy-Schwarz bound
+    float l = 0.f;
+    for (int j = 0; j < p.nblk; ++j) {
+      mbar_wait(s_full0 + t * 8, (uint32_t)(j & 1));
+      tc_fence_after();
+      const int valid = p.N - j * 128 - hf * 64;   // keys of this half block that exist (>= 64: all)
+      uint32_t pk[32];
+      float rs = 0.f;
+#pragma unroll
+      for (int c = 0; c < 64; c += 32) {
+        uint32_t sv[32];
+        tmem_ld32_nowait(s_addr + (uint32_t)c, sv);
+        tmem_ld_wait();
+        if (c == 32) {   // this thread's half row of S is in registers
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(s_free0 + t * 8);
+        }
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float p0 = ex2f(fmaf(__uint_as_float(sv[i]), sc, -msc));
+          float p1 = ex2f(fmaf(__uint_as_float(sv[i + 1]), sc, -msc));
+          if (valid < 64) {
+            if (c + i >= valid) p0 = 0.f;
+            if (c + i + 1 >= valid) p1 = 0.f;
+          }
+          rs += p0 + p1;
+          pk[(c + i) >> 1] = pack_bf16x2(p0, p1);
+        }
+      }
+      l += rs;
+      if (j > 0) {   // P_t is free once the previous block's P V has been consumed
+        mbar_wait(o_full0 + t * 8, (uint32_t)((j - 1) & 1));
+        tc_fence_after();
+      }
+      tmem_st16(p_addr, pk);
+      tmem_st16(p_addr + 16u, pk + 16);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full0 + t * 8);
+    }
+    // the other half's share of the row sum, then O / l
+    lsum[(t * 2 + hf) * 128 + r] = l;
+    asm volatile("bar.sync %0, 256;" ::"r"(1 + t) : "memory");
+    l += lsum[(t * 2 + (hf ^ 1)) * 128 + r];
+    mbar_wait(o_full0 + t * 8, (uint32_t)((p.nblk - 1) & 1));
+    tc_fence_after();
+    const float inv = 1.f / l;
+    const int qrow_i = q0 + t * 128 + r;
+    __nv_bfloat16* orow = out + ((int64_t)b * p.N + qrow_i) * p.out_ld + h * 64 + hf * 32;
+    {
+      uint32_t ov[32];
+      tmem_ld32_nowait(o_addr, ov);
+      tmem_ld_wait();
+      float v[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(ov[i]) * inv;
+      if (qrow_i < p.N) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) *reinterpret_cast<uint4*>(orow + i) = pack_bf16x8(v + i);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// norms[0..1]: max over everything; norms[2 + (b*heads + h)*2 + {0,1}]: max_i |q_i|^2, max_j |k_j|^2 of that (batch, head).
+// bf16 values, fp32 sums; non-negative floats order like their bit patterns, so integer atomicMax does the reduction.
+__global__ void __launch_bounds__(256) attn_norms_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
+                                                         int ld, int N, float* __restrict__ out) {
+  // 8 threads per token (one 16-byte chunk of the 128-byte head row each): a warp reads 4 x 128 contiguous bytes
+  const int h = blockIdx.y, b = blockIdx.z, c = threadIdx.x & 7;
+  float qmax = 0.f, kmax = 0.f;
+  for (int tkn = blockIdx.x * 256 + (threadIdx.x >> 3); tkn < min(N, (int)(blockIdx.x + 1) * 256); tkn += 32) {
+    const int64_t off = ((int64_t)b * N + tkn) * ld + h * 64 + c * 8;
+    float f[8], qn = 0.f, kn = 0.f;
+    unpack_bf16x8(*reinterpret_cast<const uint4*>(q + off), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) qn = fmaf(f[i], f[i], qn);
+    unpack_bf16x8(*reinterpret_cast<const uint4*>(k + off), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) kn = fmaf(f[i], f[i], kn);
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {   // the 8 chunks of a token are 8 consecutive lanes
+      qn += __shfl_xor_sync(0xffffffffu, qn, o);
+      kn += __shfl_xor_sync(0xffffffffu, kn, o);
+    }
+    qmax = fmaxf(qmax, qn);
+    kmax = fmaxf(kmax, kn);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    qmax = fmaxf(qmax, __shfl_xor_sync(0xffffffffu, qmax, o));
+    kmax = fmaxf(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    int* o2 = reinterpret_cast<int*>(out);
+    const int bh = (b * gridDim.y + h) * 2;
+    atomicMax(o2 + 2 + bh, __float_as_int(qmax));
+    atomicMax(o2 + 3 + bh, __float_as_int(kmax));
+    atomicMax(o2, __float_as_int(qmax));
+    atomicMax(o2 + 1, __float_as_int(kmax));
+  }
+}
+
 static int encode_tok_map(CUtensorMap* map, const void* base, int ld, int N, int B, int width) {
   auto enc = tc_encode_fn();
   DCB_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
@@ -348,9 +651,11 @@ static int encode_tok_map(CUtensorMap* map, const void* base, int ld, int N, int
   return DCB_OK;
 }
 
-// head dim 64, bf16, N >= 128; q/k/v: [B, N, heads, 64] views with row stride ld
+// head dim 64, bf16, N >= 128; q/k/v: [B, N, heads, 64] views with row stride ld.
+// norms_ws: [2 + B*heads*2] fp32 workspace or NULL.  With it (and enough key blocks for the norm pre-pass to pay) the
+// single-pass kernel is enqueued ahead of the running-maximum kernel and the device decides which of the two runs.
 int launch_flash_tc(const void* q, const void* k, const void* v, int ld, int B, int N, int heads, float scale, void* out,
-                    int out_ld, cudaStream_t st) {
+                    int out_ld, float* norms_ws, cudaStream_t st) {
   DCB_REQUIRE(out_ld % 8 == 0 && ((uintptr_t)out & 15) == 0, "attention: out rows must be 16-byte aligned");
   CUtensorMap mq, mk, mv;
   int rc;
@@ -362,12 +667,24 @@ int launch_flash_tc(const void* q, const void* k, const void* v, int ld, int B, 
   p.nblk = (N + 127) / 128;
   p.sc = scale * 1.4426950408889634f;
   p.out_ld = out_ld;
-  const size_t smem = 1024 + (2 + 2 * AT_KV_STAGES) * AT_TILE_BYTES + 256;
+  static const bool fast_on = !(getenv("DCB_ATTN_FAST") && atoi(getenv("DCB_ATTN_FAST")) == 0);
+  const bool use_fast = norms_ws != nullptr && fast_on && N >= 1024;   // short sequences: two extra launches do not pay
+  p.norms = use_fast ? norms_ws : nullptr;
+  const size_t smem = 1024 + (2 + 2 * AT_KV_STAGES) * AT_TILE_BYTES + 256 + 2048;
   static std::once_flag once;
   std::call_once(once, [] {
     cudaFuncSetAttribute(flash_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT);
+    cudaFuncSetAttribute(flash_attn_tc_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT);
   });
   dim3 grid((N + 255) / 256, heads, B);
+  if (use_fast) {
+    cudaMemsetAsync(norms_ws, 0, sizeof(float) * (2 + 2 * B * heads), st);
+    attn_norms_kernel<<<dim3((N + 255) / 256, heads, B), 256, 0, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k, ld, N,
+                                                                        norms_ws);
+    DCB_CHECK_LAUNCH("attn_norms");
+    flash_attn_tc_fast_kernel<<<grid, ATF_THREADS, smem, st>>>(mq, mk, mv, p, (__nv_bfloat16*)out);
+    DCB_CHECK_LAUNCH("flash_attn_tc_fast");
+  }
   flash_attn_tc_kernel<<<grid, AT_THREADS, smem, st>>>(mq, mk, mv, p, (__nv_bfloat16*)out);
   DCB_CHECK_LAUNCH("flash_attn_tc");
   return DCB_OK;

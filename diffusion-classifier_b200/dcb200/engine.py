@@ -204,8 +204,9 @@ def attention(ctx, qkv, B, Ntok, heads, d, q_off=0, k_off=None, v_off=None, simt
     base = qkv.data_ptr()
     out = torch.empty(B * Ntok, Cw, device=ctx.device, dtype=qkv.dtype)
     code = ctx.code | (0x100 if (simt and ctx.code == L.BF16) else 0)
-    L.check(L.lib().dcb_attention(code, base + q_off * es, base + k_off * es, base + v_off * es, ld, B, Ntok, heads, d,
-                                  float(d) ** -0.5, out.data_ptr(), Cw, ctx.stream()), "attention")
+    ws = torch.empty(2 + B * heads * 2, device=ctx.device, dtype=torch.float32) if code == L.BF16 and d == 64 else None
+    L.check(L.lib().dcb_attention_ws(code, base + q_off * es, base + k_off * es, base + v_off * es, ld, B, Ntok, heads, d,
+                                     float(d) ** -0.5, out.data_ptr(), Cw, _p(ws), ctx.stream()), "attention")
     return out
 
 

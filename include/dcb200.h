@@ -135,6 +135,10 @@ int dcb_layernorm(int dtype, const void* x, int64_t rows, int C, const float* ga
  * q/k/v: [B, Ntok, heads, d] views with row stride ld (elements); out [B, Ntok, heads*d] row stride out_ld */
 int dcb_attention(int dtype, const void* q, const void* k, const void* v, int ld, int B, int Ntok, int heads, int d,
                   float scale, void* out, int out_ld, dcb_stream stream);
+/* same with a [2 + B*heads*2] fp32 workspace: lets the tcgen05 kernel (d = 64) take its single-pass path, which uses
+ * max|q| max|k| per (batch, head) as the softmax reference instead of a running maximum (exact; falls back by itself) */
+int dcb_attention_ws(int dtype, const void* q, const void* k, const void* v, int ld, int B, int Ntok, int heads, int d,
+                     float scale, void* out, int out_ld, float* ws, dcb_stream stream);
 
 /* ---- (5) Haar DWT / IDWT (utils/wavelet.py:4-35 / 37-67), batched NCHW fp32 -------------------------------
  * dwt: [B,C,H,W] -> [B,4C,H/2,W/2] channel order 4i+{0,1,2,3} = cA,cH,cV,cD; out *= post_scale */
