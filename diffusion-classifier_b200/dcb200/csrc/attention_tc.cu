@@ -1,4 +1,5 @@
-// attention_tc.cu -- tcgen05 / TMEM flash attention (forward, no mask) for head dim 64: softmax(Q K^T * scale) V per
+// attention_tc.cu -- tcgen05 / TMEM flash attention (forward, no mask) for head dim 64 (two kernels: the running-maximum
+// kernel documented here and the single-pass kernel further down, which the launcher prefers for N >= 1024): softmax(Q K^T * scale) V per
 // (batch, head), replacing F.scaled_dot_product_attention behind diffusers' AttnProcessor2_0
 // for the DiT blocks (12 heads x 64, N = 4096 tokens) and the U-Net Transformer2D blocks with C/8 = 64.
 //
