@@ -32,7 +32,8 @@ class GemmDesc(C.Structure):
                 ("mse_target", c_void_p), ("mse_scale", c_void_p), ("mse_part", c_void_p), ("gn_part", c_void_p),
                 ("rowvec_ld", c_i32), ("gate_ld", c_i32), ("rows_per_group", c_i32), ("act", c_i32),
                 ("act_post", c_i32), ("res_ld", c_i32), ("res_mod", c_i32), ("res_dtype", c_i32),
-                ("out_ld", c_i32), ("out_dtype", c_i32), ("mse_div", c_i32), ("mse_ld", c_i32)]
+                ("out_ld", c_i32), ("out_dtype", c_i32), ("mse_div", c_i32), ("mse_ld", c_i32), ("up_phase", c_i32),
+                ("_r2", c_i32)]
 
 
 _PROTOS = {

@@ -66,6 +66,9 @@ static int to_dev(const dcb_gemm_desc* d, GemmDev* g) {
   e.res_ld = d->res_ld; e.res_mod = d->res_mod; e.res_dtype = d->res_dtype;
   e.out_ld = d->out_ld; e.out_dtype = d->out_dtype;
   e.mse_div = d->mse_div > 0 ? d->mse_div : 1; e.mse_ld = d->mse_ld;
+  e.up_phase = d->up_phase; e.OH = d->OH; e.OW = d->OW;
+  DCB_REQUIRE(e.up_phase >= 0 && e.up_phase <= 4, "gemm: up_phase must be 0..4");
+  DCB_REQUIRE(e.up_phase == 0 || (e.mse_part == nullptr && e.residual == nullptr), "gemm: up_phase excludes residual / fused MSE");
   DCB_REQUIRE(e.out != nullptr || e.mse_part != nullptr, "gemm: nothing to produce (out and mse_part both NULL)");
   DCB_REQUIRE((e.rowvec == nullptr && e.gate == nullptr) || e.rows_per_group > 0, "gemm: rows_per_group needed");
   DCB_REQUIRE(e.mse_part == nullptr || e.mse_target != nullptr, "gemm: mse_part without mse_target");

@@ -167,6 +167,8 @@ struct EpiDev {
   int res_ld, res_mod, res_dtype;
   int out_ld, out_dtype;
   int mse_div, mse_ld;
+  int up_phase;         // 0 or 1 + 2a + b (sub-pixel phase of a folded 2x upsample; see dcb200.h)
+  int OH, OW;           // output grid of THIS launch (the low-resolution grid when up_phase != 0)
 };
 
 struct GemmDev {
@@ -177,6 +179,14 @@ struct GemmDev {
   const void* W;
   EpiDev epi;
 };
+
+// output row of GEMM row m (identity, or the strided position of a folded-upsample phase)
+__device__ __forceinline__ int64_t out_row_of(const EpiDev& e, int m) {
+  if (e.up_phase == 0) return m;
+  const int a = (e.up_phase - 1) >> 1, b = (e.up_phase - 1) & 1;
+  const int x = m % e.OW, y = (m / e.OW) % e.OH, n = m / (e.OW * e.OH);
+  return ((int64_t)n * 2 * e.OH + 2 * y + a) * (2 * e.OW) + 2 * x + b;
+}
 
 // scalar epilogue for one accumulator value (column index n is in OUTPUT space; bias handled by caller)
 __device__ __forceinline__ float epi_scalar(const EpiDev& e, int m, int n, float v) {

@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmDev g) {
         v += e.bias[n];
       }
       v = epi_scalar(e, m, n, v);
-      if (e.out) store_from_f(e.out, e.out_dtype, (int64_t)m * e.out_ld + n, v);
+      if (e.out) store_from_f(e.out, e.out_dtype, out_row_of(e, m) * e.out_ld + n, v);
     }
   }
 }

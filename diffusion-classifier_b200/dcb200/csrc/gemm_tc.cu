@@ -97,7 +97,7 @@ __device__ __forceinline__ void epi_store16(const EpiDev& e, int m, int n0, floa
       }
   }
   if (e.out) {
-    const int64_t off = (int64_t)m * e.out_ld + n0;
+    const int64_t off = out_row_of(e, m) * e.out_ld + n0;
     if (e.out_dtype == DCB_BF16 && nvalid == 16 && (off & 7) == 0) {
       uint4* op = reinterpret_cast<uint4*>((__nv_bfloat16*)e.out + off);
       op[0] = pack_bf16x8(v);

@@ -238,7 +238,10 @@ __device__ __forceinline__ void staged_epilogue(const EpiGeom& gq, const EpiDev&
             const int wrow0 = tn * BN;
     const int ncols_out = geglu ? 128 : BN;
     const int ocol0 = geglu ? tn * 128 : tn * BN;
-    s_m[r] = row_ok ? m : -1;
+    // output row: identity, or the (2y + a, 2x + b) position of a folded-upsample phase
+    const int up_a = (e.up_phase - 1) >> 1, up_b = (e.up_phase - 1) & 1;
+    const int m_out = e.up_phase ? ((nb * 2 * gq.OH + 2 * y + up_a) * (2 * gq.OW) + 2 * x + up_b) : m;
+    s_m[r] = row_ok ? m_out : -1;
     if (e.residual) s_res[r] = row_ok ? (e.res_idx ? e.res_idx[m] : (e.res_mod > 0 ? m % e.res_mod : m)) : -1;
     for (int c = et; c < BN; c += 128) s_bias[c] = (e.bias && wrow0 + c < e.N) ? e.bias[wrow0 + c] : 0.f;
     if (gq.uniform && (e.rowvec || e.gate) && et < ncols_out) {
@@ -385,7 +388,10 @@ __device__ __forceinline__ void staged_epilogue(const EpiGeom& gq, const EpiDev&
       if (et < ncols_out && ocol0 + et < e.n_out && tb * gq.bn < gq.NB) {  // (tc2's odd tail sub-tile has no slot)
         const float s4 = (red[et * 2] + red[(128 + et) * 2]) + (red[(256 + et) * 2] + red[(384 + et) * 2]);
         const float q4 = (red[et * 2 + 1] + red[(128 + et) * 2 + 1]) + (red[(256 + et) * 2 + 1] + red[(384 + et) * 2 + 1]);
-        float* gp = e.gn_part + ((int64_t)tm_lin * e.n_out + ocol0 + et) * 2;
+        // phases of a folded upsample interleave their tiles per sample: [n][phase][tile of the low-resolution grid]
+        const int tps = gq.tiles_x * gq.tiles_y;
+        const int64_t gtile = e.up_phase ? ((int64_t)(tb * 4 + e.up_phase - 1) * tps + (tm_lin - tb * tps)) : (int64_t)tm_lin;
+        float* gp = e.gn_part + (gtile * e.n_out + ocol0 + et) * 2;
         gp[0] = s4;
         gp[1] = q4;
       }

@@ -58,6 +58,7 @@ class GemmProfile:
 
 PROFILE = None
 USE_TILE_STATS = __import__("os").environ.get("DCB_TILE_STATS", "1") != "0"
+FOLD_UPSAMPLE = __import__("os").environ.get("DCB_FOLD_UPSAMPLE", "1") != "0"   # A/B switch for upsample_conv
 
 
 def _p(t):
@@ -75,13 +76,16 @@ def conv3x3_segs(src, C_, H, W, stride=1, nb_div=1):
 
 def gemm(ctx: Ctx, segs, W, N, NB, OH, OW, *, bias=None, rowvec=None, rowvec_ld=0, rowvec_idx=None, rows_per_group=0,
          gate=None, gate_ld=0, residual=None, res_ld=0, res_mod=0, res_idx=None, act=L.ACT_NONE, act_post=L.ACT_NONE,
-         out=None, out_dtype=None, out_ld=None, mse=None, want_out=True, k_alg=None, gn_stats=False):
+         out=None, out_dtype=None, out_ld=None, mse=None, want_out=True, k_alg=None, gn_stats=False, up_phase=0,
+         gn_part=None):
     """D = sum_seg A_seg . W^T with the fused epilogue; returns the [M, n_out] output (or None if want_out=False).
 
     mse = dict(target=, scale=, div=, ld=, err=[S] fp32 out) enables the fused eps-MSE epilogue (tcgen05 only).
     gn_stats=True returns ``(out, part)``: part [ceil(M/128), n_out, 2] fp32 holds per-128-row-tile, per-column
     (sum, sumsq) of the written values -- the next GroupNorm's statistics -- or None when this launch cannot
     produce them (fp32 verify engine, 256-wide direct-epilogue tiles).
+    up_phase = 1 + 2a + b: this launch is phase (a, b) of a folded 2x nearest upsample + conv (see ``upsample_conv``);
+    ``out`` ([NB*4*OH*OW, n_out]) and ``gn_part`` are then shared by the four phase launches and supplied by the caller.
     """
     lib = L.lib()
     d = L.GemmDesc()
@@ -102,6 +106,8 @@ def gemm(ctx: Ctx, segs, W, N, NB, OH, OW, *, bias=None, rowvec=None, rowvec_ld=
     d.residual, d.res_idx, d.res_ld, d.res_mod = _p(residual), _p(res_idx), res_ld, res_mod
     d.res_dtype = L.F32 if (residual is not None and residual.dtype == torch.float32) else L.BF16
     d.act, d.act_post = act, act_post
+    d.up_phase = up_phase
+    assert up_phase == 0 or out is not None
     odt = out_dtype or ctx.tdtype
     if want_out and out is None:
         out = torch.empty(M, n_out if out_ld is None else out_ld, device=ctx.device, dtype=odt)
@@ -114,7 +120,8 @@ def gemm(ctx: Ctx, segs, W, N, NB, OH, OW, *, bias=None, rowvec=None, rowvec_ld=
         ok = C.c_int32()
         L.check(lib.dcb_gemm_gn_layout(C.byref(d), C.byref(ok)), "gemm_gn_layout")
         if ok.value:
-            gpart = torch.empty((M + 127) // 128, n_out, 2, device=ctx.device, dtype=torch.float32)
+            gpart = gn_part if gn_part is not None else \
+                torch.empty((M + 127) // 128, n_out, 2, device=ctx.device, dtype=torch.float32)
             d.gn_part = gpart.data_ptr()
     part = None
     if mse is not None:
@@ -147,6 +154,44 @@ def linear(ctx, x, W, N, *, K=None, c_off=0, **kw):
     """x: [M, C] row-major tokens; uses channels [c_off, c_off+K)."""
     M, C_ = x.shape
     return gemm(ctx, [seg(x, C_, 1, M, c_off, K if K is not None else C_ - c_off)], W, N, 1, 1, M, **kw)
+
+
+def upsample_conv(ctx, x, wph, bias, C_, N, NB, H, W):
+    """Upsample2D (nearest 2x, then conv3x3 pad 1) without the upsampled tensor: output pixel (2y + a, 2x + b) only ever
+    sees a 2x2 neighbourhood of the LOW-resolution input (rows y - 1 + a, y + a; columns x - 1 + b, x + b), with the 3x3
+    taps that land on the same source pixel summed -- four 2x2-tap convs (K = 4 C instead of 9 C: 2.25x fewer FLOPs,
+    no 4x larger intermediate).  wph[2a + b]: [N, (ty, tx, c)] phase weights (``fold_upsample_weights``).
+    x: [NB*H*W, C_] -> ([NB*2H*2W, N], GroupNorm tile statistics or None)."""
+    out = ctx.empty(NB * 4 * H * W, N)
+    want = H * W % 128 == 0                     # tile statistics need tiles that lie inside one sample
+    gp = torch.empty(NB * 4 * H * W // 128, N, 2, device=ctx.device, dtype=torch.float32) if want else None
+    st = None
+    for a in range(2):
+        for b in range(2):
+            segs = [seg(x, C_, H, W, 0, C_, a - 1 + ty, b - 1 + tx) for ty in range(2) for tx in range(2)]
+            r = gemm(ctx, segs, wph[2 * a + b], N, NB, H, W, bias=bias, out=out, up_phase=1 + 2 * a + b,
+                     gn_stats=want, gn_part=gp)
+            st = r[1] if want else None
+    return out, st
+
+
+def fold_upsample_weights(w):
+    """[Cout, Cin, 3, 3] conv weight (fp32) -> four [Cout, (ty, tx, Cin)] phase weights of ``upsample_conv``:
+    phase a = 0 reads source rows (y - 1, y) with taps (ky0, ky1 + ky2); a = 1 reads (y, y + 1) with (ky0 + ky1, ky2)."""
+    grp = {0: ((0,), (1, 2)), 1: ((0, 1), (2,))}
+    out = []
+    for a in range(2):
+        for b in range(2):
+            taps = []
+            for ty in range(2):
+                for tx in range(2):
+                    acc = 0
+                    for ky in grp[a][ty]:
+                        for kx in grp[b][tx]:
+                            acc = acc + w[:, :, ky, kx]
+                    taps.append(acc)
+            out.append(torch.stack(taps, 1).reshape(w.shape[0], -1).contiguous())
+    return out
 
 
 def gn_chunks(NB, HW, Ctot):

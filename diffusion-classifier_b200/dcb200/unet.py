@@ -339,6 +339,8 @@ class UNetCondition2D(nn.Module):
                 if hasattr(blk, name):
                     s = getattr(blk, name)[0]
                     pk.samp[id(s)] = SimpleNamespace(w=w(conv_w(s.conv)), b=f32(s.conv.bias))
+                    if name == "upsamplers":   # nearest-2x + conv3x3 folded into four 2x2-tap phase convs
+                        pk.samp[id(s)].wph = [w(p) for p in E.fold_upsample_weights(s.conv.weight.detach().float())]
         pk.out_g, pk.out_bn = f32(self.conv_norm_out.weight), f32(self.conv_norm_out.bias)
         pk.out_w, pk.out_b = w(conv_w(self.conv_out)), f32(self.conv_out.bias)
         return pk
@@ -468,9 +470,14 @@ class UNetCondition2D(nn.Module):
                     h = self._transformer(ctx, pk.tr[id(blk.attentions[j])], xattn, xattn_idx, h, U, rep, H, W)
             if hasattr(blk, "upsamplers"):
                 sp = pk.samp[id(blk.upsamplers[0])]
-                up = E.upsample2x(ctx, h.t, S, H, W, h.C)
-                H, W = 2 * H, 2 * W
-                h = _Act(E.gemm(ctx, E.conv3x3_segs(up, h.C, H, W), sp.w, h.C, S, H, W, bias=sp.b, gn_stats=True), h.C, 1)
+                if E.FOLD_UPSAMPLE:
+                    h = _Act(E.upsample_conv(ctx, h.t, sp.wph, sp.b, h.C, h.C, S, H, W), h.C, 1)
+                    H, W = 2 * H, 2 * W
+                else:
+                    up = E.upsample2x(ctx, h.t, S, H, W, h.C)
+                    H, W = 2 * H, 2 * W
+                    h = _Act(E.gemm(ctx, E.conv3x3_segs(up, h.C, H, W), sp.w, h.C, S, H, W, bias=sp.b, gn_stats=True),
+                             h.C, 1)
         assert h.div == 1
         Ch = h.C
         a = E.groupnorm(ctx, h.t, Ch, None, 0, S, H * W, pk.out_g, pk.out_bn, self.config.norm_eps, True, st0=h.st)

@@ -92,6 +92,11 @@ typedef struct dcb_gemm_desc {
   int32_t res_ld, res_mod, res_dtype;
   int32_t out_ld, out_dtype;
   int32_t mse_div, mse_ld;
+  int32_t up_phase;          /* 0: out row = m.  1 + 2a + b: this GEMM computes phase (a, b) of a 2x nearest-upsampled
+                                output (Upsample2D + conv folded into four 2x2-tap convs over the LOW-resolution input):
+                                row m = (n, y, x) of the (OH, OW) grid is stored at row (n, 2y + a, 2x + b) of the
+                                (2 OH, 2 OW) output; gn_part tiles are laid out [n][phase][tile] */
+  int32_t _r2;
 } dcb_gemm_desc;
 
 int dcb_gemm(const dcb_gemm_desc* d, dcb_stream stream);

@@ -247,7 +247,7 @@ def test_c_abi_exports_every_declared_symbol():
     assert lib.dcb_version() == 100 and lib.dcb_launch_count() == 0
     import ctypes
     assert ctypes.sizeof(_lib.Seg) == 48 == lib.dcb_struct_size(0)
-    assert ctypes.sizeof(_lib.GemmDesc) == 752 == lib.dcb_struct_size(1)
+    assert ctypes.sizeof(_lib.GemmDesc) == 760 == lib.dcb_struct_size(1)
 
 
 def test_product_has_no_cpu_path():

@@ -302,3 +302,46 @@ def test_tc_epilogue_groupnorm_tile_statistics(dev, NB, H, W, Ci, Co, res):
     a = E.groupnorm(ctx, out, Co, sk_out, Co, NB, HW, g2, b2, 1e-5, True, div1=rep, st0=part, st1=sk_part)
     ref = E.groupnorm(ctx, out, Co, sk_out, Co, NB, HW, g2, b2, 1e-5, True, div1=rep)
     assert rel_err(a, ref) < 2e-3
+
+
+@pytest.mark.parametrize("NB,H,W,C", [(2, 64, 64, 128), (3, 16, 16, 256), (5, 8, 8, 128), (3, 4, 4, 64), (130, 32, 32, 64)])
+def test_upsample_conv_folded_phases(dev, NB, H, W, C):
+    """Upsample2D (a5.4: nearest 2x then conv3x3 pad 1) as four 2x2-tap phase GEMMs over the low-resolution input
+    (dcb_gemm_desc.up_phase) vs torch interpolate + conv2d, vs the unfolded upsample2x + 3x3 GEMM, on the tcgen05 and
+    SIMT engines; tile statistics of the interleaved output vs the written tensor."""
+    from dcb200 import _lib as L
+    from dcb200 import engine as E
+    torch.manual_seed(0)
+    x = _bf(NB, H, W, C, dev=dev)
+    w32 = torch.randn(C, C, 3, 3, device=dev) * 0.05
+    b = torch.randn(C, device=dev)
+    wph32 = E.fold_upsample_weights(w32)
+    wph = [p.to(torch.bfloat16) for p in wph32]
+    up = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest")
+    # exact identity in real arithmetic: checked in fp32 with the un-rounded folded weights on the CUDA-core engine
+    ref32 = F.conv2d(up, w32, b, padding=1).permute(0, 2, 3, 1).reshape(-1, C)
+    c32 = E.Ctx(device=dev, precision="fp32")
+    o32, _ = E.upsample_conv(c32, x.float().reshape(-1, C).contiguous(), wph32, b, C, C, NB, H, W)
+    assert rel_err(o32, ref32) < 1e-5
+    # bf16: reference = the same bf16-rounded phase weights applied by torch (isolates the kernel from weight rounding)
+    ref = torch.empty(NB, 2 * H, 2 * W, C, device=dev)
+    xp = F.pad(x.float().permute(0, 3, 1, 2), (1, 1, 1, 1))
+    for a in range(2):
+        for bb in range(2):
+            wk = wph[2 * a + bb].float().reshape(C, 2, 2, C).permute(0, 3, 1, 2)
+            y = F.conv2d(xp[:, :, a:a + H + 1, bb:bb + W + 1], wk, b)
+            ref[:, a::2, bb::2, :] = y.permute(0, 2, 3, 1)
+    ref = ref.reshape(-1, C)
+    assert rel_err(ref, ref32) < 1e-2          # folded-then-rounded weights vs the 3x3 conv: bf16 weight rounding only
+    ctx = _ctx(dev)
+    out, st = E.upsample_conv(ctx, x.reshape(-1, C), wph, b, C, C, NB, H, W)
+    assert out.dtype == torch.bfloat16 and rel_err(out, ref) < 4e-3
+    simt, _ = E.upsample_conv(_ctx(dev, L.ENGINE_SIMT), x.reshape(-1, C), wph, b, C, C, NB, H, W)
+    assert rel_err(out, simt) < 4e-3
+    if H * W % 128 == 0:
+        assert st is not None and st.shape == (NB * 4 * H * W // 128, C, 2)
+        got = st.reshape(NB, -1, C, 2).double().sum(1)
+        o = out.reshape(NB, 4 * H * W, C).double()
+        assert rel_err(got[..., 0], o.sum(1)) < 1e-5 and rel_err(got[..., 1], (o * o).sum(1)) < 1e-5
+    else:
+        assert st is None
