@@ -34,7 +34,10 @@ WORKLOADS = {
     # name: (arch key in tests/helpers.py, classes, timesteps, GFLOP/eval, images per GPU per step)
     "unet128": ("UNET128", 2, 100, 175.79, 4),
     "cifar": ("CIFAR_UNET", 10, 32, 10.454, 16),
-    "dit": ("DIT_B4_256", 2, 25, 1315.0, 1),     # BASELINE configs[3]: CheXpert-256 DiT-B/4 (attention + adaLN kernels)
+    "dit": ("DIT_B4_256", 2, 250, 1315.0, 1),    # BASELINE configs[3]: CheXpert-256 DiT-B/4 (attention + adaLN kernels)
+    "unet256": ("UNET256", 2, 250, 530.10, 1),   # BASELINE configs[2]: CheXpert 256x256 U-Net, shifted cosine schedule
+    # BASELINE configs[4]: 10-channel 256x256 pixels -> GPU Haar DWT (/2) -> 40x128x128 wavelet-domain U-Net, full sweep
+    "ipmsa": ("IPMSA5_DWT_UNET", 2, 1000, 189.96, 1),
 }
 
 
@@ -47,6 +50,10 @@ def build_workload(name):
                            image_size=S, schedule="cosine", pred_param="eps")
     if name == "dit":
         cfg.encoder_type = "DiT"
+    if name == "unet256":
+        cfg.schedule, cfg.noise_d = "shifted_cosine", 64
+    if name == "ipmsa":
+        cfg.wavelet_transform = True
     return arch, cfg, classes, T, gflop, ipg
 
 
@@ -97,8 +104,11 @@ def cpu_port_run(arch, cfg, n_img, n_t, threads, seed=0):
     from oracle import loop
     torch.set_num_threads(threads)
     torch.manual_seed(seed)
-    net = dr.UNet2DConditionModel(**arch).eval()
-    enc = torch.nn.Embedding(cfg.classes + 1, arch["encoder_hid_dim"])
+    if "patch_size" in arch:
+        net, enc = dr.DiTTransformer2DModel(**arch).eval(), None
+    else:
+        net = dr.UNet2DConditionModel(**arch).eval()
+        enc = torch.nn.Embedding(cfg.classes + 1, arch["encoder_hid_dim"])
     import copy
     c2 = copy.deepcopy(cfg)
     c2.evaluation_per_stage = [n_t]
@@ -122,7 +132,7 @@ def run_reference(args):
         return
     arch, cfg, classes, T, gflop, ipg = build_workload(args.workload)
     threads = len(os.sched_getaffinity(0))
-    n_t = 16 if args.workload == "unet128" else 8
+    n_t = {"unet128": 16, "cifar": 8, "ipmsa": 8}.get(args.workload, 2)
     for _ in range(args.warmup):
         cpu_port_run(arch, cfg, 1, 1, threads)
     vals, times = [], []
@@ -150,7 +160,11 @@ def workload_name(w, classes, T):
             "cifar": f"CIFAR-10 32x32 class-conditional U-Net (experiments/cifar10) ELBO classification, {classes} "
                      f"classes x {T} timesteps",
             "dit": f"CheXpert 256x256 DiT-B/4 (models/chexpert-256-dit-b4) ELBO classification, {classes} classes x {T} "
-                   f"timesteps"}[w]
+                   f"timesteps",
+            "unet256": f"CheXpert 256x256 U-Net (models/unet-256.py) healthy/sick ELBO classification, {classes} classes x "
+                       f"{T} timesteps, 3x256x256, shifted cosine schedule",
+            "ipmsa": f"IPMSA 5-channel-pair DWT U-Net (models/ipmsa-5-dwt-unet.py): 10x256x256 pixels -> Haar DWT on the "
+                     f"GPU -> 40x128x128 wavelet-domain ELBO classification, {classes} classes x {T} timesteps"}[w]
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -177,7 +191,12 @@ def run_ours(args):
     dc = dcb200.DiffusionClassifier(net, cfg).to(dev).eval()
     S, C = arch["sample_size"], arch["in_channels"]
     g = torch.Generator().manual_seed(0)
-    x_host = (torch.rand(BS, C, S, S, generator=g) * 2 - 1).pin_memory()
+    if args.workload == "ipmsa":   # pixel-space input; the wavelet transform (utils/wavelet.py, /2 as in
+        x_host = (torch.rand(BS, C // 4, 2 * S, 2 * S, generator=g) * 2 - 1).pin_memory()   # experiments/ipmsa/inference.py:153-155)
+        pre = lambda v: dcb200.wavelet_dec_2(v, 0.5)                                        # runs on the GPU inside every step
+    else:
+        x_host = (torch.rand(BS, C, S, S, generator=g) * 2 - 1).pin_memory()
+        pre = lambda v: v
     x_dev = x_host.to(dev)
     evals_per_step = BS * classes * T
 
@@ -201,11 +220,11 @@ def run_ours(args):
 
     def step_resident():
         torch.manual_seed(1234)  # same t stream on every rank (CPU generator, as diffusion_classifier.py:688)
-        return dc.classify(x_dev)
+        return dc.classify(pre(x_dev))
 
     def step_e2e():
         torch.manual_seed(1234)
-        labels = dc.classify(x_host.to(dev, non_blocking=True))
+        labels = dc.classify(pre(x_host.to(dev, non_blocking=True)))
         return labels.cpu()
 
     for _ in range(max(args.warmup, 3)):
@@ -262,7 +281,7 @@ def run_ours(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         threads = len(os.sched_getaffinity(0))
-        n_t = 32 if args.workload == "unet128" else 8
+        n_t = {"unet128": 32, "cifar": 8, "ipmsa": 16}.get(args.workload, 4)
         cpu_port_run(arch, cfg, 1, 1, threads)
         v, dt = cpu_port_run(arch, cfg, 1, n_t, threads)
         cpu = {"value": v, "unit": "evals/s", "cores": threads, "kind": "port", "seconds": dt,
