@@ -9,6 +9,7 @@ fallback -- importing the ops without the built library raises.
 from ._lib import DcbError, launch_count, lib  # noqa: F401
 from .classifier import DiffusionClassifier  # noqa: F401
 from .dit import DiT  # noqa: F401
+from . import metrics  # noqa: F401
 from .ema import EMA  # noqa: F401
 from .unet import UNetCondition2D  # noqa: F401
 from .wavelet import wavelet_dec_2, wavelet_enc_2  # noqa: F401

@@ -43,6 +43,8 @@ _PROTOS = {
     "dcb_note_graph_replay": (None, [c_i64]),
     "dcb_prologue": (c_int, [c_int, c_int, c_void_p, c_void_p, c_u64, c_i64, c_void_p, c_void_p, c_void_p, c_int, c_int,
                              c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "dcb_ddpm_step": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_u64, c_i64, c_int,
+                              c_int, c_int, c_int, c_void_p, c_void_p]),
     "dcb_timestep_embed": (c_int, [c_int, c_void_p, c_int, c_int, c_int, c_float, c_float, c_void_p, c_void_p]),
     "dcb_gemm": (c_int, [C.POINTER(GemmDesc), c_void_p]),
     "dcb_struct_size": (c_int, [c_int]),

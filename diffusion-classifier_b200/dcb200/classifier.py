@@ -309,23 +309,275 @@ class DiffusionClassifier(nn.Module):
         self.last_errors = errors
         return classes[:, 0]
 
-    # ---- callers of the hot path (diffusion_classifier.py:532-578); next-row f1 in SURVEY 8 ---------------------
+    # ---- helpers shared by sample / loss -----------------------------------------------------------------------
+    def clip(self, x):
+        return torch.clamp(x, -1, 1)
+
+    def diffuse(self, x, alpha_t, sigma_t):
+        """reference API (:100-117): returns (z_t, eps).  Used by callers outside the launch sequences (the hot paths
+        fuse q_sample into dcb_prologue)."""
+        eps_t = torch.randn_like(x)
+        return alpha_t * x + sigma_t * eps_t, eps_t
+
+    def _denoiser_setup(self, net, dev):
+        is_dit = isinstance(net, DiT)
+        if not isinstance(net, (UNetCondition2D, DiT)):
+            raise TypeError("backbone must be a dcb200.UNetCondition2D or dcb200.DiT")
+        ctx = net.make_ctx(dev)
+        pk = net.packed(ctx)
+        table = None if is_dit else net.cross_attn_table(ctx, pk, E.cast(ctx, self.encoder.weight))
+        return is_dit, ctx, pk, table
+
+    def _sampler_coefs(self, from_t, dev):
+        """[sampling_steps + 1, 8] fp32 rows {c, a_t, a_s, s_t, s_s, sqrt(var), w, 0} and the logsnr fed to the denoiser per
+        evaluation, computed exactly as ddpm_sampler_step does (:189-205).  The last row is the reference's separate
+        "final step" (:268-288), which re-evaluates at steps[-2]."""
+        n = int(self.config.sampling_steps)
+        steps = torch.linspace(from_t, 0.0, n + 1)
+        lt = torch.cat([self.schedule(steps[:-1]), self.schedule(steps[-2:-1])]).float()
+        ls = torch.cat([self.schedule(steps[1:]), self.schedule(steps[-1:])]).float()
+        c = -torch.special.expm1(lt - ls)
+        a_t, a_s = torch.sqrt(torch.sigmoid(lt)), torch.sqrt(torch.sigmoid(ls))
+        s_t, s_s = torch.sqrt(torch.sigmoid(-lt)), torch.sqrt(torch.sigmoid(-ls))
+        sd = torch.sqrt((s_s ** 2) * c)
+        w = torch.full_like(c, float(self.cfg_w))
+        return torch.stack([c, a_t, a_s, s_t, s_s, sd, w, torch.zeros_like(c)], 1).contiguous().to(dev), lt.to(dev)
+
+    # ---- next row f2: DDPM ancestral sampler with classifier-free guidance (:175-293) ------------------------------
+    @torch.no_grad()
+    def ddpm_sampler_step(self, z_t, pred, u_pred, logsnr_t, logsnr_s):
+        """reference signature (:176-207): (mu, variance).  mu comes from dcb_ddpm_step (noise-free, unclipped)."""
+        dev = z_t.device
+        lt, ls = logsnr_t.reshape(-1)[:1].float().cpu(), logsnr_s.reshape(-1)[:1].float().cpu()
+        c = -torch.special.expm1(lt - ls)
+        a_t, a_s = torch.sqrt(torch.sigmoid(lt)), torch.sqrt(torch.sigmoid(ls))
+        s_t, s_s = torch.sqrt(torch.sigmoid(-lt)), torch.sqrt(torch.sigmoid(-ls))
+        var = (s_s ** 2) * c
+        coef = torch.cat([c, a_t, a_s, s_t, s_s, torch.sqrt(var), torch.tensor([float(self.cfg_w)]),
+                          torch.zeros(1)]).float().to(dev)
+        B, C, H, W = z_t.shape
+        pair = torch.stack([pred, u_pred], 1).reshape(2 * B, C, H * W).transpose(1, 2).contiguous().float()  # NHWC rows
+        ctx = E.Ctx(device=dev, precision="fp32")
+        mu = E.ddpm_step(ctx, z_t.contiguous().float(), pair, 2, 0, coef, self.pred_param == 'v', False,
+                         noise=torch.zeros_like(z_t, dtype=torch.float32))
+        return mu, var.to(dev)
+
+    @torch.no_grad()
+    def sample(self, x, text=None, from_t=1, z_init=None, noise_all=None):
+        """Same contract as the reference's ``sample(x, text, from_t)``.  Per step ONE denoiser launch sequence scores
+        the conditional and the unconditional (null-token) branch as the two "classes" of every image -- the same batch
+        folding (and, for the U-Net, the same shared class-independent prefix) as ``classify`` -- and dcb_ddpm_step fuses
+        guidance, x-prediction, clipping, the posterior mean and the z_s draw.  With cfg_w == 0 the unconditional
+        branch has weight exactly 0 and is not evaluated.  ``z_init`` / ``noise_all`` [steps,B,C,H,W] inject pre-drawn
+        noise for parity runs (default: z_T as the reference draws it, per-step noise from the in-kernel Philox)."""
+        if not x.is_cuda:
+            raise RuntimeError("dcb200.DiffusionClassifier.sample needs CUDA tensors; there is no CPU path")
+        if text is None or self.encoder_type is None:
+            raise NotImplementedError("the reference's denoisers are class-conditional: sample() needs `text` labels")
+        dev = x.device
+        B, Cimg, H, W = x.shape
+        net = self.ema.ema_model
+        is_dit, ctx, pk, table = self._denoiser_setup(net, dev)
+        if z_init is not None:
+            z = z_init.to(dev).float().contiguous()
+        elif from_t == 1:
+            z = torch.randn(x.shape).to(dev)                              # :221, CPU generator like the reference
+        else:
+            logsnr = self.schedule(torch.ones(B) * from_t).to(dev)
+            z, _ = self.diffuse(x.float(), torch.sqrt(torch.sigmoid(logsnr)).view(-1, 1, 1, 1),
+                                torch.sqrt(torch.sigmoid(-logsnr)).view(-1, 1, 1, 1))
+            z = z.contiguous()
+        coef, lt = self._sampler_coefs(from_t, dev)
+        n = int(self.config.sampling_steps)
+        guided = float(self.cfg_w) != 0.0
+        rep = 2 if guided else 1
+        text = text.to(dev).reshape(-1)
+        cls = torch.stack([text, torch.full_like(text, self.null_token)], 1) if guided else text.reshape(-1, 1)
+        cls32 = cls.reshape(-1).to(torch.int32).contiguous()
+        share = (not is_dit) and guided
+        patch = net.config.patch_size if is_dit else 1
+        v_param = self.pred_param == 'v'
+        seed = int(torch.initial_seed() & 0x7FFFFFFFFFFFFFFF) + 0x9E3779B9 * self._eps_calls
+        self._eps_calls += 1
+        for i in range(n + 1):
+            a_in, _ = E.prologue(ctx, 1 if is_dit else 0, z, B, 1 if share else rep, Cimg, H, W, pk.kpad_in, patch=patch)
+            t = lt[i].expand(B).contiguous()
+            if is_dit:
+                pred = net.run(ctx, pk, a_in, t, B, rep, cls32)
+            else:
+                pred = net.run(ctx, pk, a_in, t, B, rep, H, W, table, xattn_idx=cls32, share_prefix=share)
+            final = i == n
+            noise = None if (final or noise_all is None) else noise_all[i].to(dev).float().contiguous()
+            z = E.ddpm_step(ctx, z, pred, rep, patch if is_dit else 0, coef[i], v_param, final, noise=noise, seed=seed,
+                            unit_id0=i * B)
+        return z
+
+    # ---- next row f4: training loss, forward only (:295-344) --------------------------------------------------------
+    @torch.no_grad()
+    def loss(self, x, text=None, t=None, eps=None):
+        """min-SNR weighted eps-MSE of the ONLINE model (forward only: no autograd graph is built -- training's backward is
+        outside this library).  q_sample is the fused prologue, the squared error the fused epilogue of the last GEMM."""
+        if not x.is_cuda:
+            raise RuntimeError("dcb200.DiffusionClassifier.loss needs CUDA tensors; there is no CPU path")
+        if text is None or self.encoder_type is None:
+            raise NotImplementedError("the reference's denoisers are class-conditional: loss() needs `text` labels")
+        dev = x.device
+        B, Cimg, H, W = x.shape
+        t = torch.rand(B) if t is None else t.detach().cpu().float()
+        net = self.model
+        is_dit, ctx, pk, table = self._denoiser_setup(net, dev)
+        logsnr = self.schedule(t).to(dev).float()
+        alpha = torch.sqrt(torch.sigmoid(logsnr)).contiguous()
+        sigma = torch.sqrt(torch.sigmoid(-logsnr)).contiguous()
+        patch = net.config.patch_size if is_dit else 1
+        No = (patch * patch * Cimg) if is_dit else Cimg
+        rows = (H // patch) * (W // patch)
+        v_param = self.pred_param == 'v'
+        seed = int(torch.initial_seed() & 0x7FFFFFFFFFFFFFFF) + 0x9E3779B9 * self._eps_calls
+        self._eps_calls += 1
+        a_in, target = E.prologue(ctx, 1 if is_dit else 0, x.contiguous().float(), B, 1, Cimg, H, W, pk.kpad_in,
+                                  patch=patch, eps=None if eps is None else eps.to(dev).float().contiguous(), seed=seed,
+                                  alpha=alpha, sigma=sigma, want_target=True, v_param=v_param)
+        err = torch.empty(B, device=dev, dtype=torch.float32)
+        mse = dict(target=target, div=1, ld=No, err=err, fused=(ctx.precision == "bf16") and rows % 128 == 0,
+                   scale=alpha if v_param else None)
+        cls32 = text.to(dev).reshape(-1).to(torch.int32).contiguous()
+        if is_dit:
+            net.run(ctx, pk, a_in, logsnr.contiguous(), B, 1, cls32, mse=mse)
+        else:
+            net.run(ctx, pk, a_in, logsnr.contiguous(), B, 1, H, W, table, xattn_idx=cls32, mse=mse)
+        snr = torch.exp(logsnr).clamp_(max=5)
+        weight = 1 / (1 + snr) if v_param else 1 / snr
+        return (weight * err).sum() / (B * Cimg * H * W)
+
+    # ---- next row f1: callers of the hot paths (diffusion_classifier.py:532-655) -----------------------------------
+    @staticmethod
+    def _prefetched(loader, dev, stop_idx=None):
+        """batches of ``loader`` with every tensor on ``dev``: batch k+1 is copied (pinned staging, side stream) while
+        batch k is being scored, so the H2D never sits between two launch sequences."""
+        side = torch.cuda.Stream(dev)
+        it = iter(loader)
+
+        def load():
+            try:
+                b = next(it)
+            except StopIteration:
+                return None
+            out = {}
+            with torch.cuda.stream(side):
+                for k, v in b.items():
+                    if torch.is_tensor(v) and not v.is_cuda:
+                        v = v.pin_memory().to(dev, non_blocking=True)
+                    out[k] = v
+            ev = torch.cuda.Event()
+            ev.record(side)
+            return out, ev
+
+        idx, nxt = 0, load()
+        while nxt is not None:
+            cur, ev = nxt
+            last = stop_idx is not None and idx == stop_idx
+            nxt = None if last else load()
+            torch.cuda.current_stream(dev).wait_event(ev)
+            for v in cur.values():
+                if torch.is_tensor(v) and v.is_cuda:
+                    v.record_stream(torch.cuda.current_stream(dev))
+            yield cur
+            idx += 1
+
     @torch.no_grad()
     def evaluate(self, val_dataloader, stop_idx=None, metrics=None, classification=False, from_t=1):
-        if not classification:
-            raise NotImplementedError("sampling (DDPM + CFG) is outside the classification hot path (SURVEY 8 f2)")
+        """reference :532-578.  Differences in issue order only: the next batch's H2D overlaps the current batch's
+        launch sequences, and nothing here forces a host sync (use dcb200.metrics for counters that stay on the GPU)."""
         val_samples, batches = [], []
         dev = next(self.ema.ema_model.parameters()).device
-        for idx, batch in enumerate(val_dataloader):
-            batch = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in batch.items()}
+        for batch in self._prefetched(val_dataloader, dev, stop_idx):
             x = batch["images"]
             p = batch["prompt"] if "prompt" in batch.keys() else None
-            sample = self.classify(x, p, fast=bool(self.config.fast_classification))
+            if classification:
+                sample = self.classify(x, p, fast=bool(self.config.fast_classification))
+            else:
+                sample = self.sample(x, p, from_t)
             if metrics is not None:
                 for metric in metrics:
                     metric.update((sample, batch))
             val_samples.append(sample)
             batches.append(batch)
-            if stop_idx is not None and idx == stop_idx:
-                break
         return val_samples, batches, metrics
+
+    # ---- next row f3: accelerate-layout checkpoints (diffusion_classifier.py:727-805) --------------------------------
+    def _ckpt_modules(self):
+        mods = [self.model, self.ema]                       # accelerator.prepare order (:383-388 / :617-621)
+        if self.encoder_type == 'nn':
+            mods.append(self.encoder)
+        return mods
+
+    def save_checkpoint(self, checkpoint_dir, epoch=0, best_metric=None, experiment_key=None):
+        """writes what ``accelerator.save_state`` + the reference's experiment_state.pth write for the modules on the
+        inference path: model.safetensors, model_1.safetensors (EMA), model_2.safetensors (encoder)."""
+        from safetensors.torch import save_file
+        os.makedirs(checkpoint_dir, exist_ok=True)
+        for i, m in enumerate(self._ckpt_modules()):
+            sd = {k: v.detach().cpu().contiguous().clone() for k, v in m.state_dict().items()}
+            save_file(sd, os.path.join(checkpoint_dir, "model.safetensors" if i == 0 else f"model_{i}.safetensors"))
+        torch.save({"epoch": epoch, "best_metric": best_metric, "experiment_key": experiment_key},
+                   os.path.join(checkpoint_dir, "experiment_state.pth"))
+
+    def load_checkpoint(self, checkpoint_path, accelerator=None):
+        """reference :769-805 without accelerate: loads the state ``accelerator.save_state`` wrote (safetensors, or the
+        older pytorch_model*.bin) into model / ema / encoder -- diffusers state_dict keys, SURVEY Appendix B -- and
+        returns (epoch, best_metric, experiment_key).  Packed kernel weights are rebuilt lazily (parameter versions)."""
+        for i, m in enumerate(self._ckpt_modules()):
+            stem = "model" if i == 0 else f"model_{i}"
+            f_st = os.path.join(checkpoint_path, stem + ".safetensors")
+            f_bin = os.path.join(checkpoint_path, ("pytorch_model" if i == 0 else f"pytorch_model_{i}") + ".bin")
+            if os.path.exists(f_st):
+                from safetensors.torch import load_file
+                sd = load_file(f_st)
+            elif os.path.exists(f_bin):
+                sd = torch.load(f_bin, map_location="cpu", weights_only=True)
+            else:
+                raise FileNotFoundError(f"no {stem}.safetensors / .bin under {checkpoint_path}")
+            m.load_state_dict(sd)
+        epoch, best_metric, experiment_key = 0, None, None
+        state = os.path.join(checkpoint_path, "experiment_state.pth")
+        if os.path.exists(state):
+            ck = torch.load(state, map_location="cpu", weights_only=False)
+            epoch, best_metric, experiment_key = ck["epoch"], ck.get("best_metric"), ck.get("experiment_key")
+        return epoch, best_metric, experiment_key
+
+    @torch.no_grad()
+    def inference(self, optimizer=None, train_dataloader=None, val_dataloader=None, lr_scheduler=None, metrics=None,
+                  plot_function=None, classification=False, from_t=1, checkpoint_folder="checkpoints"):
+        """reference :580-655: load the most recent checkpoint, evaluate, sync the metrics, plot samples.  One process
+        per GPU (torchrun) replaces accelerate: with ``config.dcb_shard == 'timestep'`` every rank sees every batch and
+        ``classify`` shards the (image x timestep) units; otherwise ranks take batches round-robin (replicas)."""
+        import torch.distributed as dist
+        inference_image_path = os.path.join(self.config.experiment_path, "inference_images/")
+        os.makedirs(inference_image_path, exist_ok=True)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.to(dev)
+        checkpoint_path = os.path.join(self.config.experiment_path, checkpoint_folder)
+        self.load_checkpoint(checkpoint_path)
+        if metrics is not None:
+            for metric in metrics:
+                metric.set_device(dev)
+        self.model.eval()
+        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        replicas = multi and getattr(self.config, "dcb_shard", None) != "timestep"
+        loader = val_dataloader
+        if replicas:
+            rank, world = dist.get_rank(), dist.get_world_size()
+            loader = (b for i, b in enumerate(val_dataloader) if i % world == rank)
+        val_samples, batches, metrics = self.evaluate(loader, metrics=metrics, stop_idx=self.config.evaluation_batches,
+                                                      classification=classification, from_t=from_t)
+        metric_output = []
+        if metrics is not None:
+            for metric in metrics:
+                if replicas:
+                    metric.sync_across_processes(None)
+                metric_output.append(metric.get_output())
+        if plot_function is not None and not classification:
+            plot_function(output_dir=inference_image_path, batches=batches, samples=val_samples, epoch=0,
+                          process_idx=dist.get_rank() if multi else 0)
+        return (metric_output, val_samples, batches) if metrics is not None else (val_samples, batches)

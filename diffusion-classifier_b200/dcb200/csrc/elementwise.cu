@@ -59,6 +59,47 @@ __global__ void qsample_kernel(const float* __restrict__ x, const float* __restr
   }
 }
 
+// One ancestral DDPM step with classifier-free guidance (diffusion_classifier.py:176-207 + the z_s draw of :263-264):
+//   pred = (1+w)*cond - w*uncond ; x = clip(v ? a_t z - s_t pred : (z - s_t pred)/a_t) ; mu = a_s (z (1-c)/a_t + c x)
+//   z_out = final ? clip(mu) : mu + sqrt(var) * noise
+// z NCHW fp32; pred is read in the layout the last GEMM of the denoiser writes (NHWC, or DiT token-major (py,px,c) when
+// patch > 0), rows of sample b*rep (+1 = unconditional).  coef[8] = {c, a_t, a_s, s_t, s_s, sqrt(var), w, -} on device.
+__global__ void ddpm_step_kernel(const float* __restrict__ z_t, const float* __restrict__ pred, int rep, int patch,
+                                 const float* __restrict__ coef, int v_param, int final_step,
+                                 const float* __restrict__ noise_pre, uint64_t seed, int64_t unit_id0, int B, int C, int HW,
+                                 int W, float* __restrict__ z_out) {
+  const float c = coef[0], a_t = coef[1], a_s = coef[2], s_t = coef[3], sd = coef[5], w = coef[6];
+  const int64_t total = (int64_t)B * C * HW;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int pix = (int)(i % HW);
+    const int ch = (int)((i / HW) % C);
+    const int b = (int)(i / ((int64_t)HW * C));
+    int64_t off, per_sample;
+    if (patch > 0) {
+      const int y = pix / W, xx = pix % W, g = W / patch;
+      const int64_t tok = (int64_t)(y / patch) * g + xx / patch;
+      off = tok * (patch * patch * C) + ((y % patch) * patch + xx % patch) * C + ch;
+      per_sample = (int64_t)HW * C;
+    } else {
+      off = (int64_t)pix * C + ch;
+      per_sample = (int64_t)HW * C;
+    }
+    float p = pred[(int64_t)b * rep * per_sample + off];
+    if (rep == 2) p = (1.f + w) * p - w * pred[((int64_t)b * rep + 1) * per_sample + off];
+    const float z = z_t[i];
+    float x = v_param ? a_t * z - s_t * p : (z - s_t * p) / a_t;
+    x = fminf(fmaxf(x, -1.f), 1.f);
+    const float mu = a_s * (z * (1.f - c) / a_t + c * x);
+    float o;
+    if (final_step) o = fminf(fmaxf(mu, -1.f), 1.f);
+    else {
+      const float n = noise_pre ? noise_pre[i] : philox_normal(seed, (uint64_t)(unit_id0 + b), (uint64_t)((int64_t)ch * HW + pix));
+      o = mu + n * sd;
+    }
+    z_out[i] = o;
+  }
+}
+
 // stage the first layer's A operand from z_ws (NHWC fp32): 3x3 unfold (mode 0) or p x p patchify (mode 1)
 template <typename T>
 __global__ void stage_kernel(int mode, const float* __restrict__ z, int U, int rep, int C, int H, int W, int patch,
@@ -281,6 +322,18 @@ extern "C" int dcb_prologue(int mode, int dtype, const float* x, const float* ep
       stage_kernel<float><<<grid_for(total), 256, 0, st>>>(mode, z_ws, U, rep, C, H, W, patch, kpad, (float*)a_out);
     DCB_CHECK_LAUNCH("stage");
   }
+  return DCB_OK;
+}
+
+extern "C" int dcb_ddpm_step(const float* z_t, const float* pred, int rep, int patch, const float* coef, int v_param,
+                             int final_step, const float* noise_predrawn, uint64_t seed, int64_t unit_id0, int B, int C,
+                             int H, int W, float* z_out, dcb_stream stream) {
+  DCB_REQUIRE(rep == 1 || rep == 2, "ddpm_step: rep must be 1 (no guidance pair) or 2 (cond, uncond)");
+  DCB_REQUIRE(patch == 0 || (H % patch == 0 && W % patch == 0), "ddpm_step: H,W must be multiples of patch");
+  DCB_REQUIRE(z_t && pred && coef && z_out, "ddpm_step: null pointer");
+  ddpm_step_kernel<<<grid_for((int64_t)B * C * H * W), 256, 0, (cudaStream_t)stream>>>(
+      z_t, pred, rep, patch, coef, v_param, final_step, noise_predrawn, seed, unit_id0, B, C, H * W, W, z_out);
+  DCB_CHECK_LAUNCH("ddpm_step");
   return DCB_OK;
 }
 

@@ -283,6 +283,17 @@ def prologue(ctx, mode, x, U, rep, C_, H, W, kpad, *, patch=1, eps=None, seed=0,
     return a, tgt
 
 
+def ddpm_step(ctx, z_t, pred, rep, patch, coef, v_param, final, noise=None, seed=0, unit_id0=0, out=None):
+    """one ancestral DDPM step + classifier-free guidance (dcb_ddpm_step).  z_t [B,C,H,W] fp32; pred: fp32 output of the
+    denoiser's last GEMM (sample b*rep conditional, b*rep+1 unconditional); coef: device [8] fp32."""
+    B, C_, H, W = z_t.shape
+    assert z_t.dtype == torch.float32 and pred.dtype == torch.float32 and z_t.is_contiguous() and pred.is_contiguous()
+    out = torch.empty_like(z_t) if out is None else out
+    L.check(L.lib().dcb_ddpm_step(z_t.data_ptr(), pred.data_ptr(), rep, patch, coef.data_ptr(), int(v_param), int(final),
+                                  _p(noise), seed, unit_id0, B, C_, H, W, out.data_ptr(), ctx.stream()), "ddpm_step")
+    return out
+
+
 def eps_mse(ctx, pred, target, scale, S, div, K, err):
     L.check(L.lib().dcb_eps_mse(L.F32 if pred.dtype == torch.float32 else L.BF16, pred.data_ptr(), target.data_ptr(),
                                 _p(scale), S, div, K, err.data_ptr(), 1, ctx.stream()), "eps_mse")

@@ -48,6 +48,17 @@ int dcb_prologue(int mode, int dtype, const float* x, const float* eps_predrawn,
                  const float* alpha, const float* sigma, const int32_t* img, int U, int rep, int C, int H, int W,
                  int patch, int kpad, float* z_ws, void* a_out, float* target, int v_param, dcb_stream stream);
 
+/* ---- (1b) DDPM ancestral sampler step with classifier-free guidance (next-row f2) -------------------------
+ * replaces DiffusionClassifier.ddpm_sampler_step + the z_s draw (diffusion_classifier.py:176-207, 263-264, 280-284):
+ *   pred = (1+w)*cond - w*uncond;  x = clip(v_param ? a_t*z - s_t*pred : (z - s_t*pred)/a_t);
+ *   mu = a_s*(z*(1-c)/a_t + c*x);  z_out = final_step ? clip(mu) : mu + sqrt(var)*noise
+ * z_t / z_out / noise_predrawn: [B,C,H,W] fp32 NCHW (noise NULL -> Philox(seed, unit_id0+b)); pred: fp32 output of the
+ * denoiser's last GEMM for samples b*rep (+1 = unconditional when rep == 2), NHWC rows (patch == 0) or DiT token-major
+ * (py,px,c) columns (patch > 0); coef: DEVICE [8] = {c, a_t, a_s, s_t, s_s, sqrt(var), w, 0}. */
+int dcb_ddpm_step(const float* z_t, const float* pred, int rep, int patch, const float* coef, int v_param,
+                  int final_step, const float* noise_predrawn, uint64_t seed, int64_t unit_id0, int B, int C, int H,
+                  int W, float* z_out, dcb_stream stream);
+
 /* sinusoidal embedding of the noise label (diffusers get_timestep_embedding):
  * out[s][0:half] = cos(t*w_k), out[s][half:] = sin(t*w_k), w_k = exp(-ln(max_period)*k/(half-shift)); s = u*rep+r */
 int dcb_timestep_embed(int dtype, const float* t, int U, int rep, int dim, float shift, float max_period, void* out,

@@ -77,3 +77,71 @@ def classify_oracle(denoiser, encoder, config, x, text=None, fast=False, t_all=N
         _, classes = torch.topk(stage_err, config.n_keep_per_stage[i], dim=1, largest=False)
     assert classes.shape[1] == 1
     return (classes[:, 0], errors) if return_errors else classes[:, 0]
+
+
+# ---- next rows f2 / f4: DDPM sampler with classifier-free guidance, and the training loss forward -------
+def ddpm_sampler_step_oracle(config, z_t, pred, u_pred, logsnr_t, logsnr_s):
+    """diffusion_classifier.py:176-207 restated: returns (mu, variance)."""
+    c = -torch.special.expm1(logsnr_t - logsnr_s)
+    alpha_t, alpha_s = torch.sqrt(torch.sigmoid(logsnr_t)), torch.sqrt(torch.sigmoid(logsnr_s))
+    sigma_t, sigma_s = torch.sqrt(torch.sigmoid(-logsnr_t)), torch.sqrt(torch.sigmoid(-logsnr_s))
+    w = config.cfg_w
+    pred = (1 + w) * pred - w * u_pred
+    x_pred = alpha_t * z_t - sigma_t * pred if config.pred_param == "v" else (z_t - sigma_t * pred) / alpha_t
+    x_pred = torch.clamp(x_pred, -1, 1)
+    mu = alpha_s * (z_t * (1 - c) / alpha_t + c * x_pred)
+    return mu, (sigma_s ** 2) * c
+
+
+@torch.no_grad()
+def sample_oracle(denoiser, encoder, config, x, text, from_t=1, z_init=None, noise_all=None):
+    """diffusion_classifier.py:209-293 restated.  denoiser(z, logsnr[1], encoder_hidden_states=) -> prediction;
+    encoder = nn.Embedding (null token id = config.classes) or None (DiT: labels pass through).
+    z_init [B,C,H,W]: the initial state (the reference draws randn, or diffuses x to from_t);
+    noise_all [sampling_steps,B,C,H,W]: the per-step randn_like draws.  Note the reference evaluates the denoiser
+    sampling_steps + 1 times: the loop's last iteration already steps to t = 0, then the "final step" re-evaluates at
+    steps[-2] from that state and returns clip(mu)."""
+    sched = schedule_fn(config)
+    if z_init is not None:
+        z_t = z_init.clone()
+    elif from_t == 1:
+        z_t = torch.randn(x.shape).to(x.device)
+    else:
+        logsnr = sched(torch.ones(x.shape[0]) * from_t).to(x.device)
+        a = torch.sqrt(torch.sigmoid(logsnr)).view(-1, 1, 1, 1)
+        s = torch.sqrt(torch.sigmoid(-logsnr)).view(-1, 1, 1, 1)
+        z_t = a * x + s * torch.randn_like(x)
+    null = torch.full_like(text, config.classes)
+    emb = encoder(text).unsqueeze(1) if encoder is not None else text
+    nemb = encoder(null).unsqueeze(1) if encoder is not None else null
+    steps = torch.linspace(from_t, 0.0, config.sampling_steps + 1)
+    for i in range(len(steps) - 1):
+        lt, ls = sched(steps[i]).to(x.device).unsqueeze(0), sched(steps[i + 1]).to(x.device).unsqueeze(0)
+        pred = denoiser(z_t, lt, encoder_hidden_states=emb)
+        u_pred = denoiser(z_t, lt, encoder_hidden_states=nemb)
+        mu, var = ddpm_sampler_step_oracle(config, z_t, pred, u_pred, lt, ls)
+        n = torch.randn_like(mu) if noise_all is None else noise_all[i].to(x.device)
+        z_t = mu + n * torch.sqrt(var)
+    l1, l0 = sched(steps[-2]).to(x.device).unsqueeze(0), sched(steps[-1]).to(x.device).unsqueeze(0)
+    pred = denoiser(z_t, l1, encoder_hidden_states=emb)
+    u_pred = denoiser(z_t, l1, encoder_hidden_states=nemb)
+    x_pred, _ = ddpm_sampler_step_oracle(config, z_t, pred, u_pred, l1, l0)
+    return torch.clamp(x_pred, -1, 1)
+
+
+def loss_oracle(denoiser, encoder, config, x, text, t=None, eps=None):
+    """diffusion_classifier.py:295-344 restated (min-SNR weighted eps-MSE): denoiser(x=, noise_labels=,
+    encoder_hidden_states=).  t [B] / eps [B,C,H,W] inject the reference's torch.rand / randn_like draws."""
+    sched = schedule_fn(config)
+    t = torch.rand(x.shape[0]) if t is None else t.cpu()
+    emb = (encoder(text).unsqueeze(1) if encoder is not None else text) if text is not None else None
+    logsnr = sched(t).to(x.device)
+    alpha = torch.sqrt(torch.sigmoid(logsnr)).view(-1, 1, 1, 1)
+    sigma = torch.sqrt(torch.sigmoid(-logsnr)).view(-1, 1, 1, 1)
+    eps = torch.randn_like(x) if eps is None else eps
+    z = alpha * x + sigma * eps
+    pred = denoiser(x=z, noise_labels=logsnr, encoder_hidden_states=emb)
+    eps_pred = sigma * z + alpha * pred if config.pred_param == "v" else pred
+    snr = torch.exp(logsnr).clamp_(max=5)
+    weight = 1 / (1 + snr) if config.pred_param == "v" else 1 / snr
+    return torch.mean(weight.view(-1, 1, 1, 1) * (eps_pred - eps) ** 2)

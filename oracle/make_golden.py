@@ -56,6 +56,53 @@ def classify_fixture(ref, name, kind, arch, cfg_kw, BS, seed, factor):
     print(name, "labels", labels.tolist(), "final means", st["stage_means"][-1][0].tolist())
 
 
+def sample_loss_fixture(ref, name, kind, arch, cfg_kw, BS, seed, factor, from_t=1):
+    """verbatim DiffusionClassifier.sample (:209-293) and .loss (:295-344); the draws the reference makes with the
+    default CPU generator (randn for z_T, randn_like per step; rand + randn_like for the loss) are replayed from the
+    same seed and stored, so the product can be fed identical noise."""
+    from oracle import loop
+    torch.manual_seed(seed)
+    net = (ref.UNetCondition2D if kind == "unet" else ref.DiT)(**arch)
+    cfg = Config(**cfg_kw)
+    dc = ref.DiffusionClassifier(net, cfg).eval()
+    amplify_class_signal(dc, kind, factor)
+    C, S = arch["in_channels"], arch["sample_size"]
+    g = torch.Generator().manual_seed(seed + 1)
+    x = torch.rand(BS, C, S, S, generator=g) * 2 - 1
+    text = torch.randint(0, cfg.classes, (BS,), generator=g)
+    torch.manual_seed(seed + 2)
+    out = dc.sample(x, text, from_t=from_t)
+    torch.manual_seed(seed + 2)
+    if from_t == 1:
+        z_init = torch.randn(x.shape)
+    else:
+        lam = dc.schedule(torch.ones(BS) * from_t)
+        a, sg = torch.sqrt(torch.sigmoid(lam)).view(-1, 1, 1, 1), torch.sqrt(torch.sigmoid(-lam)).view(-1, 1, 1, 1)
+        z_init = a * x + sg * torch.randn_like(x)
+    noise_all = torch.stack([torch.randn(x.shape) for _ in range(cfg.sampling_steps)])
+
+    class Den(torch.nn.Module):
+        def forward(self, x, noise_labels, encoder_hidden_states):
+            return dc.ema(x, noise_labels, encoder_hidden_states=encoder_hidden_states)
+
+    replay = loop.sample_oracle(Den(), dc.encoder, cfg, x, text, from_t=from_t, z_init=z_init, noise_all=noise_all)
+    assert torch.equal(replay, out), "replayed draws must reproduce the reference's sample bit for bit"
+    torch.manual_seed(seed + 3)
+    loss = dc.loss(x, text)
+    torch.manual_seed(seed + 3)
+    t = torch.rand(BS)
+    eps = torch.randn(x.shape)
+    with torch.no_grad():
+        l2 = loop.loss_oracle(lambda x, noise_labels, encoder_hidden_states: dc.model(
+            x=x, noise_labels=noise_labels, encoder_hidden_states=encoder_hidden_states), dc.encoder, cfg, x, text, t=t,
+            eps=eps)
+    assert torch.equal(l2, loss.detach()), "replayed draws must reproduce the reference's loss bit for bit"
+    np.savez_compressed(os.path.join(OUT, name), x=x.numpy(), text=text.numpy(), z_init=z_init.numpy(),
+                        noise_all=noise_all.numpy(), sample=out.numpy(), t=t.numpy(), eps=eps.numpy(),
+                        loss=float(loss), seed=seed, factor=factor, from_t=from_t, checksum=checksum(dc.ema.ema_model))
+    print(name, "sample mean/std", float(out.mean()), float(out.std()), "loss", float(loss))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = load_reference()
@@ -86,6 +133,15 @@ def main():
                      dict(pred_param="v", schedule="shifted_cosine", noise_d=16, image_size=32, encoder_type="DiT",
                           classes=3, n_stages=2, evaluation_per_stage=[2, 3], n_keep_per_stage=[2, 1], **base), BS=2,
                      seed=5, factor=20.0)
+
+    # (2b) verbatim sample (DDPM + classifier-free guidance) and loss
+    sample_loss_fixture(ref, "sample_loss_unet_tiny.npz", "unet", TINY_UNET,
+                        dict(pred_param="eps", schedule="cosine", noise_d=16, image_size=16, encoder_type="nn", classes=4,
+                             sampling_steps=4, **{**base, "cfg_w": 1.5}), BS=2, seed=21, factor=40.0)
+    sample_loss_fixture(ref, "sample_loss_dit_tiny.npz", "dit", TINY_DIT,
+                        dict(pred_param="v", schedule="shifted_cosine", noise_d=16, image_size=32, encoder_type="DiT",
+                             classes=3, sampling_steps=3, **{**base, "cfg_w": 0.5}), BS=2, seed=23, factor=20.0,
+                        from_t=0.5)
 
     # (3) plain forwards through the reference's wrappers (nets/unet.py:186-195, nets/dit.py:49-51)
     torch.manual_seed(11)
