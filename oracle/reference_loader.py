@@ -83,7 +83,7 @@ def load_reference():
     # the reference uses top-level package names (diffusion, nets, utils); make sure none is shadowed
     for name in ("diffusion", "nets", "utils"):
         m = sys.modules.get(name)
-        if m is not None and not getattr(m, "__file__", REFERENCE_ROOT).startswith(REFERENCE_ROOT):
+        if m is not None and not (getattr(m, "__file__", None) or REFERENCE_ROOT).startswith(REFERENCE_ROOT):
             paths = list(getattr(m, "__path__", []))
             if not any(p.startswith(REFERENCE_ROOT) for p in paths):
                 raise ImportError(f"module {name!r} already imported from elsewhere: {m}")
