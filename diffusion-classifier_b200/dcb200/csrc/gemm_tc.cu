@@ -42,78 +42,6 @@ struct TcParams {
   int uniform;  // every row of an M tile belongs to one rowvec/gate group (tile-constant vectors live in smem)
 };
 
-// ---- epilogue for 16 consecutive output columns of one row ------------------------------------------------
-// v[] holds acc (+bias already added by caller for GEGLU); n0 is the first OUTPUT column.
-__device__ __forceinline__ void epi_store16(const EpiDev& e, int m, int n0, float* v, float& mse_acc, int sample,
-                                            int pix) {
-  const int grp = e.rows_per_group > 0 ? m / e.rows_per_group : 0;
-  const int nvalid = min(16, e.n_out - n0);
-  if (e.rowvec) {
-    const float* rv = e.rowvec + (int64_t)(e.rowvec_idx ? e.rowvec_idx[grp] : grp) * e.rowvec_ld + n0;
-#pragma unroll
-    for (int i = 0; i < 16; ++i)
-      if (i < nvalid) v[i] += rv[i];
-  }
-  if (e.act == DCB_ACT_SILU || e.act == DCB_ACT_GELU_TANH) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = apply_act(e.act, v[i]);
-  }
-  if (e.gate) {
-    const float* gt = e.gate + (int64_t)grp * e.gate_ld + n0;
-#pragma unroll
-    for (int i = 0; i < 16; ++i)
-      if (i < nvalid) v[i] *= gt[i];
-  }
-  if (e.residual) {
-    const int64_t r = e.res_idx ? e.res_idx[m] : (e.res_mod > 0 ? m % e.res_mod : m);
-    const int64_t off = r * e.res_ld + n0;
-    if (e.res_dtype == DCB_BF16 && nvalid == 16 && (off & 7) == 0) {
-      const uint4* rp = reinterpret_cast<const uint4*>((const __nv_bfloat16*)e.residual + off);
-      float f[8];
-      unpack_bf16x8(rp[0], f);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] += f[i];
-      unpack_bf16x8(rp[1], f);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) v[8 + i] += f[i];
-    } else {
-#pragma unroll
-      for (int i = 0; i < 16; ++i)
-        if (i < nvalid) v[i] += load_as_f(e.residual, e.res_dtype, off + i);
-    }
-  }
-  if (e.act_post != DCB_ACT_NONE) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = apply_act(e.act_post, v[i]);
-  }
-  if (e.mse_part) {
-    const float sc = e.mse_scale ? e.mse_scale[sample] : 1.f;
-    const float* tg = e.mse_target + ((int64_t)(sample / e.mse_div) * e.rows_per_sample + pix) * e.mse_ld + n0;
-#pragma unroll
-    for (int i = 0; i < 16; ++i)
-      if (i < nvalid) {
-        float d = sc * v[i] - tg[i];
-        mse_acc = fmaf(d, d, mse_acc);
-      }
-  }
-  if (e.out) {
-    const int64_t off = out_row_of(e, m) * e.out_ld + n0;
-    if (e.out_dtype == DCB_BF16 && nvalid == 16 && (off & 7) == 0) {
-      uint4* op = reinterpret_cast<uint4*>((__nv_bfloat16*)e.out + off);
-      op[0] = pack_bf16x8(v);
-      op[1] = pack_bf16x8(v + 8);
-    } else if (e.out_dtype == DCB_F32 && nvalid == 16 && (off & 3) == 0) {
-      float4* op = reinterpret_cast<float4*>((float*)e.out + off);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) op[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-    } else {
-#pragma unroll
-      for (int i = 0; i < 16; ++i)
-        if (i < nvalid) store_from_f(e.out, e.out_dtype, off + i, v[i]);
-    }
-  }
-}
-
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB,
@@ -450,7 +378,7 @@ static int encode_a_map(CUtensorMap* map, const SegDev& s, int NBsrc, const TcGe
 }
 
 int launch_gemm_tc2(const GemmDev& g, cudaStream_t st, int bw, int bh, int bn, int tiles_x, int tiles_y, int tiles_nb,
-                    int BN, int uniform);
+                    int BN, int uniform, int staged);
 
 int launch_gemm_tc(const GemmDev& g, cudaStream_t st) {
   DCB_REQUIRE(g.dtype == DCB_BF16, "tcgen05 engine is bf16 only");
@@ -535,9 +463,13 @@ int launch_gemm_tc(const GemmDev& g, cudaStream_t st) {
     else p.uniform = t.bn == 1 && e.rows_per_group % e.rows_per_sample == 0;
   }
   // big N<=128-wide problems: 256-pixel CTAs with split A/B rings (+ x-halo reuse for 3x3 convs), see gemm_tc2.cu
-  if (p.staged && t.BN <= 128 && g.epi.act != DCB_ACT_GEGLU && !getenv("DCB_NO_TC2") &&
+  // (also the fused eps-MSE of conv_out -- N = out_channels, nothing stored: with 9 separately loaded taps it is bound by
+  //  L2->SMEM traffic, the x-halo boxes cut that 3x)
+  const bool mse_only = g.epi.mse_part != nullptr && g.epi.out == nullptr && g.epi.residual == nullptr && t.bn == 1 &&
+                        (g.OH * g.OW) % TC_BM == 0 && !getenv("DCB_NO_TC2_MSE");
+  if ((p.staged || mse_only) && t.BN <= 128 && g.epi.act != DCB_ACT_GEGLU && !getenv("DCB_NO_TC2") &&
       t.tiles_x * t.tiles_y * t.tiles_nb * t.n_tiles >= 4 * num_sms()) {
-    rc = launch_gemm_tc2(g, st, t.bw, t.bh, t.bn, t.tiles_x, t.tiles_y, t.tiles_nb, t.BN, p.uniform);
+    rc = launch_gemm_tc2(g, st, t.bw, t.bh, t.bn, t.tiles_x, t.tiles_y, t.tiles_nb, t.BN, p.uniform, p.staged);
     if (rc != DCB_EUNSUPPORTED) return rc;
   }
   const int epi_bytes = p.staged ? 2 * TC_EPI_BYTES : 0;

@@ -32,6 +32,7 @@ struct Tc2Params {
   int a_slots, b_slots, a_slot_bytes;
   uint32_t idesc;
   int uniform, base_off_mode;
+  int staged;    // 0: direct epilogue (fused eps-MSE of conv_out: nothing is written but per-tile partial sums)
   int dbg;  // experiments: 1 = no TMA traffic (barriers only), 2 = no epilogue work, 4 = no MMA issue
 };
 
@@ -69,6 +70,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
   uint64_t* tfull_bar = bars + 4 * T2_MAX_SLOTS;   // [2 TMEM stages][2 sub-tiles]
   uint64_t* tempty_bar = tfull_bar + 4;            // [2 TMEM stages][2 sub-tiles]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 4);
+  float* mse_smem = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 384);  // [2 groups][4 warps]
   uint8_t* stg8 = reinterpret_cast<uint8_t*>(bars) + 512;
 
   // warp-uniform role dispatch (see gemm_tc.cu): loop state and descriptors stay in uniform registers
@@ -262,8 +264,50 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
         if (++as == 2) { as = 0; aphase ^= 1; }
         continue;
       }
-      staged_epilogue(gq, e, my_stg, it & 1, 2 * tp + grp, tn, p.BN, taddr, smem_u32(&tfull_bar[as * 2 + grp]), aphase, true,
-                      smem_u32(&tempty_bar[as * 2 + grp]), true, 1 + grp);
+      if (p.staged) {
+        staged_epilogue(gq, e, my_stg, it & 1, 2 * tp + grp, tn, p.BN, taddr, smem_u32(&tfull_bar[as * 2 + grp]), aphase, true,
+                        smem_u32(&tempty_bar[as * 2 + grp]), true, 1 + grp);
+      } else {
+        // direct epilogue (same arithmetic and summation order as gemm_tc_kernel's): thread-per-row over the BN columns,
+        // fused eps-MSE -> one partial per 128-row sub-tile
+        const int tm_lin = 2 * tp + grp;
+        const SubTile st = decode_sub(p, tm_lin);
+        const int rr = q * 32 + lane;
+        const int xl = rr % p.bw, yl = (rr / p.bw) % p.bh, nl = rr / (p.bw * p.bh);
+        const int x = st.x0 + xl, y = st.y0 + yl, nb = st.nb0 + nl;
+        const bool row_ok = tm_lin < p.m_tiles && x < p.OW && y < p.OH && nb < p.NB;
+        const int pix = y * p.OW + x;
+        const int m = nb * e.rows_per_sample + pix;
+        mbar_wait(smem_u32(&tfull_bar[as * 2 + grp]), aphase);
+        tc_fence_after();
+        float mse_acc = 0.f;
+        for (int c = 0; c < p.BN; c += 16) {
+          const int n0 = tn * p.BN + c;
+          if (n0 >= e.N) break;  // warp-uniform
+          float v[16];
+          tmem_ld16(taddr + (uint32_t)c, v);
+          if (row_ok) {
+            if (e.bias) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (n0 + i < e.N) v[i] += e.bias[n0 + i];
+            }
+            epi_store16(e, m, n0, v, mse_acc, nb, pix);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[as * 2 + grp]));
+        if (e.mse_part) {
+          float* my_mse = mse_smem + grp * 4;
+          mse_acc = warp_sum(mse_acc);
+          if (lane == 0) my_mse[q] = mse_acc;
+          epi_bar(1 + grp);
+          if (q == 0 && lane == 0 && tm_lin < p.m_tiles)
+            e.mse_part[(int64_t)tm_lin * p.n_tiles + tn] = (my_mse[0] + my_mse[1]) + (my_mse[2] + my_mse[3]);
+          epi_bar(1 + grp);
+        }
+      }
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
   }
@@ -303,10 +347,11 @@ static int encode_map(CUtensorMap* map, const SegDev& s, int NBsrc, int bx, int 
 
 // returns DCB_EUNSUPPORTED when the descriptor does not fit this kernel (the caller falls back to gemm_tc_kernel)
 int launch_gemm_tc2(const GemmDev& g, cudaStream_t st, int bw, int bh, int bn, int tiles_x, int tiles_y, int tiles_nb,
-                    int BN, int uniform) {
+                    int BN, int uniform, int staged) {
   const EpiDev& e = g.epi;
   Tc2Params p;
   memset(&p, 0, sizeof(p));
+  p.staged = staged;
   p.bw = bw; p.bh = bh; p.bn = bn; p.tiles_x = tiles_x; p.tiles_y = tiles_y; p.tiles_nb = tiles_nb;
   p.m_tiles = tiles_x * tiles_y * tiles_nb;
   p.OW = g.OW; p.OH = g.OH; p.NB = g.NB; p.BN = BN;

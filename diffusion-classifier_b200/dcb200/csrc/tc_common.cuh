@@ -203,6 +203,78 @@ __device__ __forceinline__ void lds16f(uint32_t addr, float* f) {
                  : "r"(addr + 16 * i));
 }
 
+// ---- epilogue for 16 consecutive output columns of one row ------------------------------------------------
+// v[] holds acc (+bias already added by caller for GEGLU); n0 is the first OUTPUT column.
+__device__ __forceinline__ void epi_store16(const EpiDev& e, int m, int n0, float* v, float& mse_acc, int sample,
+                                            int pix) {
+  const int grp = e.rows_per_group > 0 ? m / e.rows_per_group : 0;
+  const int nvalid = min(16, e.n_out - n0);
+  if (e.rowvec) {
+    const float* rv = e.rowvec + (int64_t)(e.rowvec_idx ? e.rowvec_idx[grp] : grp) * e.rowvec_ld + n0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (i < nvalid) v[i] += rv[i];
+  }
+  if (e.act == DCB_ACT_SILU || e.act == DCB_ACT_GELU_TANH) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = apply_act(e.act, v[i]);
+  }
+  if (e.gate) {
+    const float* gt = e.gate + (int64_t)grp * e.gate_ld + n0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (i < nvalid) v[i] *= gt[i];
+  }
+  if (e.residual) {
+    const int64_t r = e.res_idx ? e.res_idx[m] : (e.res_mod > 0 ? m % e.res_mod : m);
+    const int64_t off = r * e.res_ld + n0;
+    if (e.res_dtype == DCB_BF16 && nvalid == 16 && (off & 7) == 0) {
+      const uint4* rp = reinterpret_cast<const uint4*>((const __nv_bfloat16*)e.residual + off);
+      float f[8];
+      unpack_bf16x8(rp[0], f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] += f[i];
+      unpack_bf16x8(rp[1], f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[8 + i] += f[i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (i < nvalid) v[i] += load_as_f(e.residual, e.res_dtype, off + i);
+    }
+  }
+  if (e.act_post != DCB_ACT_NONE) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = apply_act(e.act_post, v[i]);
+  }
+  if (e.mse_part) {
+    const float sc = e.mse_scale ? e.mse_scale[sample] : 1.f;
+    const float* tg = e.mse_target + ((int64_t)(sample / e.mse_div) * e.rows_per_sample + pix) * e.mse_ld + n0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (i < nvalid) {
+        float d = sc * v[i] - tg[i];
+        mse_acc = fmaf(d, d, mse_acc);
+      }
+  }
+  if (e.out) {
+    const int64_t off = out_row_of(e, m) * e.out_ld + n0;
+    if (e.out_dtype == DCB_BF16 && nvalid == 16 && (off & 7) == 0) {
+      uint4* op = reinterpret_cast<uint4*>((__nv_bfloat16*)e.out + off);
+      op[0] = pack_bf16x8(v);
+      op[1] = pack_bf16x8(v + 8);
+    } else if (e.out_dtype == DCB_F32 && nvalid == 16 && (off & 3) == 0) {
+      float4* op = reinterpret_cast<float4*>((float*)e.out + off);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) op[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (i < nvalid) store_from_f(e.out, e.out_dtype, off + i, v[i]);
+    }
+  }
+}
+
 // ---- staged epilogue of one 128-row accumulator sub-tile (bf16 outputs, <= 128 output columns per tile) --------
 //  0. per-row ids + tile-constant bias/rowvec/gate vectors -> smem
 //  1. cp.async prefetch of the whole residual tile (32 KB in flight per SM) into the swizzled staging tile

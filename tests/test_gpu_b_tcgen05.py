@@ -345,3 +345,37 @@ def test_upsample_conv_folded_phases(dev, NB, H, W, C):
         assert rel_err(got[..., 0], o.sum(1)) < 1e-5 and rel_err(got[..., 1], (o * o).sum(1)) < 1e-5
     else:
         assert st is None
+
+
+@pytest.mark.parametrize("S,div,H,W,Ci,Co", [(5, 1, 128, 128, 128, 3), (6, 2, 128, 128, 64, 12), (3, 1, 64, 256, 128, 40)])
+def test_tc2_halo_fused_mse_is_bit_identical_to_tap_kernel(dev, S, div, H, W, Ci, Co):
+    """conv_out at full resolution runs in gemm_tc2 (x-halo boxes, direct eps-MSE epilogue): same K-block order and the
+    same summation order as gemm_tc_kernel with nine separately loaded taps => bit-identical per-sample errors; both
+    equal the torch fp32 reduction of the written prediction."""
+    import os
+    from dcb200 import engine as E
+    torch.manual_seed(0)
+    a = _bf(S, H, W, Ci, dev=dev)
+    w = (torch.randn(Co, Ci, 3, 3, device=dev) * 0.05).to(torch.bfloat16)
+    b = torch.randn(Co, device=dev)
+    wp = w.permute(0, 2, 3, 1).reshape(Co, -1).contiguous()
+    tgt = torch.randn(S // div, H * W, Co, device=dev)
+    scale = torch.rand(S, device=dev)
+    ctx = _ctx(dev)
+
+    def run():
+        err = torch.empty(S, device=dev)
+        E.gemm(ctx, E.conv3x3_segs(a, Ci, H, W), wp, Co, S, H, W, bias=b, want_out=False,
+               mse=dict(target=tgt, scale=scale, div=div, ld=Co, err=err))
+        return err
+
+    e_halo = run()
+    os.environ["DCB_NO_TC2_MSE"] = "1"
+    try:
+        e_tap = run()
+    finally:
+        del os.environ["DCB_NO_TC2_MSE"]
+    assert torch.equal(e_halo, e_tap)
+    pred = conv_ref(a.float(), w.float(), b).reshape(S, H * W, Co)
+    ref = ((scale.view(-1, 1, 1) * pred - tgt.repeat_interleave(div, 0)) ** 2).sum((1, 2))
+    assert rel_err(e_halo, ref) < 2e-5
