@@ -21,7 +21,7 @@ esac
 if [ "$1" = "traffic" ]; then
   $CMD > gpurun_out/plain.log 2>&1 &&
   ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,lts__t_sector_hit_rate.pct,sm__cycles_elapsed.avg.per_second \
-      --clock-control none -k regex:gemm_tc -s 333 -c 111 --csv --log-file gpurun_out/gemm_traffic.csv $CMD > gpurun_out/ncu_traffic.log 2>&1
+      --clock-control none -k regex:gemm_tc -s 369 -c 123 --csv --log-file gpurun_out/gemm_traffic.csv $CMD > gpurun_out/ncu_traffic.log 2>&1
 fi
 # tools/profile.sh attn -> gpurun_out/prof_attn.ncu-rep (--set full of 2 flash_attn_tc launches of the DiT-B/4 workload)
 if [ "$1" = "attn" ]; then
