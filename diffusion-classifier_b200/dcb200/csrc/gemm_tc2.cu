@@ -287,12 +287,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
           float v[16];
           tmem_ld16(taddr + (uint32_t)c, v);
           if (row_ok) {
-            if (e.bias) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i)
-                if (n0 + i < e.N) v[i] += e.bias[n0 + i];
-            }
-            epi_store16(e, m, n0, v, mse_acc, nb, pix);
+            epi_add_bias_rowvec16(e, m, n0, v);
+            epi_store16(e, m, n0, v, mse_acc, nb, pix, false);
           }
         }
         tc_fence_before();

@@ -162,6 +162,14 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* r) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// same, carrying a (fake) dependency on the loaded registers so that no use of them can be scheduled above the wait
+__device__ __forceinline__ void tmem_ld_wait_dep(uint32_t* r) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+}
 // named barrier of one epilogue group (4 warps); group g uses barrier id 1 + g
 __device__ __forceinline__ void epi_bar(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ bool elect_one() {
@@ -203,13 +211,26 @@ __device__ __forceinline__ void lds16f(uint32_t addr, float* f) {
                  : "r"(addr + 16 * i));
 }
 
+// v[i] += bias[n0 + i] + rowvec[group(m)][n0 + i]: every tcgen05 epilogue associates the two vectors first (the staged
+// epilogue keeps their sum in shared memory), so a layer's result does not depend on which epilogue its tile shape selects
+__device__ __forceinline__ void epi_add_bias_rowvec16(const EpiDev& e, int m, int n0, float* v) {
+  const float* rv = nullptr;
+  if (e.rowvec) {
+    const int grp = e.rows_per_group > 0 ? m / e.rows_per_group : 0;
+    rv = e.rowvec + (int64_t)(e.rowvec_idx ? e.rowvec_idx[grp] : grp) * e.rowvec_ld + n0;
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i)
+    if (n0 + i < e.n_out) v[i] += (e.bias ? e.bias[n0 + i] : 0.f) + (rv ? rv[i] : 0.f);
+}
+
 // ---- epilogue for 16 consecutive output columns of one row ------------------------------------------------
 // v[] holds acc (+bias already added by caller for GEGLU); n0 is the first OUTPUT column.
 __device__ __forceinline__ void epi_store16(const EpiDev& e, int m, int n0, float* v, float& mse_acc, int sample,
-                                            int pix) {
+                                            int pix, bool add_rowvec = true) {
   const int grp = e.rows_per_group > 0 ? m / e.rows_per_group : 0;
   const int nvalid = min(16, e.n_out - n0);
-  if (e.rowvec) {
+  if (e.rowvec && add_rowvec) {
     const float* rv = e.rowvec + (int64_t)(e.rowvec_idx ? e.rowvec_idx[grp] : grp) * e.rowvec_ld + n0;
 #pragma unroll
     for (int i = 0; i < 16; ++i)
@@ -315,13 +336,17 @@ __device__ __forceinline__ void staged_epilogue(const EpiGeom& gq, const EpiDev&
     const int m_out = e.up_phase ? ((nb * 2 * gq.OH + 2 * y + up_a) * (2 * gq.OW) + 2 * x + up_b) : m;
     s_m[r] = row_ok ? m_out : -1;
     if (e.residual) s_res[r] = row_ok ? (e.res_idx ? e.res_idx[m] : (e.res_mod > 0 ? m % e.res_mod : m)) : -1;
+    const bool rv_folded = gq.uniform && e.rowvec != nullptr && !geglu;
     for (int c = et; c < BN; c += 128) s_bias[c] = (e.bias && wrow0 + c < e.N) ? e.bias[wrow0 + c] : 0.f;
     if (gq.uniform && (e.rowvec || e.gate) && et < ncols_out) {
       const int m0 = (tb * gq.bn) * e.rows_per_sample + (ty * gq.bh) * gq.OW + tx * gq.bw;
       const int grp0 = m0 / e.rows_per_group;
       const bool ok = ocol0 + et < e.n_out;
-      if (e.rowvec)
-        s_rowvec[et] = ok ? e.rowvec[(int64_t)(e.rowvec_idx ? e.rowvec_idx[grp0] : grp0) * e.rowvec_ld + ocol0 + et] : 0.f;
+      if (e.rowvec) {
+        const float rvv = ok ? e.rowvec[(int64_t)(e.rowvec_idx ? e.rowvec_idx[grp0] : grp0) * e.rowvec_ld + ocol0 + et] : 0.f;
+        if (rv_folded) s_bias[et] += rvv;   // thread et wrote s_bias[et] just above (BN <= 128 here): acc + (bias + rowvec)
+        else s_rowvec[et] = rvv;
+      }
       if (e.gate) s_gate[et] = ok ? e.gate[(int64_t)grp0 * e.gate_ld + ocol0 + et] : 0.f;
     }
     epi_bar(bar_id);  // ids/constants visible; everybody has finished copying the previous tile out of the staging tile
@@ -349,27 +374,31 @@ __device__ __forceinline__ void staged_epilogue(const EpiGeom& gq, const EpiDev&
       epi_bar(bar_id);
     }
     const int grp = (!gq.uniform && e.rows_per_group > 0 && row_ok) ? m / e.rows_per_group : 0;
-    // ---- thread-per-row pass ----
-    for (int c = 0; c < ncols_out; c += 16) {
-      uint32_t ra[16], rg[16];
-      tmem_ld16_nowait(taddr + (uint32_t)c, ra);
-      if (geglu) tmem_ld16_nowait(taddr + (uint32_t)(128 + c), rg);
-      tmem_ld_wait();
+    // ---- thread-per-row pass: 16 columns per step; the TMEM load of step i+1 is in flight while step i is processed ----
+    auto process = [&](int c, const uint32_t (&ra)[16], const uint32_t (&rg)[16]) {
       float v[16], bz[16], bg[16];
-      // tile-constant vectors through explicit 16-byte shared loads (the generic-pointer form compiles to LD.E)
+      // tile-constant vectors through explicit 16-byte shared loads (the generic-pointer form compiles to LD.E);
+      // s_bias already holds bias + rowvec when the tile has one rowvec group (rv_folded)
       lds16f(smem_u32(s_bias + c), bz);
       if (geglu) lds16f(smem_u32(s_bias + 128 + c), bg);
+      if (e.rowvec && !rv_folded && !geglu && row_ok) {   // row-dependent group: same (bias + rowvec) association
+        const float* rv = e.rowvec + (int64_t)(e.rowvec_idx ? e.rowvec_idx[grp] : grp) * e.rowvec_ld + ocol0 + c;
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (ocol0 + c + i < e.n_out) bz[i] += rv[i];
+      }
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         float a = __uint_as_float(ra[i]) + bz[i];
         if (geglu) a *= gelu_erf_fast_f(__uint_as_float(rg[i]) + bg[i]);
         v[i] = a;
       }
-      if (e.rowvec) {
+      if (e.rowvec && geglu) {
         if (gq.uniform) {
-          { float rvv[16]; lds16f(smem_u32(s_rowvec + c), rvv);
+          float rvv[16];
+          lds16f(smem_u32(s_rowvec + c), rvv);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] += rvv[i]; }
+          for (int i = 0; i < 16; ++i) v[i] += rvv[i];
         } else if (row_ok) {
           const float* rv = e.rowvec + (int64_t)(e.rowvec_idx ? e.rowvec_idx[grp] : grp) * e.rowvec_ld + ocol0 + c;
 #pragma unroll
@@ -383,9 +412,10 @@ __device__ __forceinline__ void staged_epilogue(const EpiGeom& gq, const EpiDev&
       }
       if (e.gate) {
         if (gq.uniform) {
-          { float gvv[16]; lds16f(smem_u32(s_gate + c), gvv);
+          float gvv[16];
+          lds16f(smem_u32(s_gate + c), gvv);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] *= gvv[i]; }
+          for (int i = 0; i < 16; ++i) v[i] *= gvv[i];
         } else if (row_ok) {
           const float* gt = e.gate + (int64_t)grp * e.gate_ld + ocol0 + c;
 #pragma unroll
@@ -410,6 +440,29 @@ __device__ __forceinline__ void staged_epilogue(const EpiGeom& gq, const EpiDev&
       }
       *s0 = pack_bf16x8(v);
       *s1 = pack_bf16x8(v + 8);
+    };
+    if (geglu) {
+      for (int c = 0; c < ncols_out; c += 16) {
+        uint32_t ra[16], rg[16];
+        tmem_ld16_nowait(taddr + (uint32_t)c, ra);
+        tmem_ld16_nowait(taddr + (uint32_t)(128 + c), rg);
+        tmem_ld_wait_dep(ra);
+        process(c, ra, rg);
+      }
+    } else {
+      uint32_t ra[16], rb[16];
+      tmem_ld16_nowait(taddr, ra);
+      for (int c = 0; c < ncols_out; c += 32) {
+        tmem_ld_wait_dep(ra);
+        const bool more1 = c + 16 < ncols_out;
+        if (more1) tmem_ld16_nowait(taddr + (uint32_t)(c + 16), rb);
+        process(c, ra, ra);
+        if (more1) {
+          tmem_ld_wait_dep(rb);
+          if (c + 32 < ncols_out) tmem_ld16_nowait(taddr + (uint32_t)(c + 32), ra);
+          process(c + 16, rb, rb);
+        }
+      }
     }
     // accumulator fully drained: hand the TMEM stage back to the MMA warp
     tc_fence_before();
