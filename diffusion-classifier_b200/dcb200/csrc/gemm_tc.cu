@@ -38,6 +38,7 @@ struct TcParams {
   int BN, stages, total_kb;
   uint32_t idesc;
   int conv9, nkb_conv;  // segments 0..8 are the taps of one 3x3 conv (any stride): issue them (ky, channel block, kx)
+  int kx_outer;         // ... or (kx, channel block, ky): stride-1 convs with OW < 128, the order of gemm_tc2's y-halo mode
   int staged;   // epilogue through the swizzled smem staging tile + coalesced second pass
   int uniform;  // every row of an M tile belongs to one rowvec/gate group (tile-constant vectors live in smem)
 };
@@ -123,9 +124,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         // 3x3 taps in (ky, channel block, kx) order -- the accumulation order of gemm_tc2's x-halo mode, so a layer's
         // result does not depend on which of the two kernels the tile count selects (bit-stable across batch sizes)
         const int nbs = p.seg[0].div > 1 ? nb0 / p.seg[0].div : nb0;
-        for (int ky = 0; ky < 3; ++ky)
-          for (int kb = 0; kb < p.nkb_conv; ++kb)
-            for (int kx = 0; kx < 3; ++kx) issue(p.seg[ky * 3 + kx], nbs, kb, (ky * 3 + kx) * p.nkb_conv + kb);
+        if (p.kx_outer) {
+          for (int kx = 0; kx < 3; ++kx)
+            for (int kb = 0; kb < p.nkb_conv; ++kb)
+              for (int ky = 0; ky < 3; ++ky) issue(p.seg[ky * 3 + kx], nbs, kb, (ky * 3 + kx) * p.nkb_conv + kb);
+        } else {
+          for (int ky = 0; ky < 3; ++ky)
+            for (int kb = 0; kb < p.nkb_conv; ++kb)
+              for (int kx = 0; kx < 3; ++kx) issue(p.seg[ky * 3 + kx], nbs, kb, (ky * 3 + kx) * p.nkb_conv + kb);
+        }
         s_first = 9;
         kb_glob = 9 * p.nkb_conv;
       }
@@ -283,6 +290,11 @@ bool is_conv9(const GemmDev& g) {
   return true;
 }
 
+// K-block order of such a conv: (kx, channel block, ky) when the rows are narrower than a tile (stride 1, OW < 128) --
+// gemm_tc2 then serves the three ky taps of a (kx, channel block) from one y-halo box -- else (ky, channel block, kx), the
+// order of its x-halo boxes.  Every tcgen05 code path follows the same rule, so results do not depend on the kernel chosen.
+bool conv9_kx_outer(const GemmDev& g) { return is_conv9(g) && g.seg[0].stride == 1 && g.OW < 128; }
+
 struct TcGeom {
   int bw, bh, bn, tiles_x, tiles_y, tiles_nb, BN, n_tiles;
 };
@@ -427,6 +439,7 @@ int launch_gemm_tc(const GemmDev& g, cudaStream_t st) {
   }
   for (int j = nmaps; j < 3; ++j) maps[j] = maps[0];
   p.conv9 = is_conv9(g);
+  p.kx_outer = conv9_kx_outer(g);
   p.nkb_conv = p.conv9 ? g.seg[0].kc / TC_BK : 0;
 
   CUtensorMap mapB;

@@ -23,7 +23,13 @@ constexpr int T2_HALO_SUB = 17 * 1024;  // 130 rows x 128 B = 16640 B, padded to
 struct Tc2Params {
   int nseg;
   TcSeg seg[DCB_MAX_SEGS];
-  int halo;      // segments 0..8 are a stride-1 3x3 conv served by x-halo boxes (map 0); segments 9.. are plain taps
+  int halo;      // segments 0..8 are a stride-1 3x3 conv served by halo boxes (map 0); segments 9.. are plain taps
+                 // 1: x-halo, one [130 px x 64 ch] box per sub-tile and (ky, channel block); tap kx = row offset kx
+                 // 2: y-halo (OW < 128), one [OW px x (2 bh + 2) rows x 64 ch] box per (kx, channel block) for BOTH sub-tiles;
+                 //    tap ky of sub-tile s = row offset (s bh + ky) OW
+  int halo_jstep;   // descriptor-word step between the three taps served by one box: 8 (one 128-B row) or OW * 8
+  int halo_bytes;   // bytes of one halo item (expect_tx)
+  int kx_outer;     // conv9 issued (kx, channel block, ky) (see conv9_kx_outer in gemm_tc.cu)
   int nkb_conv;  // K blocks per tap of that conv (Cin / 64)
   int halo_div;  // nb_div of the halo source
   int conv9;     // segments 0..8 are one 3x3 conv (halo or not): K blocks are issued in (ky, channel block, kx) order
@@ -119,7 +125,24 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
         __syncwarp();
         if (++bi == p.b_slots) { bi = 0; bph ^= 1; }
       };
-      if (p.halo) {
+      if (p.halo == 2) {
+        const int h0 = p.halo_div > 1 ? s0.nb0 / p.halo_div : s0.nb0;
+        for (int kx = 0; kx < 3; ++kx)
+          for (int kb = 0; kb < p.nkb_conv; ++kb) {
+            mbar_wait(a_empty0 + ai * 8, aph ^ 1);
+            if (elect_one()) {
+              const uint32_t fa = a_full0 + ai * 8;
+              if (no_tma) mbar_arrive(fa);
+              else {
+                mbar_expect_tx(fa, (uint32_t)p.halo_bytes);
+                tma_load_5d(a_ring0 + (uint32_t)(ai * p.a_slot_bytes), &mapA0, fa, kb * TC_BK, kx - 1, 0, s0.y0 - 1, h0);
+              }
+            }
+            __syncwarp();
+            if (++ai == p.a_slots) { ai = 0; aph ^= 1; }
+            for (int ky = 0; ky < 3; ++ky) load_b((ky * 3 + kx) * p.nkb_conv + kb);
+          }
+      } else if (p.halo) {
         const int h0 = p.halo_div > 1 ? s0.nb0 / p.halo_div : s0.nb0, h1 = p.halo_div > 1 ? s1.nb0 / p.halo_div : s1.nb0;
         for (int ky = 0; ky < 3; ++ky)
           for (int kb = 0; kb < p.nkb_conv; ++kb) {
@@ -159,10 +182,16 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
       };
       int kb_glob = p.halo ? 9 * p.nkb_conv : 0;
       int s_first = first_tap_seg;
-      if (!p.halo && p.conv9) {   // same (ky, channel block, kx) accumulation order as the halo mode and gemm_tc
-        for (int ky = 0; ky < 3; ++ky)
-          for (int kb = 0; kb < p.nkb_conv; ++kb)
-            for (int kx = 0; kx < 3; ++kx) issue_tap(p.seg[ky * 3 + kx], kb, (ky * 3 + kx) * p.nkb_conv + kb);
+      if (!p.halo && p.conv9) {   // same accumulation order as the halo modes and gemm_tc
+        if (p.kx_outer) {
+          for (int kx = 0; kx < 3; ++kx)
+            for (int kb = 0; kb < p.nkb_conv; ++kb)
+              for (int ky = 0; ky < 3; ++ky) issue_tap(p.seg[ky * 3 + kx], kb, (ky * 3 + kx) * p.nkb_conv + kb);
+        } else {
+          for (int ky = 0; ky < 3; ++ky)
+            for (int kb = 0; kb < p.nkb_conv; ++kb)
+              for (int kx = 0; kx < 3; ++kx) issue_tap(p.seg[ky * 3 + kx], kb, (ky * 3 + kx) * p.nkb_conv + kb);
+        }
         s_first = 9;
         kb_glob = 9 * p.nkb_conv;
       }
@@ -190,7 +219,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
     long long w_te = 0, w_a = 0, w_b = 0, w_iss = 0, w_com = 0, t_all = prof ? clock64() : 0;
     // running descriptor words / barrier addresses of the current slots (no multiplications in the K loop)
     const uint32_t a_step = (uint32_t)p.a_slot_bytes >> 4, b_step = (uint32_t)b_bytes >> 4;
-    const uint32_t a_lo_base = (((a_ring0 + (uint32_t)sub * (p.halo ? (uint32_t)T2_HALO_SUB : (uint32_t)TC_A_BYTES)) & 0x3FFFFu) >> 4) | (1u << 16);
+    const uint32_t a_lo_base = (((a_ring0 + (uint32_t)sub * (p.halo == 1 ? (uint32_t)T2_HALO_SUB : (uint32_t)TC_A_BYTES)) & 0x3FFFFu) >> 4) | (1u << 16);
+    const uint32_t jstep = (uint32_t)p.halo_jstep;
     const uint32_t a_lo_tap_base = (((a_ring0 + (uint32_t)sub * (uint32_t)TC_A_BYTES) & 0x3FFFFu) >> 4) | (1u << 16);
     const uint32_t b_lo_base = ((b_ring0 & 0x3FFFFu) >> 4) | (1u << 16);
     uint32_t a_off = 0, b_lo = b_lo_base;           // a_off: (slot index * slot bytes) >> 4
@@ -210,7 +240,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
           if (!no_ring) { long long c0 = prof ? clock64() : 0; mbar_wait(b_fb, bph); if (prof) w_b += clock64() - c0; }
           tc_fence_after();
           // halo box: output pixel xl with tap kx=j reads smem row xl + j  ->  start the operand j rows (128 B) in
-          const uint32_t alo = alo_item + (uint32_t)(j * 8);
+          // (y-halo box: tap ky=j of this sub-tile starts j image rows = j * OW smem rows further in)
+          const uint32_t alo = alo_item + (uint32_t)j * jstep;
           const bool last_j = j == nb_blocks - 1;
           if (elect_one()) {
             const long long c_i0 = prof ? clock64() : 0;
@@ -319,6 +350,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
 // ---- host side ----------------------------------------------------------------------------------------------
 PFN_cuTensorMapEncodeTiled_v12000 tc_encode_fn();
 bool is_conv9(const GemmDev& g);
+bool conv9_kx_outer(const GemmDev& g);
 
 static int encode_map(CUtensorMap* map, const SegDev& s, int NBsrc, int bx, int by, int bnb) {
   auto enc = tc_encode_fn();
@@ -369,7 +401,20 @@ int launch_gemm_tc2(const GemmDev& g, cudaStream_t st, int bw, int bh, int bn, i
            s.kc == s.C && s.dy == i / 3 - 1 && s.dx == i % 3 - 1 && s.nb_div == g.seg[0].nb_div;
   }
   for (int i = 9; halo && i < g.nseg; ++i) halo = g.seg[i].src != g.seg[0].src;
-  p.halo = halo;
+  // y-halo mode: rows narrower than a tile (a sub-tile = bh full rows of one sample), sub-tile pairs stacked vertically
+  bool yhalo = !halo && g.nseg >= 9 && g.OW < 128 && bw == g.OW && bn == 1 && tiles_x == 1 && tiles_y % 2 == 0 &&
+               bh * bw == TC_BM && !getenv("DCB_TC2_NO_YHALO");
+  for (int i = 0; yhalo && i < 9; ++i) {
+    const SegDev& s = g.seg[i];
+    yhalo = s.src == g.seg[0].src && s.C == g.seg[0].C && s.H == g.OH && s.W == g.OW && s.stride == 1 && s.c_off == 0 &&
+            s.kc == s.C && s.dy == i / 3 - 1 && s.dx == i % 3 - 1 && s.nb_div == g.seg[0].nb_div;
+  }
+  for (int i = 9; yhalo && i < g.nseg; ++i) yhalo = g.seg[i].src != g.seg[0].src;
+  p.halo = halo ? 1 : (yhalo ? 2 : 0);
+  p.halo_jstep = yhalo ? g.OW * 8 : 8;
+  p.halo_bytes = yhalo ? (2 * bh + 2) * g.OW * 128 : 2 * 130 * 128;
+  halo = halo || yhalo;
+  p.kx_outer = conv9_kx_outer(g);
   p.conv9 = is_conv9(g);
   p.nkb_conv = (halo || p.conv9) ? g.seg[0].kc / TC_BK : 0;
   p.halo_div = halo ? g.seg[0].nb_div : 1;
@@ -380,7 +425,8 @@ int launch_gemm_tc2(const GemmDev& g, cudaStream_t st, int bw, int bh, int bn, i
   int nmaps = 0;
   int rc;
   if (halo) {
-    rc = encode_map(&maps[0], g.seg[0], (g.NB + g.seg[0].nb_div - 1) / g.seg[0].nb_div, 130, 1, 1);
+    rc = yhalo ? encode_map(&maps[0], g.seg[0], (g.NB + g.seg[0].nb_div - 1) / g.seg[0].nb_div, g.OW, 2 * bh + 2, 1)
+               : encode_map(&maps[0], g.seg[0], (g.NB + g.seg[0].nb_div - 1) / g.seg[0].nb_div, 130, 1, 1);
     if (rc) return rc;
     map_key[0] = g.seg[0];
     map_key[0].src = nullptr;  // never matches a tap segment: the halo map has a different box
@@ -431,7 +477,8 @@ int launch_gemm_tc2(const GemmDev& g, cudaStream_t st, int bw, int bh, int bn, i
   }
 
   const int b_bytes = BN * TC_BK * 2;
-  p.a_slot_bytes = halo ? 2 * T2_HALO_SUB : 2 * TC_A_BYTES;
+  p.a_slot_bytes = yhalo ? p.halo_bytes : (halo ? 2 * T2_HALO_SUB : 2 * TC_A_BYTES);
+  if (yhalo && p.a_slot_bytes < 2 * TC_A_BYTES) return DCB_EUNSUPPORTED;   // tap segments share the ring slots
   p.a_slots = getenv("DCB_TC2_ASLOTS") ? atoi(getenv("DCB_TC2_ASLOTS")) : 2;
   const int fixed = 1024 + 512 + 2 * TC_EPI_BYTES + p.a_slots * p.a_slot_bytes;
   int b_slots = (TC_SMEM_LIMIT - fixed) / b_bytes;

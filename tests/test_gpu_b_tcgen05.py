@@ -379,3 +379,54 @@ def test_tc2_halo_fused_mse_is_bit_identical_to_tap_kernel(dev, S, div, H, W, Ci
     pred = conv_ref(a.float(), w.float(), b).reshape(S, H * W, Co)
     ref = ((scale.view(-1, 1, 1) * pred - tgt.repeat_interleave(div, 0)) ** 2).sum((1, 2))
     assert rel_err(e_halo, ref) < 2e-5
+
+
+@pytest.mark.parametrize("NB,H,W,Ci,Co,extra", [
+    (20, 64, 64, 128, 128, "res"),        # OW = 64: box [64 px x 6 rows], residual prefetch
+    (40, 32, 32, 64, 256, "rowvec"),      # OW = 32: box [32 px x 10 rows], two N tiles, conv1-style row vector
+    (160, 16, 16, 128, 128, "shortcut"),  # OW = 16: box [16 px x 18 rows] + 1x1 shortcut segments as plain taps
+    (12, 64, 64, 64, 64, "unit"),         # per-unit source (dcb_seg.nb_div = 2) and BN = 64
+])
+def test_tc2_yhalo_conv3x3(dev, NB, H, W, Ci, Co, extra):
+    """y-halo mode of gemm_tc2 (rows narrower than a tile: one [OW px x (2 bh + 2) rows] box per (kx, channel block) serves
+    the three ky taps of both sub-tiles) vs torch, vs the SIMT engine and -- bit for bit, same K-block order -- vs the same
+    kernel with nine separately loaded taps (DCB_TC2_NO_YHALO=1) and vs gemm_tc_kernel (DCB_NO_TC2=1)."""
+    import os
+    from dcb200 import _lib as L
+    from dcb200 import engine as E
+    torch.manual_seed(0)
+    div = 2 if extra == "unit" else 1
+    x = _bf(NB // div, H, W, Ci, dev=dev)
+    w = (torch.randn(Co, Ci, 3, 3, device=dev) * 0.05).to(torch.bfloat16)
+    b = torch.randn(Co, device=dev)
+    wp = w.permute(0, 2, 3, 1).reshape(Co, -1).contiguous()
+    segs = E.conv3x3_segs(x, Ci, H, W, nb_div=div)
+    xr = x.float().repeat_interleave(div, 0)
+    ref = conv_ref(xr, w.float(), b).reshape(-1, Co)
+    kw = dict(bias=b)
+    if extra == "res":
+        r = _bf(NB * H * W, Co, dev=dev)
+        kw.update(residual=r, res_ld=Co)
+        ref = ref + r.float()
+    elif extra == "rowvec":
+        rv = torch.randn(NB, Co, device=dev)
+        kw.update(rowvec=rv, rowvec_ld=Co, rows_per_group=H * W)
+        ref = (ref.reshape(NB, H * W, Co) + rv[:, None, :]).reshape(-1, Co)
+    elif extra == "shortcut":
+        x0 = _bf(NB, H, W, 64, dev=dev)
+        ws = (torch.randn(Co, 64, 1, 1, device=dev) * 0.05).to(torch.bfloat16)
+        wp = torch.cat([wp, ws.reshape(Co, -1)], 1).contiguous()
+        segs = segs + [E.seg(x0, 64, H, W)]
+        ref = ref + conv_ref(x0.float(), ws.float(), None, 1, 0).reshape(-1, Co)
+    out, st = E.gemm(_ctx(dev), segs, wp, Co, NB, H, W, gn_stats=True, **kw)
+    assert out.dtype == torch.bfloat16 and rel_err(out, ref) < 5e-3
+    simt = E.gemm(_ctx(dev, L.ENGINE_SIMT), segs, wp, Co, NB, H, W, **kw)
+    assert rel_err(out, simt.float()) < 1e-3
+    for knob in ("DCB_TC2_NO_YHALO", "DCB_NO_TC2"):
+        os.environ[knob] = "1"
+        try:
+            other, st2 = E.gemm(_ctx(dev), segs, wp, Co, NB, H, W, gn_stats=True, **kw)
+        finally:
+            del os.environ[knob]
+        assert torch.equal(out, other), knob
+        assert torch.equal(st, st2), knob
