@@ -205,6 +205,9 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    if args.path != "classify":
+        return run_next_row(args, dc, cfg, x_host, x_dev, pre, classes, T, world, rank, dev, barrier)
+
     def timed(fn, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -323,6 +326,92 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_next_row(args, dc, cfg, x_host, x_dev, pre, classes, T, world, rank, dev, barrier):
+    """SURVEY 8(f) rows measured like the hot path: CUDA events around K steps, inputs resident (value) and from pinned
+    host memory with the result read back (e2e).  sample: DDPM + CFG, 2 evaluations per step and image (+1 final step);
+    loss: one forward per image; evaluate: classify through DiffusionClassifier.evaluate with a host-side loader
+    (prefetched H2D) and GPU-side metrics."""
+    import dcb200
+    BS = x_dev.shape[0]
+    g = torch.Generator().manual_seed(1)
+    text_host = torch.randint(0, classes, (BS,), generator=g).pin_memory()
+    text_dev = text_host.to(dev)
+    if args.path == "sample":
+        cfg.sampling_steps, cfg.cfg_w = 20, 1.0
+        dc.cfg_w = 1.0
+        evals = BS * 2 * (cfg.sampling_steps + 1)
+        res = lambda: dc.sample(pre(x_dev), text_dev)
+        e2e = lambda: dc.sample(pre(x_host.to(dev, non_blocking=True)), text_host.to(dev, non_blocking=True)).cpu()
+        d2h = x_host.numel() * 4
+        what = f"DiffusionClassifier.sample: DDPM, {cfg.sampling_steps} steps + final, cfg_w=1 (cond + uncond folded into the batch)"
+    elif args.path == "loss":
+        evals = BS
+        res = lambda: dc.loss(pre(x_dev), text_dev)
+        e2e = lambda: dc.loss(pre(x_host.to(dev, non_blocking=True)), text_host.to(dev, non_blocking=True)).item()
+        d2h = 4
+        what = "DiffusionClassifier.loss forward (min-SNR weighted eps-MSE of the online model)"
+    else:
+        nb = 3
+        loader = [{"images": x_host.clone(), "prompt": text_host.clone()} for _ in range(nb)]
+        loader_dev = [{"images": pre(x_dev), "prompt": text_dev} for _ in range(nb)]
+        evals = nb * BS * classes * T
+        mets = [dcb200.metrics.Accuracy("accuracy"), dcb200.metrics.F1("f1")]
+        for m in mets:
+            m.set_device(dev)
+
+        def run(ld):
+            torch.manual_seed(1234)
+            _, _, ms_ = dc.evaluate(ld, metrics=mets, classification=True)
+            return ms_
+
+        res = lambda: run(loader_dev)
+        e2e = lambda: float(run(loader)[0].get_output()["accuracy"])
+        d2h = 16
+        what = f"DiffusionClassifier.evaluate: {nb} host batches of {BS} images, next batch's H2D overlapped, GPU-side Accuracy/F1"
+
+    def timed(fn):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(max(args.warmup, 3)):
+        res()
+    sampler = ClockSampler(dev.index or 0)
+    if rank == 0:
+        sampler.start()
+    n0 = dcb200.launch_count()
+    ms = timed(res)
+    launches = dcb200.launch_count() - n0
+    clocks = sampler.stop() if rank == 0 else None
+    e2e()
+    ms2 = timed(e2e)
+    if rank == 0:
+        wl = workload_name(args.workload, classes, T)
+        # replicas: every rank runs the same step on its own images (no collective on these paths)
+        print(json.dumps({
+            "metric": "denoiser evals/sec", "value": world * evals * args.steps / (ms / 1e3), "unit": "evals/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"{what}; network and image shape of: {wl}", "path": args.path,
+                       "images_per_step": BS * world, "evals_per_step": evals * world, "replicas": world},
+            "e2e": {"value": world * evals * args.steps / (ms2 / 1e3), "unit": "evals/s",
+                    "h2d_bytes_per_step": x_host.numel() * 4 + BS * 8, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms2 / args.steps},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": None, "cpu_baseline": None}))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -333,6 +422,8 @@ def main():
     ap.add_argument("--images", type=int, default=0, help="images per GPU per step")
     ap.add_argument("--max-batch", type=int, default=0, help="denoiser samples per launch sequence")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--path", default="classify", choices=["classify", "sample", "loss", "evaluate"],
+                    help="which caller of the denoiser kernels a step is (SURVEY 8f rows; default = the hot path)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -328,7 +328,7 @@ class DiffusionClassifier(nn.Module):
         table = None if is_dit else net.cross_attn_table(ctx, pk, E.cast(ctx, self.encoder.weight))
         return is_dit, ctx, pk, table
 
-    def _sampler_coefs(self, from_t, dev):
+    def _sampler_coefs(self, from_t, dev, call=0):
         """[sampling_steps + 1, 8] fp32 rows {c, a_t, a_s, s_t, s_s, sqrt(var), w, 0} and the logsnr fed to the denoiser per
         evaluation, computed exactly as ddpm_sampler_step does (:189-205).  The last row is the reference's separate
         "final step" (:268-288), which re-evaluates at steps[-2]."""
@@ -341,7 +341,9 @@ class DiffusionClassifier(nn.Module):
         s_t, s_s = torch.sqrt(torch.sigmoid(-lt)), torch.sqrt(torch.sigmoid(-ls))
         sd = torch.sqrt((s_s ** 2) * c)
         w = torch.full_like(c, float(self.cfg_w))
-        return torch.stack([c, a_t, a_s, s_t, s_s, sd, w, torch.zeros_like(c)], 1).contiguous().to(dev), lt.to(dev)
+        # Philox unit base of every evaluation as int bits: distinct per step and per sample() call under one seed
+        step = (torch.arange(n + 1, dtype=torch.int64) + call * (n + 1)).remainder(1 << 30).to(torch.int32).view(torch.float32)
+        return torch.stack([c, a_t, a_s, s_t, s_s, sd, w, step], 1).contiguous().to(dev), lt.to(dev)
 
     # ---- next row f2: DDPM ancestral sampler with classifier-free guidance (:175-293) ------------------------------
     @torch.no_grad()
@@ -387,7 +389,9 @@ class DiffusionClassifier(nn.Module):
             z, _ = self.diffuse(x.float(), torch.sqrt(torch.sigmoid(logsnr)).view(-1, 1, 1, 1),
                                 torch.sqrt(torch.sigmoid(-logsnr)).view(-1, 1, 1, 1))
             z = z.contiguous()
-        coef, lt = self._sampler_coefs(from_t, dev)
+        call = self._eps_calls
+        self._eps_calls += 1
+        coef, lt = self._sampler_coefs(from_t, dev, call)
         n = int(self.config.sampling_steps)
         guided = float(self.cfg_w) != 0.0
         rep = 2 if guided else 1
@@ -397,10 +401,67 @@ class DiffusionClassifier(nn.Module):
         share = (not is_dit) and guided
         patch = net.config.patch_size if is_dit else 1
         v_param = self.pred_param == 'v'
-        seed = int(torch.initial_seed() & 0x7FFFFFFFFFFFFFFF) + 0x9E3779B9 * self._eps_calls
-        self._eps_calls += 1
+        seed = int(torch.initial_seed() & 0x7FFFFFFFFFFFFFFF)
+        use_graph = ctx.precision == "bf16" and noise_all is None and getattr(self.config, "dcb_cuda_graph", None) is not False \
+            and os.environ.get("DCB_CUDA_GRAPH", "1") != "0"
+        mode = 1 if is_dit else 0
+        rows = (H // patch) * (W // patch)
+        if use_graph:   # persistent buffers: a replay reads / writes fixed addresses; z is updated in place
+            key = ("sample", id(net), id(pk), B, rep, Cimg, H, W, v_param, share, str(dev))
+            st = self._graphs.get(key)
+            if st is None:
+                if len(self._graphs) >= 6:
+                    self._graphs.clear()
+                st = self._graphs[key] = dict(
+                    z=torch.empty(B, Cimg, H, W, device=dev), t=torch.empty(B, device=dev), coef=torch.empty(8, device=dev),
+                    a_in=ctx.empty((B if share else B * rep) * rows, pk.kpad_in), table=None, graph=None, warm=0, seed=0,
+                    cls=torch.empty(B * rep, device=dev, dtype=torch.int32))
+            st["z"].copy_(z)
+            if table is not None:
+                if st["table"] is None or st["table"].shape != table.shape:
+                    st["table"] = torch.empty_like(table)
+                st["table"].copy_(table)
+            st["cls"].copy_(cls32)
+
+            def body(final):
+                E.prologue(ctx, mode, st["z"], B, 1 if share else rep, Cimg, H, W, pk.kpad_in, patch=patch, a_out=st["a_in"])
+                if is_dit:
+                    pred = net.run(ctx, pk, st["a_in"], st["t"], B, rep, st["cls"])
+                else:
+                    pred = net.run(ctx, pk, st["a_in"], st["t"], B, rep, H, W, st["table"], xattn_idx=st["cls"],
+                                   share_prefix=share)
+                E.ddpm_step(ctx, st["z"], pred, rep, patch if is_dit else 0, st["coef"], v_param, final, seed=st["seed"],
+                            out=st["z"])
+            if st["graph"] is not None and st["seed"] != seed:
+                st["graph"] = None      # the Philox seed is a kernel argument baked into the graph: capture again
+            st["seed"] = seed
+            for i in range(n + 1):
+                st["t"].copy_(lt[i].expand(B))
+                st["coef"].copy_(coef[i])
+                if i == n:
+                    body(True)                                   # the final (noise-free, clipped) step runs eagerly
+                elif st["graph"] is not None:
+                    st["graph"].replay()
+                    L.lib().dcb_note_graph_replay(st["n_kernels"])
+                elif st["warm"] < 1:
+                    body(False)
+                    st["warm"] += 1
+                else:
+                    torch.cuda.synchronize()
+                    g = torch.cuda.CUDAGraph()
+                    if _GraphedDenoiser._pool is None:
+                        _GraphedDenoiser._pool = torch.cuda.graph_pool_handle()
+                    n0 = L.launch_count()
+                    with torch.cuda.graph(g, pool=_GraphedDenoiser._pool):
+                        body(False)
+                    st["n_kernels"] = L.launch_count() - n0
+                    L.lib().dcb_note_graph_replay(-st["n_kernels"])
+                    st["graph"] = g
+                    g.replay()
+                    L.lib().dcb_note_graph_replay(st["n_kernels"])
+            return st["z"].clone()
         for i in range(n + 1):
-            a_in, _ = E.prologue(ctx, 1 if is_dit else 0, z, B, 1 if share else rep, Cimg, H, W, pk.kpad_in, patch=patch)
+            a_in, _ = E.prologue(ctx, mode, z, B, 1 if share else rep, Cimg, H, W, pk.kpad_in, patch=patch)
             t = lt[i].expand(B).contiguous()
             if is_dit:
                 pred = net.run(ctx, pk, a_in, t, B, rep, cls32)
@@ -408,8 +469,7 @@ class DiffusionClassifier(nn.Module):
                 pred = net.run(ctx, pk, a_in, t, B, rep, H, W, table, xattn_idx=cls32, share_prefix=share)
             final = i == n
             noise = None if (final or noise_all is None) else noise_all[i].to(dev).float().contiguous()
-            z = E.ddpm_step(ctx, z, pred, rep, patch if is_dit else 0, coef[i], v_param, final, noise=noise, seed=seed,
-                            unit_id0=i * B)
+            z = E.ddpm_step(ctx, z, pred, rep, patch if is_dit else 0, coef[i], v_param, final, noise=noise, seed=seed)
         return z
 
     # ---- next row f4: training loss, forward only (:295-344) --------------------------------------------------------
@@ -453,31 +513,43 @@ class DiffusionClassifier(nn.Module):
     # ---- next row f1: callers of the hot paths (diffusion_classifier.py:532-655) -----------------------------------
     @staticmethod
     def _prefetched(loader, dev, stop_idx=None):
-        """batches of ``loader`` with every tensor on ``dev``: batch k+1 is copied (pinned staging, side stream) while
-        batch k is being scored, so the H2D never sits between two launch sequences."""
+        """batches of ``loader`` with every tensor on ``dev``: batch k+1 is copied (persistent pinned staging buffers, side
+        stream) while batch k is being scored, so the H2D never sits between two launch sequences and no pinned memory is
+        allocated per batch."""
         side = torch.cuda.Stream(dev)
         it = iter(loader)
+        staging = [{}, {}]          # two generations of pinned buffers per batch key; reused when shape / dtype match
+        copied = [None, None]       # event of the last H2D that read generation g
 
-        def load():
+        def load(gen):
             try:
                 b = next(it)
             except StopIteration:
                 return None
+            if copied[gen] is not None:
+                copied[gen].synchronize()            # the copy out of these staging buffers (two batches ago) is done
             out = {}
             with torch.cuda.stream(side):
                 for k, v in b.items():
                     if torch.is_tensor(v) and not v.is_cuda:
-                        v = v.pin_memory().to(dev, non_blocking=True)
+                        if not v.is_pinned():
+                            buf = staging[gen].get(k)
+                            if buf is None or buf.shape != v.shape or buf.dtype != v.dtype:
+                                buf = staging[gen][k] = torch.empty(v.shape, dtype=v.dtype, pin_memory=True)
+                            buf.copy_(v)
+                            v = buf
+                        v = v.to(dev, non_blocking=True)
                     out[k] = v
             ev = torch.cuda.Event()
             ev.record(side)
+            copied[gen] = ev
             return out, ev
 
-        idx, nxt = 0, load()
+        idx, nxt = 0, load(0)
         while nxt is not None:
             cur, ev = nxt
             last = stop_idx is not None and idx == stop_idx
-            nxt = None if last else load()
+            nxt = None if last else load((idx + 1) & 1)
             torch.cuda.current_stream(dev).wait_event(ev)
             for v in cur.values():
                 if torch.is_tensor(v) and v.is_cuda:

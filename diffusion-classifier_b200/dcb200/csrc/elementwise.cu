@@ -63,12 +63,15 @@ __global__ void qsample_kernel(const float* __restrict__ x, const float* __restr
 //   pred = (1+w)*cond - w*uncond ; x = clip(v ? a_t z - s_t pred : (z - s_t pred)/a_t) ; mu = a_s (z (1-c)/a_t + c x)
 //   z_out = final ? clip(mu) : mu + sqrt(var) * noise
 // z NCHW fp32; pred is read in the layout the last GEMM of the denoiser writes (NHWC, or DiT token-major (py,px,c) when
-// patch > 0), rows of sample b*rep (+1 = unconditional).  coef[8] = {c, a_t, a_s, s_t, s_s, sqrt(var), w, -} on device.
+// patch > 0), rows of sample b*rep (+1 = unconditional).  coef[8] = {c, a_t, a_s, s_t, s_s, sqrt(var), w, step index (int bits)}.
 __global__ void ddpm_step_kernel(const float* __restrict__ z_t, const float* __restrict__ pred, int rep, int patch,
                                  const float* __restrict__ coef, int v_param, int final_step,
                                  const float* __restrict__ noise_pre, uint64_t seed, int64_t unit_id0, int B, int C, int HW,
                                  int W, float* __restrict__ z_out) {
   const float c = coef[0], a_t = coef[1], a_s = coef[2], s_t = coef[3], sd = coef[5], w = coef[6];
+  // coef[7] carries the step index as an int bit pattern: the Philox unit of image b at step i is unit_id0 + i*B + b, so a
+  // CUDA graph of the step (fixed kernel arguments) still draws fresh noise every replay
+  const int64_t unit0 = unit_id0 + (int64_t)__float_as_int(coef[7]) * B;
   const int64_t total = (int64_t)B * C * HW;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int pix = (int)(i % HW);
@@ -93,7 +96,7 @@ __global__ void ddpm_step_kernel(const float* __restrict__ z_t, const float* __r
     float o;
     if (final_step) o = fminf(fmaxf(mu, -1.f), 1.f);
     else {
-      const float n = noise_pre ? noise_pre[i] : philox_normal(seed, (uint64_t)(unit_id0 + b), (uint64_t)((int64_t)ch * HW + pix));
+      const float n = noise_pre ? noise_pre[i] : philox_normal(seed, (uint64_t)(unit0 + b), (uint64_t)((int64_t)ch * HW + pix));
       o = mu + n * sd;
     }
     z_out[i] = o;

@@ -54,7 +54,8 @@ int dcb_prologue(int mode, int dtype, const float* x, const float* eps_predrawn,
  *   mu = a_s*(z*(1-c)/a_t + c*x);  z_out = final_step ? clip(mu) : mu + sqrt(var)*noise
  * z_t / z_out / noise_predrawn: [B,C,H,W] fp32 NCHW (noise NULL -> Philox(seed, unit_id0+b)); pred: fp32 output of the
  * denoiser's last GEMM for samples b*rep (+1 = unconditional when rep == 2), NHWC rows (patch == 0) or DiT token-major
- * (py,px,c) columns (patch > 0); coef: DEVICE [8] = {c, a_t, a_s, s_t, s_s, sqrt(var), w, 0}. */
+ * (py,px,c) columns (patch > 0); coef: DEVICE [8] = {c, a_t, a_s, s_t, s_s, sqrt(var), w, step index i as int32 bits};
+ * the Philox unit of image b is unit_id0 + i*B + b (so a captured CUDA graph of the step draws fresh noise per replay). */
 int dcb_ddpm_step(const float* z_t, const float* pred, int rep, int patch, const float* coef, int v_param,
                   int final_step, const float* noise_predrawn, uint64_t seed, int64_t unit_id0, int B, int C, int H,
                   int W, float* z_out, dcb_stream stream);
