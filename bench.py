@@ -178,6 +178,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the ONE JSON line (NCCL_DEBUG=VERSION prints)
         dist.init_process_group("nccl", device_id=dev)
     arch, cfg, classes, T, gflop, ipg = build_workload(args.workload)
     if args.images:
