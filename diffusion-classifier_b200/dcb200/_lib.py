@@ -62,6 +62,8 @@ _PROTOS = {
                                         c_void_p, c_void_p]),
     "dcb_groupnorm_apply_div": (c_int, [c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                         c_void_p, c_void_p, c_void_p, c_float, c_int, c_void_p, c_void_p]),
+    "dcb_groupnorm_fused": (c_int, [c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                                    c_void_p, c_float, c_int, c_void_p, c_void_p]),
     "dcb_expand_samples": (c_int, [c_int, c_void_p, c_int, c_int, c_i64, c_void_p, c_void_p]),
     "dcb_layernorm": (c_int, [c_int, c_void_p, c_i64, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int,
                               c_int, c_void_p, c_void_p]),

@@ -124,7 +124,51 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const T* __restric
   __shared__ float s_mean[64], s_rstd[64];
   const int n = blockIdx.y;
   const int C = C0 + C1, V = C / VN, cpg = C / G;
-  if (threadIdx.x < G) {
+  if (part == nullptr) {
+    // fused mode (one block per sample, dcb_groupnorm_fused; V <= blockDim): the statistics pass runs here with the apply
+    // pass's own thread -> (pixel row, 16-byte channel slot) mapping, so the whole sample is in flight at once; a thread's
+    // slot lies in one group, partials are combined per group in fixed order.  The apply pass re-reads the sample from
+    // L1/L2: HBM sees one read and one write, and there is one launch instead of two.
+    __shared__ float s_ps[GN_THREADS], s_pq[GN_THREADS];
+    const int nrows_f = blockDim.x / V, prow_f = threadIdx.x / V, v_f = threadIdx.x % V;
+    const int c_f = v_f * VN;
+    const T* base;
+    int cs;
+    if (c_f < C0) { base = x0 + (int64_t)(n / div0) * HW * C0 + c_f; cs = C0; }
+    else { base = x1 + (int64_t)(n / div1) * HW * C1 + (c_f - C0); cs = C1; }
+    float s = 0.f, q = 0.f;
+    for (int p = prow_f; p < HW; p += 4 * nrows_f) {
+      float f[4][VN];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (p + u * nrows_f < HW) Vec<T>::load(base + (int64_t)(p + u * nrows_f) * cs, f[u]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (p + u * nrows_f < HW) {
+#pragma unroll
+          for (int i = 0; i < VN; ++i) { s += f[u][i]; q = fmaf(f[u][i], f[u][i], q); }
+        }
+    }
+    s_ps[threadIdx.x] = s;
+    s_pq[threadIdx.x] = q;
+    __syncthreads();
+    if (threadIdx.x < G) {
+      const int vpg = cpg / VN;
+      double ds = 0.0, dq = 0.0;
+      for (int r = 0; r < nrows_f; ++r)
+        for (int j = 0; j < vpg; ++j) {
+          const int t = r * V + threadIdx.x * vpg + j;
+          ds += s_ps[t];
+          dq += s_pq[t];
+        }
+      const double cnt = (double)HW * cpg;
+      const double mean = ds / cnt;
+      double var = dq / cnt - mean * mean;
+      if (var < 0.0) var = 0.0;
+      s_mean[threadIdx.x] = (float)mean;
+      s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+  } else if (threadIdx.x < G) {
     double s = 0.0, q = 0.0;
     const float* pp = part + ((int64_t)n * chunks * G + threadIdx.x) * 2;
     for (int k = 0; k < chunks; ++k) { s += pp[(int64_t)k * G * 2]; q += pp[(int64_t)k * G * 2 + 1]; }
@@ -346,6 +390,32 @@ extern "C" int dcb_groupnorm_apply_div(int dtype, const void* x0, int C0, int di
                                                        out, st, div0, div1)
                            : gn_apply_t<float>(x0, C0, x1, C1, NB, HW, G, chunks, part, gamma, beta, eps, silu, out, st,
                                                div0, div1);
+}
+
+extern "C" int dcb_groupnorm_fused(int dtype, const void* x0, int C0, int div0, const void* x1, int C1, int div1, int NB,
+                                   int HW, int G, const float* gamma, const float* beta, float eps, int silu, void* out,
+                                   dcb_stream stream) {
+  int rc = gn_check(dtype, C0, C1, G, x1);
+  if (rc) return rc;
+  const int vn = dtype == DCB_BF16 ? 8 : 4, cpg = (C0 + C1) / G;
+  DCB_REQUIRE(cpg % vn == 0 && C0 % cpg == 0, "groupnorm_fused: channels per group (%d) must be a multiple of %d and "
+              "divide C0 (%d)", cpg, vn, C0);
+  DCB_REQUIRE((C0 + C1) / vn <= GN_THREADS, "groupnorm_fused: at most %d channels", GN_THREADS * vn);
+  DCB_REQUIRE(NB >= 1 && NB <= 65535 && HW >= 1, "groupnorm_fused: bad NB/HW");
+  if (div0 < 1) div0 = 1;
+  if (div1 < 1) div1 = 1;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int V = (C0 + C1) / vn, threads = gn_threads(V);
+  dim3 grid(1, NB);
+  if (dtype == DCB_BF16)
+    gn_apply_kernel<__nv_bfloat16><<<grid, threads, 0, st>>>((const __nv_bfloat16*)x0, C0, (const __nv_bfloat16*)x1, C1, HW,
+                                                             G, 1, nullptr, gamma, beta, eps, silu, (__nv_bfloat16*)out,
+                                                             HW, div0, div1);
+  else
+    gn_apply_kernel<float><<<grid, threads, 0, st>>>((const float*)x0, C0, (const float*)x1, C1, HW, G, 1, nullptr, gamma,
+                                                     beta, eps, silu, (float*)out, HW, div0, div1);
+  DCB_CHECK_LAUNCH("gn_fused");
+  return DCB_OK;
 }
 
 extern "C" int dcb_groupnorm_stats_from_tiles(const float* part0, int C0, int div0, const float* part1, int C1, int div1,

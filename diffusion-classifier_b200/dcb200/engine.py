@@ -58,6 +58,7 @@ class GemmProfile:
 
 PROFILE = None
 USE_TILE_STATS = __import__("os").environ.get("DCB_TILE_STATS", "1") != "0"
+USE_FUSED_SMALL_GN = __import__("os").environ.get("DCB_FUSED_SMALL_GN", "1") != "0"
 FOLD_UPSAMPLE = __import__("os").environ.get("DCB_FOLD_UPSAMPLE", "1") != "0"   # A/B switch for upsample_conv
 
 
@@ -211,6 +212,13 @@ def groupnorm(ctx, x0, C0, x1, C1, NB, HW, gamma, beta, eps, silu, G=32, div0=1,
         part = torch.empty(NB * G * 2, device=ctx.device, dtype=torch.float32)
         L.check(lib.dcb_groupnorm_stats_from_tiles(st0.data_ptr(), C0, div0, _p(st1), C1, div1, NB, HW // 128, G,
                                                    part.data_ptr(), ctx.stream()), "groupnorm_stats_from_tiles")
+    elif USE_FUSED_SMALL_GN and HW < 128 and ((C0 + C1) // G) % (8 if ctx.code == L.BF16 else 4) == 0 \
+            and C0 % ((C0 + C1) // G) == 0 and (C0 + C1) <= 256 * (8 if ctx.code == L.BF16 else 4):
+        # samples smaller than a GEMM tile: statistics + apply in one launch, one block per sample (a function of the
+        # per-sample shape only, so results stay independent of the batch composition)
+        L.check(lib.dcb_groupnorm_fused(ctx.code, x0.data_ptr(), C0, div0, _p(x1), C1, div1, NB, HW, G, gamma.data_ptr(),
+                                        beta.data_ptr(), eps, int(silu), out.data_ptr(), ctx.stream()), "groupnorm_fused")
+        return out
     else:
         chunks = gn_chunks(NB, HW, C0 + C1)
         part = torch.empty(NB * chunks * G * 2, device=ctx.device, dtype=torch.float32)

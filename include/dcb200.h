@@ -132,6 +132,11 @@ int dcb_groupnorm_stats(int dtype, const void* x0, int C0, const void* x1, int C
 int dcb_groupnorm_apply(int dtype, const void* x0, int C0, const void* x1, int C1, int NB, int HW, int G, int chunks,
                         const float* part, const float* gamma, const float* beta, float eps, int silu, void* out,
                         dcb_stream stream);
+/* statistics + apply in ONE launch, one thread block per sample: for samples too small to feed a GEMM tile of their own
+ * (HW < 128: no producer-side tile statistics), where two launches and a second HBM read of the tensor dominate.
+ * Needs (C0 + C1) / G to be a multiple of the vector width (8 bf16 / 4 fp32) and to divide C0. */
+int dcb_groupnorm_fused(int dtype, const void* x0, int C0, int div0, const void* x1, int C1, int div1, int NB, int HW,
+                        int G, const float* gamma, const float* beta, float eps, int silu, void* out, dcb_stream stream);
 /* statistics pass replaced by a reduction of producer-written tile partials (dcb_gemm_desc.gn_part):
  * part0/part1: [n_src*tiles_per_sample][C][2] per source (part1 NULL when C1 == 0), sample n reads source sample n/div;
  * writes part_out[NB][1][G][2] = (sum, sumsq) per group, i.e. the `part` of dcb_groupnorm_apply with chunks = 1 */

@@ -274,3 +274,33 @@ def test_attention_tcgen05_head64(dev, B, heads, N, qscale):
     assert rel_err(out, ref) < 1e-2
     simt = E.attention(_ctx(dev, "bf16"), qb, B, N, heads, d, simt=True).float()
     assert rel_err(out, simt) < 1e-2
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("C0,C1,HW,NB,div1", [(256, 0, 64, 7, 1), (256, 256, 16, 300, 1), (512, 0, 16, 33, 1),
+                                              (384, 128, 64, 12, 3), (1024, 0, 64, 5, 1)])
+def test_groupnorm_fused_small_samples(dev, precision, C0, C1, HW, NB, div1):
+    """dcb_groupnorm_fused (HW < 128: statistics + apply in one launch, one block per sample) vs torch and vs the
+    two-kernel path; a sample's result does not depend on the batch it sits in."""
+    from dcb200 import engine as E
+    ctx = _ctx(dev, precision)
+    torch.manual_seed(0)
+    x0 = (torch.randn(NB, HW, C0, device=dev) * 2 + 0.5).to(ctx.tdtype)
+    x1 = (torch.randn(NB // div1, HW, C1, device=dev) - 1.0).to(ctx.tdtype) if C1 else None
+    g, b = torch.randn(C0 + C1, device=dev), torch.randn(C0 + C1, device=dev)
+    assert E.USE_FUSED_SMALL_GN
+    out = E.groupnorm(ctx, x0, C0, x1, C1, NB, HW, g, b, 1e-5, True, div1=div1)
+    xc = x0.float() if x1 is None else torch.cat([x0.float(), x1.float().repeat_interleave(div1, 0)], -1)
+    ref = F.silu(F.group_norm(xc.permute(0, 2, 1), 32, g, b, 1e-5).permute(0, 2, 1))
+    tol = 2e-5 if precision == "fp32" else 6e-3
+    assert rel_err(out.float().reshape(NB, HW, -1), ref) < tol
+    E.USE_FUSED_SMALL_GN = False
+    try:
+        two = E.groupnorm(ctx, x0, C0, x1, C1, NB, HW, g, b, 1e-5, True, div1=div1)
+    finally:
+        E.USE_FUSED_SMALL_GN = True
+    assert rel_err(out.float(), two.float()) < (1e-6 if precision == "fp32" else 3e-3)
+    k = div1 * max(1, NB // div1 // 2)       # a prefix of the batch (whole units) gives bit-identical rows
+    part = E.groupnorm(ctx, x0[:k].contiguous(), C0, None if x1 is None else x1[:k // div1].contiguous(), C1, k, HW, g, b, 1e-5,
+                       True, div1=div1)
+    assert torch.equal(part, out[:k * HW])
