@@ -118,8 +118,14 @@ def gemm(ctx: Ctx, segs, W, N, NB, OH, OW, *, bias=None, rowvec=None, rowvec_ld=
         d.out_dtype = L.F32 if out.dtype == torch.float32 else L.BF16
     gpart = None
     if gn_stats and ctx.code == L.BF16 and out is not None:
+        # Ask for the layer shape at a canonical LARGE batch: the tile width (hence staged vs direct epilogue, hence whether
+        # tile statistics exist) shrinks with the tile count, and a small batch must not take a different statistics path
+        # than a large one -- a sample's result has to be independent of the batch it is scored in.  (Staged at the large
+        # batch implies staged at every smaller one: tiles only get narrower.)
         ok = C.c_int32()
+        d.NB = max(NB, 1 << 14)
         L.check(lib.dcb_gemm_gn_layout(C.byref(d), C.byref(ok)), "gemm_gn_layout")
+        d.NB = NB
         if ok.value:
             gpart = gn_part if gn_part is not None else \
                 torch.empty((M + 127) // 128, n_out, 2, device=ctx.device, dtype=torch.float32)

@@ -75,3 +75,43 @@ def test_c5_ipmsa5_dwt_unet_with_gpu_haar(dev):
     assert w.shape == (1, 40, 128, 128) and (w.cpu() - w_ref).abs().max() < 1e-6
     cfg = base_cfg(classes=2, evaluation_per_stage=[1], noise_d=128, image_size=128, wavelet_transform=True)
     _run(dev, "unet", IPMSA5_DWT_UNET, cfg, w_ref, 1, 1, 40.0)
+
+
+# ---- size-independent properties at the BASELINE configs' full tensor sizes ------------------------------------------------
+def test_c5_haar_roundtrip_and_energy_at_full_size(dev):
+    """IDWT(DWT(x)) == x and Parseval (orthonormal Haar: sum of squares preserved) on a full IPMSA batch [8,10,256,256]."""
+    import dcb200
+    x = torch.rand(8, 10, 256, 256, device=dev, generator=torch.Generator(device=dev).manual_seed(0)) * 2 - 1
+    w = dcb200.wavelet_dec_2(x)
+    assert w.shape == (8, 40, 128, 128)
+    assert abs(float((w.double() ** 2).sum()) / float((x.double() ** 2).sum()) - 1) < 1e-6
+    back = dcb200.wavelet_enc_2(w)
+    assert (back - x).abs().max() < 1e-6
+    # linearity of the transform and the /2 scaling used by experiments/ipmsa/inference.py:153-155
+    y = torch.rand_like(x)
+    assert (dcb200.wavelet_dec_2(x + 2 * y) - (w + 2 * dcb200.wavelet_dec_2(y))).abs().max() < 1e-5
+    assert torch.equal(dcb200.wavelet_dec_2(x, 0.5), w * 0.5)
+
+
+def test_c2_unet128_error_table_invariant_to_chunking_and_graphs(dev):
+    """unet-128 at its real size: the per-(image, class, timestep) error table is bit-identical whatever the launch-sequence
+    size (dcb_max_batch: different tile counts select different tcgen05 kernels / halo modes), with CUDA-graph replay or
+    eager launches, and with or without the shared class-independent prefix; in-kernel Philox noise is a function of
+    (seed, unit) only."""
+    import dcb200
+    torch.manual_seed(0)
+    net = dcb200.UNetCondition2D(**UNET128)
+    cfg = base_cfg(classes=2, evaluation_per_stage=[6], noise_d=128, image_size=128)
+    dc = dcb200.DiffusionClassifier(net, cfg).to(dev).eval()
+    x = torch.rand(3, 3, 128, 128, device=dev, generator=torch.Generator(device=dev).manual_seed(1)) * 2 - 1
+    tables = []
+    for mb, graph, share in ((0, None, None), (8, None, None), (14, False, None), (36, None, False), (2, False, False)):
+        cfg.dcb_max_batch, cfg.dcb_cuda_graph, cfg.dcb_share_prefix = mb, graph, share
+        for _ in range(3 if graph is None else 1):     # third call replays the captured graph
+            dc._eps_calls = 0
+            torch.manual_seed(5)
+            labels = dc.classify(x)
+        tables.append((dc.last_errors.clone(), labels.clone()))
+    for t, l in tables[1:]:
+        assert torch.equal(t, tables[0][0]) and torch.equal(l, tables[0][1])
+    assert torch.isfinite(tables[0][0]).all()
