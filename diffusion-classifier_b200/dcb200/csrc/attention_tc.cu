@@ -80,7 +80,12 @@ __device__ __forceinline__ float ex2f(float x) {
 }
 
 // the single-pass kernel is exact iff nothing underflows: max|q| max|k| c <= 50 bounds every (M_i - s_ij) c by 100 < 126
-__device__ __forceinline__ bool at_fast_ok(const float* norms, float sc) { return sqrtf(norms[0] * norms[1]) * sc <= 50.f; }
+// Decided per (batch, head) -- blockIdx.z, blockIdx.y -- from that head's own max|q|^2, max|k|^2, so which of the two kernels
+// scores a sample never depends on the other samples of the launch (results stay independent of the batch composition).
+__device__ __forceinline__ bool at_fast_ok(const float* norms, float sc) {
+  const float* n = norms + 2 + ((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * 2;
+  return sqrtf(n[0] * n[1]) * sc <= 50.f;
+}
 
 struct AtParams {
   int N, nblk;        // tokens per (batch, head); ceil(N / 128)
@@ -109,7 +114,7 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
   uint64_t* o_full = p_full + 2;                 // [2]  MMA -> softmax: O_t(j) = P_t(j) V_j complete
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
 
-  // when the single-pass kernel (attention_tc_fast.cu) can take this launch, this one has nothing to do
+  // when the single-pass kernel can take this (batch, head), this one has nothing to do for it
   if (p.norms != nullptr && at_fast_ok(p.norms, p.sc)) return;
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
@@ -350,7 +355,8 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
 // of a score row are independent, so each query row is shared by TWO threads (warps w and w+8: keys 0-63 / 64-127, O
 // channels 0-31 / 32-63) with no exchange until the final row sum -- 16 softmax warps, four per scheduler, keep the MUFU
 // pipe fed.  Exact as long as nothing underflows; the launch falls back to flash_attn_tc_kernel by itself otherwise
-// (at_fast_ok, evaluated on the device: both kernels are always enqueued and one of them returns at once).
+// (at_fast_ok, evaluated on the device per (batch, head): both kernels are always enqueued and, for every head, the CTAs of
+// one of them return at once).
 // =====================================================================================================================
 constexpr int ATF_THREADS = 64 + 512;   // TMA warp, MMA warp, 2 tiles x 2 halves x 4 softmax warps
 

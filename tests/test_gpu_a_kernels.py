@@ -304,3 +304,22 @@ def test_groupnorm_fused_small_samples(dev, precision, C0, C1, HW, NB, div1):
     part = E.groupnorm(ctx, x0[:k].contiguous(), C0, None if x1 is None else x1[:k // div1].contiguous(), C1, k, HW, g, b, 1e-5,
                        True, div1=div1)
     assert torch.equal(part, out[:k * HW])
+
+
+def test_attention_tcgen05_fast_path_decided_per_head(dev):
+    """single-pass vs running-maximum kernel is chosen per (batch, head) from that head's own norms: a sample's attention
+    output is bit-identical whether or not a sample with huge logits (which forces the fallback for ITS heads) shares the
+    launch."""
+    from dcb200 import engine as E
+    torch.manual_seed(0)
+    B, heads, N, d = 3, 4, 1024, 64
+    qkv = torch.randn(B * N, 3 * heads * d, device=dev)
+    qkv[N:2 * N, :heads * d] *= 14.0          # sample 1: logits far beyond the single-pass kernel's exactness bound
+    qb = qkv.to(torch.bfloat16)
+    q, k, v = (t.float().reshape(B, N, heads, d).transpose(1, 2) for t in qb.chunk(3, -1))
+    ref = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B * N, heads * d)
+    out = E.attention(_ctx(dev, "bf16"), qb, B, N, heads, d)
+    assert torch.isfinite(out).all() and rel_err(out.float(), ref) < 1e-2
+    alone0 = E.attention(_ctx(dev, "bf16"), qb[:N].contiguous(), 1, N, heads, d)
+    alone2 = E.attention(_ctx(dev, "bf16"), qb[2 * N:].contiguous(), 1, N, heads, d)
+    assert torch.equal(out[:N], alone0) and torch.equal(out[2 * N:], alone2)
