@@ -93,17 +93,18 @@ def test_c5_haar_roundtrip_and_energy_at_full_size(dev):
     assert torch.equal(dcb200.wavelet_dec_2(x, 0.5), w * 0.5)
 
 
-def test_c2_unet128_error_table_invariant_to_chunking_and_graphs(dev):
-    """unet-128 at its real size: the per-(image, class, timestep) error table is bit-identical whatever the launch-sequence
+@pytest.mark.parametrize("arch,C,S", [(UNET128, 3, 128), (IPMSA5_DWT_UNET, 40, 128)], ids=["c2_unet128", "c5_ipmsa5"])
+def test_unet_error_table_invariant_to_chunking_and_graphs(dev, arch, C, S):
+    """unet-128 / ipmsa-5-dwt at their real sizes: the per-(image, class, timestep) error table is bit-identical whatever the launch-sequence
     size (dcb_max_batch: different tile counts select different tcgen05 kernels / halo modes), with CUDA-graph replay or
     eager launches, and with or without the shared class-independent prefix; in-kernel Philox noise is a function of
     (seed, unit) only."""
     import dcb200
     torch.manual_seed(0)
-    net = dcb200.UNetCondition2D(**UNET128)
-    cfg = base_cfg(classes=2, evaluation_per_stage=[6], noise_d=128, image_size=128)
+    net = dcb200.UNetCondition2D(**arch)
+    cfg = base_cfg(classes=2, evaluation_per_stage=[6], noise_d=S, image_size=S)
     dc = dcb200.DiffusionClassifier(net, cfg).to(dev).eval()
-    x = torch.rand(3, 3, 128, 128, device=dev, generator=torch.Generator(device=dev).manual_seed(1)) * 2 - 1
+    x = torch.rand(3, C, S, S, device=dev, generator=torch.Generator(device=dev).manual_seed(1)) * 2 - 1
     tables = []
     for mb, graph, share in ((0, None, None), (8, None, None), (14, False, None), (36, None, False), (2, False, False)):
         cfg.dcb_max_batch, cfg.dcb_cuda_graph, cfg.dcb_share_prefix = mb, graph, share
@@ -115,3 +116,26 @@ def test_c2_unet128_error_table_invariant_to_chunking_and_graphs(dev):
     for t, l in tables[1:]:
         assert torch.equal(t, tables[0][0]) and torch.equal(l, tables[0][1])
     assert torch.isfinite(tables[0][0]).all()
+
+
+def test_c4_dit_b4_error_table_invariant_to_chunking(dev):
+    """DiT-B/4 256 at its real size: bit-identical error table for every launch-sequence size (tile counts select
+    different tile widths / epilogues / tcgen05 kernels; attention picks its kernel per (batch, head))."""
+    import dcb200
+    torch.manual_seed(0)
+    net = dcb200.DiT(**DIT_B4_256)
+    cfg = base_cfg(classes=2, evaluation_per_stage=[3], noise_d=64, image_size=256, schedule="shifted_cosine",
+                   encoder_type="DiT", pred_param="v")
+    dc = dcb200.DiffusionClassifier(net, cfg).to(dev).eval()
+    x = torch.rand(2, 3, 256, 256, device=dev, generator=torch.Generator(device=dev).manual_seed(1)) * 2 - 1
+    tables = []
+    for mb, graph in ((0, False), (2, False), (6, None), (4, False)):
+        cfg.dcb_max_batch, cfg.dcb_cuda_graph = mb, graph
+        for _ in range(3 if graph is None else 1):
+            dc._eps_calls = 0
+            torch.manual_seed(5)
+            dc.classify(x)
+        tables.append(dc.last_errors.clone())
+    for t in tables[1:]:
+        assert torch.equal(t, tables[0])
+    assert torch.isfinite(tables[0]).all()
