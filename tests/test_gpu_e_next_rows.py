@@ -200,3 +200,43 @@ def test_loss_default_noise_and_dit(dev):
     dc._eps_calls = 0
     b = dc.loss(x, text)
     assert a.dim() == 0 and torch.isfinite(a) and torch.equal(a, b) and float(a) > 0
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_sample_and_loss_at_unet128_size_vs_oracle(dev, precision):
+    """f2 / f4 at BASELINE configs[1]'s real architecture and image size: DDPM + CFG sampling (3 denoiser evaluation pairs)
+    and the loss forward vs the fp32 oracle on the host with identical pre-drawn noise."""
+    import dcb200
+    from helpers import UNET128, make_pair
+    from oracle import loop
+    o, p = make_pair("unet", UNET128, seed=0)
+    cfg = base_cfg(classes=2, noise_d=128, image_size=128, sampling_steps=2, cfg_w=1.5)
+    torch.manual_seed(1)
+    dc = dcb200.DiffusionClassifier(p, cfg)
+    with torch.no_grad():
+        dc.encoder.weight.mul_(40.0)
+    enc = torch.nn.Embedding(3, UNET128["encoder_hid_dim"])
+    enc.load_state_dict(dc.encoder.state_dict())
+    g = torch.Generator().manual_seed(2)
+    x = torch.rand(1, 3, 128, 128, generator=g) * 2 - 1
+    text = torch.tensor([1])
+    z0, noise = torch.randn(1, 3, 128, 128, generator=g), torch.randn(2, 1, 3, 128, 128, generator=g)
+    t, eps = torch.rand(1, generator=g), torch.randn(1, 3, 128, 128, generator=g)
+    den = lambda z, lam, encoder_hidden_states: o(z, lam, encoder_hidden_states)[0]  # noqa: E731
+    ref = loop.sample_oracle(den, enc, cfg, x, text, z_init=z0, noise_all=noise)
+    with torch.no_grad():
+        lref = loop.loss_oracle(lambda x, noise_labels, encoder_hidden_states: o(x, noise_labels, encoder_hidden_states)[0],
+                                enc, cfg, x, text, t=t, eps=eps)
+    dc = dc.to(dev).eval()
+    dc.ema.ema_model.precision = dc.model.precision = precision
+    out = dc.sample(x.to(dev), text.to(dev), z_init=z0, noise_all=noise).cpu()
+    d = (out - ref).abs()
+    if precision == "fp32":
+        # the first step divides the prediction by alpha(t=1) ~ 5e-4 before clipping: the few pixels whose x-prediction
+        # falls inside (-1, 1) there carry the denoiser's 1e-4 relative fp32 difference amplified ~2000x
+        assert d.median() < 1e-5 and d.max() < 5e-2 and float((d > 1e-3).float().mean()) < 1e-3, \
+            (float(d.median()), float(d.max()))
+    else:
+        assert d.median() < 2e-2 and d.mean() < 0.1, (float(d.median()), float(d.mean()))
+    l = dc.loss(x.to(dev), text.to(dev), t=t, eps=eps)
+    assert abs(float(l) - float(lref)) < (1e-4 if precision == "fp32" else 1e-2) * float(lref)
