@@ -472,6 +472,24 @@ int launch_gemm_tc(const GemmDev& g, cudaStream_t st) {
     else p.uniform = t.bn == 1 && e.rows_per_group % e.rows_per_sample == 0;
   }
   // big N<=128-wide problems: 256-pixel CTAs with split A/B rings (+ x-halo reuse for 3x3 convs), see gemm_tc2.cu
+  // wide mode of gemm_tc2 (256 x 256 CTA tiles: a third less L2 -> SMEM operand traffic per FLOP for the K <= 3072
+  // projections) -- EXPERIMENT, opt-in with DCB_TC2_WIDE=1.  Measured on B200 (M = 204800): K=N=768 438 vs 950 TF/s,
+  // N=2304 451 vs 1005, K=3072/N=768 952 vs 1138, K=512/N=1536 310 vs 614: with both 128 x 256 accumulators filling TMEM
+  // there is no second accumulator stage, and the thread-per-row direct epilogue (~10k cycles per tile) serialises with
+  // the MMAs.  It needs a coalesced epilogue and cta_group::2 (256 columns per CTA) to pay; kept bit-identical to the
+  // default path so that it can be A/B'd (test_tc2_wide_256x256_tiles).
+  {
+    const int m_tiles = t.tiles_x * t.tiles_y * t.tiles_nb;
+    const EpiDev& e = g.epi;
+    const bool wide = getenv("DCB_TC2_WIDE") && !getenv("DCB_NO_TC2") && e.N % 256 == 0 && e.N >= 512 && g.K >= 512 &&
+                      e.act != DCB_ACT_GEGLU && e.gn_part == nullptr && e.mse_part == nullptr && e.out != nullptr &&
+                      e.out_dtype == DCB_BF16 && e.out_ld % 8 == 0 && ((uintptr_t)e.out % 16) == 0 && !is_conv9(g) &&
+                      t.bn == 1 && (m_tiles / 2) * (e.N / 256) >= 2 * num_sms();
+    if (wide) {
+      rc = launch_gemm_tc2(g, st, t.bw, t.bh, t.bn, t.tiles_x, t.tiles_y, t.tiles_nb, 256, p.uniform, 0);
+      if (rc != DCB_EUNSUPPORTED) return rc;
+    }
+  }
   // (also the fused eps-MSE of conv_out -- N = out_channels, nothing stored: with 9 separately loaded taps it is bound by
   //  L2->SMEM traffic, the x-halo boxes cut that 3x)
   const bool mse_only = g.epi.mse_part != nullptr && g.epi.out == nullptr && g.epi.residual == nullptr && t.bn == 1 &&

@@ -38,6 +38,8 @@ struct Tc2Params {
   int a_slots, b_slots, a_slot_bytes;
   uint32_t idesc;
   int uniform, base_off_mode;
+  int acc_stages, acc_stage_cols, acc_sub_cols;   // TMEM accumulators: 2 stages x 2 sub-tiles x 128 columns, or (wide
+                                                  // mode, BN = 256) 1 stage x 2 sub-tiles x 256 columns
   int staged;    // 0: direct epilogue (fused eps-MSE of conv_out: nothing is written but per-tile partial sums)
   int dbg;  // experiments: 1 = no TMA traffic (barriers only), 2 = no epilogue work, 4 = no MMA issue
 };
@@ -227,7 +229,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
     uint32_t a_fb = a_full0, a_eb = a_empty0, b_fb = b_full0, b_eb = b_empty0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       { long long c0 = prof ? clock64() : 0; mbar_wait(smem_u32(&tempty_bar[as * 2 + sub]), aphase ^ 1); if (prof) w_te += clock64() - c0; }
-      const uint32_t d_tmem = tmem_base + (uint32_t)(as * 256 + sub * 128);
+      const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.acc_stage_cols + sub * p.acc_sub_cols);
       const uint32_t tfull_addr = smem_u32(&tfull_bar[as * 2 + sub]);
       uint32_t accumulate = 0;
       for (int item = 0; item < items; ++item) {
@@ -270,7 +272,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
         a_off += a_step; a_fb += 8; a_eb += 8;
         if (++ai == p.a_slots) { ai = 0; aph ^= 1; a_off = 0; a_fb = a_full0; a_eb = a_empty0; }
       }
-      if (++as == 2) { as = 0; aphase ^= 1; }
+      if (++as == p.acc_stages) { as = 0; aphase ^= 1; }
     }
     if (prof && (blockIdx.x % 21 == 0) && lane == 0)
       printf("tc2 block %d mma warp %d: total %lld cycles, waits: tempty %lld a_full %lld b_full %lld; mma issue %lld commits %lld (tiles %d, k-blocks/tile %d)\n", (int)blockIdx.x, sub,
@@ -285,14 +287,14 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
     uint32_t aphase = 0;
     for (int tile = blockIdx.x, it = 0; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int tn = tile % p.n_tiles, tp = tile / p.n_tiles;
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 256 + grp * 128);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.acc_stage_cols + grp * p.acc_sub_cols);
       if (p.dbg & 2) {
         mbar_wait(smem_u32(&tfull_bar[as * 2 + grp]), aphase);
         tc_fence_after();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[as * 2 + grp]));
-        if (++as == 2) { as = 0; aphase ^= 1; }
+        if (++as == p.acc_stages) { as = 0; aphase ^= 1; }
         continue;
       }
       if (p.staged) {
@@ -335,7 +337,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
           epi_bar(1 + grp);
         }
       }
-      if (++as == 2) { as = 0; aphase ^= 1; }
+      if (++as == p.acc_stages) { as = 0; aphase ^= 1; }
     }
   }
 
@@ -380,6 +382,12 @@ int launch_gemm_tc2(const GemmDev& g, cudaStream_t st, int bw, int bh, int bn, i
   Tc2Params p;
   memset(&p, 0, sizeof(p));
   p.staged = staged;
+  // wide mode (BN = 256): two 128 x 256 accumulators fill the 512 TMEM columns, so there is one accumulator stage -- the
+  // MMAs of the next tile wait for the epilogue -- in exchange for 64 instead of 94 B/clk/SM of operand traffic
+  DCB_REQUIRE(BN <= 128 || (BN == 256 && !staged), "gemm_tc2: BN = 256 needs the direct epilogue");
+  p.acc_stages = BN == 256 ? 1 : 2;
+  p.acc_stage_cols = BN == 256 ? 0 : 256;
+  p.acc_sub_cols = BN == 256 ? 256 : 128;
   p.bw = bw; p.bh = bh; p.bn = bn; p.tiles_x = tiles_x; p.tiles_y = tiles_y; p.tiles_nb = tiles_nb;
   p.m_tiles = tiles_x * tiles_y * tiles_nb;
   p.OW = g.OW; p.OH = g.OH; p.NB = g.NB; p.BN = BN;
@@ -484,7 +492,8 @@ int launch_gemm_tc2(const GemmDev& g, cudaStream_t st, int bw, int bh, int bn, i
   // (6 K blocks) + 5 B slots, but tap-mode GEMMs (the K <= 768 projections) were A-ring bound with 2 slots -- with 3 + 3
   // the same kernel moves 20 % more (measured: 782 -> 941 TF/s at M=204800, K=N=768).
   const int kb_per_a = halo ? 3 : 1;
-  const int ring_bytes = TC_SMEM_LIMIT - (1024 + 512 + 2 * TC_EPI_BYTES);
+  const int epi_bytes = staged ? 2 * TC_EPI_BYTES : 0;   // the direct epilogues need no staging tiles: deeper rings
+  const int ring_bytes = TC_SMEM_LIMIT - (1024 + 512 + epi_bytes);
   int best_a = 2, best_score = -1;
   for (int a = 2; a <= 4; ++a) {
     int b = (ring_bytes - a * p.a_slot_bytes) / b_bytes;
@@ -494,7 +503,7 @@ int launch_gemm_tc2(const GemmDev& g, cudaStream_t st, int bw, int bh, int bn, i
     if (score > best_score) { best_score = score; best_a = a; }
   }
   p.a_slots = getenv("DCB_TC2_ASLOTS") ? atoi(getenv("DCB_TC2_ASLOTS")) : best_a;
-  const int fixed = 1024 + 512 + 2 * TC_EPI_BYTES + p.a_slots * p.a_slot_bytes;
+  const int fixed = 1024 + 512 + epi_bytes + p.a_slots * p.a_slot_bytes;
   int b_slots = (TC_SMEM_LIMIT - fixed) / b_bytes;
   if (b_slots > T2_MAX_SLOTS) b_slots = T2_MAX_SLOTS;
   if (getenv("DCB_TC2_BSLOTS") && atoi(getenv("DCB_TC2_BSLOTS")) < b_slots) b_slots = atoi(getenv("DCB_TC2_BSLOTS"));

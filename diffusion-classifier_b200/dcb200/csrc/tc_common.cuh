@@ -236,9 +236,12 @@ __device__ __forceinline__ void epi_store16(const EpiDev& e, int m, int n0, floa
     for (int i = 0; i < 16; ++i)
       if (i < nvalid) v[i] += rv[i];
   }
+  // bf16 outputs use the one-MUFU activations of the staged epilogue (a layer must not depend on which epilogue its tile
+  // shape selects); fp32 outputs keep the exact ones
+  const bool fast_act = e.out != nullptr && e.out_dtype == DCB_BF16;
   if (e.act == DCB_ACT_SILU || e.act == DCB_ACT_GELU_TANH) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = apply_act(e.act, v[i]);
+    for (int i = 0; i < 16; ++i) v[i] = fast_act ? apply_act_fast(e.act, v[i]) : apply_act(e.act, v[i]);
   }
   if (e.gate) {
     const float* gt = e.gate + (int64_t)grp * e.gate_ld + n0;
@@ -266,7 +269,7 @@ __device__ __forceinline__ void epi_store16(const EpiDev& e, int m, int n0, floa
   }
   if (e.act_post != DCB_ACT_NONE) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = apply_act(e.act_post, v[i]);
+    for (int i = 0; i < 16; ++i) v[i] = fast_act ? apply_act_fast(e.act_post, v[i]) : apply_act(e.act_post, v[i]);
   }
   if (e.mse_part) {
     const float sc = e.mse_scale ? e.mse_scale[sample] : 1.f;

@@ -430,3 +430,46 @@ def test_tc2_yhalo_conv3x3(dev, NB, H, W, Ci, Co, extra):
             del os.environ[knob]
         assert torch.equal(out, other), knob
         assert torch.equal(st, st2), knob
+
+
+@pytest.mark.parametrize("M,K,N,extra", [
+    (128 * 200, 768, 768, "gate_res"),        # DiT attention out-projection: adaLN gate + residual
+    (128 * 203 + 50, 768, 2304, "bias"),      # QKV; odd number of 128-row sub-tiles + ragged last tile
+    (128 * 240, 768, 3072, "gelu"),           # DiT FFN1: tanh-GELU in the direct epilogue (one-MUFU form, as staged)
+    (128 * 400, 3072, 768, "gate_res"),       # DiT FFN2 (deep K)
+    (128 * 300, 512, 1536, "rowvec"),         # U-Net QKV shape with a per-group row vector
+])
+def test_tc2_wide_256x256_tiles(dev, M, K, N, extra):
+    """experimental wide mode of gemm_tc2 (DCB_TC2_WIDE=1; BN = 256: two 128 x 256 accumulators, single TMEM stage, direct
+    epilogue -- measured slower than the default, see gemm_tc.cu) vs torch fp32 math and, bit for bit, vs the default
+    128-wide staged path: the direct and staged epilogues perform the same arithmetic in the same order."""
+    import os
+    from dcb200 import _lib as L
+    from dcb200 import engine as E
+    torch.manual_seed(0)
+    x, w, b = _bf(M, K, dev=dev), _bf(N, K, dev=dev, scale=0.05), torch.randn(N, device=dev)
+    rpg = 128 * 25
+    ngrp = (M + rpg - 1) // rpg
+    kw = dict(bias=b)
+    ref = x.float() @ w.float().t() + b
+    grp = torch.arange(M, device=dev) // rpg
+    if extra == "gate_res":
+        gate, res = torch.randn(ngrp, N, device=dev), _bf(M, N, dev=dev)
+        kw.update(gate=gate, gate_ld=N, rows_per_group=rpg, residual=res, res_ld=N)
+        ref = ref * gate[grp] + res.float()
+    elif extra == "gelu":
+        kw.update(act=L.ACT_GELU_TANH)
+        ref = F.gelu(ref, approximate="tanh")
+    elif extra == "rowvec":
+        rv = torch.randn(ngrp, N, device=dev)
+        kw.update(rowvec=rv, rowvec_ld=N, rows_per_group=rpg)
+        ref = ref + rv[grp]
+    narrow = E.linear(_ctx(dev), x, w, N, **kw)
+    assert narrow.dtype == torch.bfloat16 and rel_err(narrow, ref) < 6e-3
+    n0 = L.launch_count()
+    os.environ["DCB_TC2_WIDE"] = "1"
+    try:
+        out = E.linear(_ctx(dev), x, w, N, **kw)
+    finally:
+        del os.environ["DCB_TC2_WIDE"]
+    assert L.launch_count() == n0 + 1 and torch.equal(out, narrow)
