@@ -219,8 +219,11 @@ def groupnorm(ctx, x0, C0, x1, C1, NB, HW, gamma, beta, eps, silu, G=32, div0=1,
         L.check(lib.dcb_groupnorm_stats_from_tiles(st0.data_ptr(), C0, div0, _p(st1), C1, div1, NB, HW // 128, G,
                                                    part.data_ptr(), ctx.stream()), "groupnorm_stats_from_tiles")
     elif USE_FUSED_SMALL_GN and HW < 128 and ((C0 + C1) // G) % (8 if ctx.code == L.BF16 else 4) == 0 \
-            and C0 % ((C0 + C1) // G) == 0 and (C0 + C1) <= 256 * (8 if ctx.code == L.BF16 else 4):
-        # samples smaller than a GEMM tile: statistics + apply in one launch, one block per sample (a function of the
+            and C0 % ((C0 + C1) // G) == 0 and (C0 + C1) <= 256 * (8 if ctx.code == L.BF16 else 4) \
+            and HW * (C0 + C1) <= 32768:
+        # (one block walks the whole sample twice: beyond ~32 k elements -- the 8^2 x 1024-channel level of unet-128 -- the
+        #  two-kernel path with several blocks per sample is faster: 15.7 vs 11.8 ms of gn_apply per 200 evals, ncu)
+        # small samples below a GEMM tile: statistics + apply in one launch, one block per sample (a function of the
         # per-sample shape only, so results stay independent of the batch composition)
         L.check(lib.dcb_groupnorm_fused(ctx.code, x0.data_ptr(), C0, div0, _p(x1), C1, div1, NB, HW, G, gamma.data_ptr(),
                                         beta.data_ptr(), eps, int(silu), out.data_ptr(), ctx.stream()), "groupnorm_fused")
