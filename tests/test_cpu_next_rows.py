@@ -179,3 +179,39 @@ def test_sampler_coefficients_match_step_oracle():
         assert torch.allclose(coef[i, 5] ** 2, var[0], rtol=1e-5, atol=1e-12)
         assert torch.allclose(coef[i, 0], -torch.special.expm1(l_t - l_s)[0])
         assert float(coef[i, 6]) == 1.25
+
+
+def _metrics_gloo_worker(rank, world, port, out):
+    import torch.distributed as dist
+    from dcb200 import metrics as M
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(100 + rank)
+    mets = [M.Accuracy("accuracy"), M.F1("f1")]
+    for i in range(3):      # replicas: every rank scores its own batches (inference() without dcb_shard)
+        yp, yt = torch.randint(0, 2, (5,), generator=g), torch.randint(0, 2, (5,), generator=g)
+        for m in mets:
+            m.update((yp, {"prompt": yt}))
+    for m in mets:
+        m.sync_across_processes(None)          # one all-reduce per metric
+    if rank == 0:
+        torch.save({m.name: float(m.get_output()[m.name]) for m in mets}, out)
+    dist.destroy_process_group()
+
+
+def test_metrics_sync_across_processes_gloo_world2(tmp_path):
+    """replica mode of inference(): per-rank counters are summed by one all-reduce (utils/metrics.py's accelerator.reduce)."""
+    import torch.multiprocessing as mp
+    out = str(tmp_path / "m.pt")
+    port = 31500 + os.getpid() % 2000
+    mp.spawn(_metrics_gloo_worker, args=(2, port, out), nprocs=2, join=True)
+    got = torch.load(out)
+    yp, yt = [], []
+    for rank in range(2):
+        g = torch.Generator().manual_seed(100 + rank)
+        for i in range(3):
+            yp.append(torch.randint(0, 2, (5,), generator=g))
+            yt.append(torch.randint(0, 2, (5,), generator=g))
+    yp, yt = torch.cat(yp), torch.cat(yt)
+    tp, fp, fn = ((yp == 1) & (yt == 1)).sum(), ((yp == 1) & (yt == 0)).sum(), ((yp == 0) & (yt == 1)).sum()
+    assert abs(got["accuracy"] - float((yp == yt).float().mean())) < 1e-6
+    assert abs(got["f1"] - float(2 * tp / (2 * tp + fp + fn))) < 1e-6
