@@ -495,17 +495,40 @@ class DiffusionClassifier(nn.Module):
         v_param = self.pred_param == 'v'
         seed = int(torch.initial_seed() & 0x7FFFFFFFFFFFFFFF) + 0x9E3779B9 * self._eps_calls
         self._eps_calls += 1
-        a_in, target = E.prologue(ctx, 1 if is_dit else 0, x.contiguous().float(), B, 1, Cimg, H, W, pk.kpad_in,
-                                  patch=patch, eps=None if eps is None else eps.to(dev).float().contiguous(), seed=seed,
-                                  alpha=alpha, sigma=sigma, want_target=True, v_param=v_param)
-        err = torch.empty(B, device=dev, dtype=torch.float32)
-        mse = dict(target=target, div=1, ld=No, err=err, fused=(ctx.precision == "bf16") and rows % 128 == 0,
-                   scale=alpha if v_param else None)
+        fused = (ctx.precision == "bf16") and rows % 128 == 0
         cls32 = text.to(dev).reshape(-1).to(torch.int32).contiguous()
-        if is_dit:
-            net.run(ctx, pk, a_in, logsnr.contiguous(), B, 1, cls32, mse=mse)
+        pro = dict(patch=patch, eps=None if eps is None else eps.to(dev).float().contiguous(), seed=seed, alpha=alpha,
+                   sigma=sigma, want_target=True, v_param=v_param)
+        use_graph = ctx.precision == "bf16" and getattr(self.config, "dcb_cuda_graph", None) is not False \
+            and os.environ.get("DCB_CUDA_GRAPH", "1") != "0"
+        if use_graph:      # same captured launch sequence as classify's, with one "class" (the label) per image
+            key = ("loss", id(net), id(pk), is_dit, B, Cimg, H, W, v_param, fused, str(dev))
+            gr = self._graphs.get(key)
+            if gr is None:
+                if len(self._graphs) >= 6:
+                    self._graphs.clear()
+                gr = self._graphs[key] = _GraphedDenoiser(net, ctx, pk, is_dit, B, 1, Cimg, H, W, patch, v_param, fused,
+                                                          False)
+            if table is not None:
+                if gr.table is None or gr.table.shape != table.shape:
+                    gr.table = torch.empty_like(table)
+                gr.table.copy_(table)
+            E.prologue(ctx, 1 if is_dit else 0, x.contiguous().float(), B, 1, Cimg, H, W, pk.kpad_in, a_out=gr.a_in,
+                       target_out=gr.target, **pro)
+            gr.logsnr.copy_(logsnr)
+            gr.cls.copy_(cls32)
+            if v_param:
+                gr.scale.copy_(alpha)
+            gr.launch()
+            err = gr.err
         else:
-            net.run(ctx, pk, a_in, logsnr.contiguous(), B, 1, H, W, table, xattn_idx=cls32, mse=mse)
+            a_in, target = E.prologue(ctx, 1 if is_dit else 0, x.contiguous().float(), B, 1, Cimg, H, W, pk.kpad_in, **pro)
+            err = torch.empty(B, device=dev, dtype=torch.float32)
+            mse = dict(target=target, div=1, ld=No, err=err, fused=fused, scale=alpha if v_param else None)
+            if is_dit:
+                net.run(ctx, pk, a_in, logsnr.contiguous(), B, 1, cls32, mse=mse)
+            else:
+                net.run(ctx, pk, a_in, logsnr.contiguous(), B, 1, H, W, table, xattn_idx=cls32, mse=mse)
         snr = torch.exp(logsnr).clamp_(max=5)
         weight = 1 / (1 + snr) if v_param else 1 / snr
         return (weight * err).sum() / (B * Cimg * H * W)

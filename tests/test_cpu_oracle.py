@@ -319,3 +319,41 @@ def test_timestep_shard_allreduce_gloo_world2(tmp_path):
                 assert torch.equal(errors[b, c, 2:], truth[b, c])
             else:
                 assert torch.isinf(errors[b, c, 2:]).all()
+
+
+def test_c_abi_argument_validation_returns_codes_not_crashes():
+    """error behaviour of the boundary: bad arguments are rejected with DCB_EINVAL (-1) and a message in dcb_last_error()
+    before anything is launched (so this runs without a GPU); nothing throws or exits across the ABI."""
+    import ctypes as C
+    from dcb200 import _lib
+    lib = _lib.lib()
+
+    def err():
+        return lib.dcb_last_error().decode()
+
+    d = _lib.GemmDesc()
+    assert lib.dcb_gemm(None, None) == -1 and "null descriptor" in err()
+    d.dtype, d.nseg = 7, 1
+    assert lib.dcb_gemm(C.byref(d), None) == -1 and "dtype" in err()
+    d.dtype, d.nseg = _lib.BF16, 0
+    assert lib.dcb_gemm(C.byref(d), None) == -1 and "nseg" in err()
+    d.nseg, d.NB, d.OH, d.OW, d.N = 1, 1, 1, 128, 64
+    assert lib.dcb_gemm(C.byref(d), None) == -1 and "weights" in err()
+    ok = C.c_int32(5)
+    assert lib.dcb_gemm_gn_layout(C.byref(d), C.byref(ok)) == -1
+    assert lib.dcb_ddpm_step(1, 1, 3, 0, 1, 0, 0, None, 0, 0, 1, 3, 8, 8, 1, None) == -1 and "rep" in err()
+    assert lib.dcb_ddpm_step(None, 1, 2, 0, 1, 0, 0, None, 0, 0, 1, 3, 8, 8, 1, None) == -1 and "null" in err()
+    assert lib.dcb_prologue(2, _lib.BF16, 1, None, 0, 0, None, None, None, 1, 1, 3, 8, 8, 1, 64, 1, 1, None, 0, None) == -1
+    assert "mode" in err()
+    assert lib.dcb_prologue(0, _lib.BF16, 1, None, 0, 0, None, None, None, 1, 1, 3, 8, 8, 1, 20, 1, 1, None, 0, None) == -1
+    assert "kpad" in err()
+    assert lib.dcb_groupnorm_fused(_lib.BF16, 1, 64, 1, None, 0, 1, 2, 64, 32, 1, 1, 1e-5, 1, 1, None) == -1   # 2 channels / group
+    assert "channels per group" in err()
+    assert lib.dcb_groupnorm_apply(_lib.BF16, 1, 60, None, 0, 2, 64, 32, 1, 1, 1, 1, 1e-5, 1, 1, None) == -1
+    assert lib.dcb_layernorm(_lib.BF16, 1, 4, 2048, None, None, 1e-5, None, None, 0, 0, 1, None) == -1 and "layernorm" in err()
+    assert lib.dcb_attention(_lib.BF16, 1, 1, 1, 192, 1, 128, 1, 48, 1.0, 1, 48, None) == -1 and "head dim" in err()
+    assert lib.dcb_timestep_embed(_lib.BF16, 1, 1, 1, 7, 0.0, 10000.0, 1, None) == -1 and "even" in err()
+    assert lib.dcb_eps_mse(_lib.BF16, 1, 1, None, 1, 0, 16, 1, 1, None) == -1 and "div" in err()
+    assert lib.dcb_upsample2x(_lib.BF16, 1, 1, 4, 4, 12, 1, None) == -1
+    assert lib.dcb_expand_samples(_lib.BF16, 1, 2, 1, 3, 1, None) == -1
+    assert lib.dcb_launch_count() == 0          # nothing was launched
