@@ -126,6 +126,44 @@ def cpu_port_run(arch, cfg, n_img, n_t, threads, seed=0):
     return n_img * n_t * cfg.classes / dt, dt
 
 
+def gpu_eager_port_run(arch, cfg, n_img, n_t, dev, autocast, seed=0):
+    """the same oracle port (reference loop around the restated diffusers denoiser) in plain torch eager ON THE GPU: what the
+    reference's own code path costs on this B200 (cuDNN / cuBLAS kernels, one forward of batch BS per class and timestep).
+    A second reference line next to the CPU one; test infrastructure, never part of the product path."""
+    from oracle import diffusers_restated as dr
+    from oracle import loop
+    import copy
+    torch.manual_seed(seed)
+    if "patch_size" in arch:
+        net, enc = dr.DiTTransformer2DModel(**arch).eval().to(dev), None
+    else:
+        net = dr.UNet2DConditionModel(**arch).eval().to(dev)
+        enc = torch.nn.Embedding(cfg.classes + 1, arch["encoder_hid_dim"]).to(dev)
+    c2 = copy.deepcopy(cfg)
+    c2.evaluation_per_stage = [n_t]
+    S, C = arch["sample_size"], arch["in_channels"]
+    x = (torch.rand(n_img, C, S, S) * 2 - 1).to(dev)
+
+    class Den(torch.nn.Module):
+        def forward(self, x, noise_labels, encoder_hidden_states):
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+                return net(x, noise_labels, encoder_hidden_states)[0].float()
+
+    den = Den()
+    with torch.no_grad():
+        loop.classify_oracle(den, enc, c2, x[:1])          # warm-up (cuDNN autotune, allocator)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        loop.classify_oracle(den, enc, c2, x)
+        e1.record()
+        torch.cuda.synchronize()
+    dt = e0.elapsed_time(e1) / 1e3
+    del net
+    torch.cuda.empty_cache()
+    return n_img * n_t * cfg.classes / dt, dt
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -307,6 +345,20 @@ def run_ours(args):
                "sample": f"1 image x {n_t} timesteps x {classes} classes ({n_t * classes} evals) of the same workload, "
                          f"fp32 oracle port (reference loop + restated diffusers U-Net) on torch CPU"}
 
+    eager = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        try:
+            n_t = {"unet128": 8, "cifar": 8, "ipmsa": 8}.get(args.workload, 2)
+            rows = {}
+            for tag, ac in (("fp32 (torch default: TF32 cuDNN convs, fp32 matmuls)", False), ("bf16 autocast", True)):
+                v, dt = gpu_eager_port_run(arch, cfg, ipg, n_t, dev, ac)
+                rows[tag] = {"value": v, "seconds": dt}
+            eager = {"unit": "evals/s", "kind": "port", "by_dtype": rows,
+                     "sample": f"{ipg} images x {n_t} timesteps x {classes} classes, one forward of batch {ipg} per (class, "
+                               f"timestep) as diffusion_classifier.py:686-704 issues them; oracle port in torch eager on cuda:0"}
+        except Exception as ex:  # the checker must never take the bench line down
+            eager = {"error": repr(ex)[:200]}
+
     if rank == 0:
         line = {
             "metric": "denoiser evals/sec", "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps,
@@ -321,6 +373,7 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": x_host.numel() * 4,
                     "d2h_bytes_per_step": BS * 8, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "torch_eager_gpu_baseline": eager,
         }
         print(json.dumps(line))
     if world > 1:
