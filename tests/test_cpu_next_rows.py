@@ -215,3 +215,34 @@ def test_metrics_sync_across_processes_gloo_world2(tmp_path):
     tp, fp, fn = ((yp == 1) & (yt == 1)).sum(), ((yp == 1) & (yt == 0)).sum(), ((yp == 0) & (yt == 1)).sum()
     assert abs(got["accuracy"] - float((yp == yt).float().mean())) < 1e-6
     assert abs(got["f1"] - float(2 * tp / (2 * tp + fp + fn))) < 1e-6
+
+
+def test_fold_upsample_weights_identity_on_cpu():
+    """host algebra behind dcb_gemm_desc.up_phase: nearest-2x upsample + conv3x3(pad 1) == four 2x2-tap convs over the
+    low-resolution input whose outputs interleave as (2y + a, 2x + b) -- checked with torch on the CPU in float64."""
+    import torch.nn.functional as F
+    from dcb200 import engine as E
+    torch.manual_seed(0)
+    N, C, Co, H, W = 2, 5, 7, 6, 9
+    x = torch.randn(N, C, H, W, dtype=torch.float64)
+    w = torch.randn(Co, C, 3, 3, dtype=torch.float64)
+    b = torch.randn(Co, dtype=torch.float64)
+    ref = F.conv2d(F.interpolate(x, scale_factor=2.0, mode="nearest"), w, b, padding=1)
+    ph = E.fold_upsample_weights(w)
+    assert len(ph) == 4 and ph[0].shape == (Co, 4 * C)
+    out = torch.empty_like(ref)
+    xp = F.pad(x, (1, 1, 1, 1))
+    for a in range(2):
+        for bb in range(2):
+            wk = ph[2 * a + bb].reshape(Co, 2, 2, C).permute(0, 3, 1, 2)      # [(ty, tx, c)] -> OIHW
+            out[:, :, a::2, bb::2] = F.conv2d(xp[:, :, a:a + H + 1, bb:bb + W + 1], wk, b)
+    assert torch.allclose(out, ref, atol=1e-12)
+    # the segment offsets engine.upsample_conv passes: phase (a, b), tap (ty, tx) reads source pixel (y - 1 + a + ty, x - 1 + b + tx)
+    y0, x0, a, bb = 3, 4, 1, 0
+    acc = b.clone()
+    for ty in range(2):
+        for tx in range(2):
+            yy, xx = y0 - 1 + a + ty, x0 - 1 + bb + tx
+            if 0 <= yy < H and 0 <= xx < W:
+                acc += ph[2 * a + bb].reshape(Co, 2, 2, C)[:, ty, tx] @ x[0, :, yy, xx]
+    assert torch.allclose(acc, ref[0, :, 2 * y0 + a, 2 * x0 + bb], atol=1e-12)
