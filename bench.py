@@ -216,8 +216,19 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the ONE JSON line (NCCL_DEBUG=VERSION prints)
-        dist.init_process_group("nccl", device_id=dev)
+        # keep stdout to the ONE JSON line: NCCL prints its version banner on stdout when the communicator is created
+        # (NCCL_DEBUG=VERSION on the boxes), so file descriptor 1 points at stderr while that happens
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     arch, cfg, classes, T, gflop, ipg = build_workload(args.workload)
     if args.images:
         ipg = args.images
