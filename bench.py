@@ -24,14 +24,14 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-for _p in (ROOT, os.path.join(ROOT, "diffusion-classifier_b200"), os.path.join(ROOT, "tests")):
+for _p in (ROOT, os.path.join(ROOT, "diffusion-classifier_b200")):
     if _p not in sys.path:
         sys.path.insert(0, _p)
 
 import torch  # noqa: E402
 
 WORKLOADS = {
-    # name: (arch key in tests/helpers.py, classes, timesteps, GFLOP/eval, images per GPU per step)
+    # name: (arch key in dcb200/configs.py, classes, timesteps, GFLOP/eval, images per GPU per step)
     "unet128": ("UNET128", 2, 100, 175.79, 4),
     "cifar": ("CIFAR_UNET", 10, 32, 10.454, 16),
     "dit": ("DIT_B4_256", 2, 250, 1315.0, 1),    # BASELINE configs[3]: CheXpert-256 DiT-B/4 (attention + adaLN kernels)
@@ -42,11 +42,11 @@ WORKLOADS = {
 
 
 def build_workload(name):
-    import helpers
-    arch = getattr(helpers, WORKLOADS[name][0])
+    from dcb200 import configs
+    arch = getattr(configs, WORKLOADS[name][0])
     _, classes, T, gflop, ipg = WORKLOADS[name]
     S = arch["sample_size"]
-    cfg = helpers.base_cfg(classes=classes, evaluation_per_stage=[T], n_stages=1, n_keep_per_stage=[1], noise_d=S,
+    cfg = configs.classify_config(classes=classes, evaluation_per_stage=[T], n_stages=1, n_keep_per_stage=[1], noise_d=S,
                            image_size=S, schedule="cosine", pred_param="eps")
     if name == "dit":
         cfg.encoder_type = "DiT"
@@ -316,24 +316,37 @@ def run_ours(args):
     peaks, peak_src = measured_peaks()
     peak = peaks["bf16_tflops_sustained"]
     passes = min(2, args.steps)
-    executed = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
-    # algorithmic FLOPs (the reference graph's convs / linears for the evals of one pass) over the time these launches take
-    achieved = ref_flops * passes / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+    # the dominant kernel on the FLOPs its launches EXECUTE (2 M N K of every tcgen05 GEMM launch of the instrumented
+    # passes) over their summed CUDA-event durations: this is the roofline fraction
+    achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+    # the same launch time against the REFERENCE graph's conv / linear FLOPs (per-class prefix recomputed,
+    # Upsample2D unfolded): an effective rate that credits the exact work-saving rewrites -- never a fraction of peak
+    algorithmic = ref_flops * passes / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+    gn_ms, gn_bytes, n_gn = prof.gn_totals()
+    hbm_peak = peaks["hbm_gbs"]
+    gn_gbs = gn_bytes / (gn_ms / 1e3) / 1e9 if gn_ms > 0 else 0.0
     roofline = {
         "bound": "tensor", "kernel": "gemm_tc_kernel + gemm_tc2_kernel (tcgen05 implicit GEMM)", "achieved": achieved,
         "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
         "peak_source": f"{peak_src} bf16_tflops_sustained",
-        "achieved_basis": "FLOPs of the reference graph's convs/linears (SURVEY 8d algorithmic work: per-class prefix, "
-                          "unfolded Upsample2D) / summed CUDA-event durations of the tcgen05 GEMM launches",
-        # the same launches on the FLOPs they actually execute (shared class-independent prefix, folded upsample)
-        "achieved_executed": executed, "frac_executed": executed / peak,
+        "achieved_basis": "executed FLOPs (2 M N K of every tcgen05 GEMM launch) / summed CUDA-event durations of those "
+                          "launches, eager launches on the bench workload",
+        "effective_tflops_on_reference_graph": algorithmic,
+        "effective_speedup_vs_reference_flops": (ref_flops * passes) / gemm_flops if gemm_flops else None,
         "launches_per_step": n_gemm // passes, "avg_launch_ms": gemm_ms / max(n_gemm, 1),
         "kernel_share_of_step": (gemm_ms / passes) / (ms / args.steps),
         "executed_gflop_per_eval": gemm_flops / passes / (evals_per_step / world) / 1e9,
-        "algorithmic_gemm_gflop_per_eval": ref_flops / (evals_per_step / world) / 1e9,
+        "reference_graph_gemm_gflop_per_eval": ref_flops / (evals_per_step / world) / 1e9,
         "reference_gflop_per_eval": gflop,
-        "whole_step_frac_of_peak_executed": (gemm_flops / passes) / (ms / args.steps / 1e3) / 1e12 / peak,
-        "whole_step_frac_of_peak": gflop * 1e9 * (evals_per_step / world) / (ms / args.steps / 1e3) / 1e12 / peak,
+        "whole_step_frac_of_peak": (gemm_flops / passes) / (ms / args.steps / 1e3) / 1e12 / peak,
+        "whole_step_frac_of_peak_on_reference_flops":
+            gflop * 1e9 * (evals_per_step / world) / (ms / args.steps / 1e3) / 1e12 / peak,
+        # second kernel by share of the step: the streaming GroupNorm(+SiLU) apply pass, HBM bound
+        "secondary": None if n_gn == 0 else {
+            "kernel": "gn_apply_kernel (GroupNorm + SiLU apply, streaming)", "bound": "hbm", "achieved": gn_gbs,
+            "peak": hbm_peak, "unit": "GB/s", "frac": gn_gbs / hbm_peak, "peak_source": f"{peak_src} hbm_gbs",
+            "achieved_basis": "one read + one write of every normalised tensor / summed CUDA-event durations",
+            "launches_per_step": n_gn // passes, "kernel_share_of_step": (gn_ms / passes) / (ms / args.steps)},
     }
     tr = os.path.join(ROOT, "profiles", "r01_traffic.json")   # per-launch DRAM bytes of the dominant kernel from the
     if os.path.exists(tr):                                     # committed `ncu --set full` capture (same workload)

@@ -41,6 +41,8 @@ _PROTOS = {
     "dcb_last_error": (C.c_char_p, []),
     "dcb_launch_count": (c_i64, []),
     "dcb_note_graph_replay": (None, [c_i64]),
+    "dcb_set_knobs": (None, [C.c_uint32]),
+    "dcb_get_knobs": (C.c_uint32, []),
     "dcb_prologue": (c_int, [c_int, c_int, c_void_p, c_void_p, c_u64, c_i64, c_void_p, c_void_p, c_void_p, c_int, c_int,
                              c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "dcb_ddpm_step": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_u64, c_i64, c_int,
@@ -82,6 +84,11 @@ _PROTOS = {
 EXPORTS = tuple(_PROTOS)
 _lib = None
 
+# DCB_KNOB_* of include/dcb200.h.  The environment variables of the same name (DCB_NO_TC2=1 ...) are read ONCE, when the
+# library is loaded; tests switch at run time with ``knob()``.
+KNOBS = {"NO_TC2": 1, "TC2_NO_HALO": 2, "TC2_NO_YHALO": 4, "NO_TC2_MSE": 8, "TC2_WIDE": 16, "TC_DIRECT_EPILOGUE": 32,
+         "ATTN_NO_TC": 64, "ATTN_NO_FAST": 128}
+
 
 class DcbError(RuntimeError):
     pass
@@ -101,8 +108,31 @@ def lib():
             fn.restype, fn.argtypes = res, args
         if L.dcb_struct_size(0) != C.sizeof(Seg) or L.dcb_struct_size(1) != C.sizeof(GemmDesc):
             raise ImportError("dcb200: ctypes struct layout does not match libdcb200.so (rebuild the extension)")
+        mask = 0
+        for name, bit in KNOBS.items():
+            if os.environ.get("DCB_" + name, "0") not in ("", "0"):
+                mask |= bit
+        L.dcb_set_knobs(mask)
         _lib = L
     return _lib
+
+
+class knob:
+    """``with knob("NO_TC2", "TC2_NO_YHALO"): ...`` -- run the enclosed launches on an alternative (bit-identical) kernel."""
+
+    def __init__(self, *names):
+        self.mask = 0
+        for n in names:
+            self.mask |= KNOBS[n]
+
+    def __enter__(self):
+        self.old = lib().dcb_get_knobs()
+        lib().dcb_set_knobs(self.old | self.mask)
+        return self
+
+    def __exit__(self, *exc):
+        lib().dcb_set_knobs(self.old)
+        return False
 
 
 def check(rc, what=""):

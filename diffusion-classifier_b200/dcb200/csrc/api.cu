@@ -10,6 +10,8 @@ namespace dcb {
 
 static thread_local char g_err[512] = "";
 static std::atomic<int64_t> g_launches{0};
+static std::atomic<uint32_t> g_knobs{0};
+uint32_t knobs() { return g_knobs.load(std::memory_order_relaxed); }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -89,6 +91,9 @@ extern "C" int dcb_version(void) { return 100; }
 extern "C" const char* dcb_last_error(void) { return g_err; }
 extern "C" int64_t dcb_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 extern "C" void dcb_note_graph_replay(int64_t n_kernels) { g_launches.fetch_add(n_kernels, std::memory_order_relaxed); }
+
+extern "C" void dcb_set_knobs(uint32_t mask) { g_knobs.store(mask, std::memory_order_relaxed); }
+extern "C" uint32_t dcb_get_knobs(void) { return knobs(); }
 
 extern "C" int dcb_struct_size(int which) { return which == 0 ? (int)sizeof(dcb_seg) : (int)sizeof(dcb_gemm_desc); }
 

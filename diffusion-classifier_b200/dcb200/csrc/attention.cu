@@ -295,7 +295,7 @@ extern "C" int dcb_attention_ws(int dtype, const void* q, const void* k, const v
                 "attention: bf16 path needs 16-byte aligned rows");
     // head dim 64 with at least one full key block: tcgen05 / TMEM kernel (attention_tc.cu); the mma.sync kernel keeps
     // the small-N / other-head-dim cases (d = 32, 96, 128 are a few per cent of the U-Net configs' FLOPs)
-    static const bool tc_on = !(getenv("DCB_ATTN_TC") && atoi(getenv("DCB_ATTN_TC")) == 0);
+    const bool tc_on = !(knobs() & DCB_KNOB_ATTN_NO_TC);
     if (d == 64 && Ntok >= 128 && tc_on && out_ld % 8 == 0 && ((uintptr_t)out & 15) == 0)
       return launch_flash_tc(q, k, v, ld, B, Ntok, heads, scale, out, out_ld, ws, st);
     DCB_ATTN_DISPATCH(launch_flash, )

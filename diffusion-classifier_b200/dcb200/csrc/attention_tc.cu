@@ -674,7 +674,7 @@ int launch_flash_tc(const void* q, const void* k, const void* v, int ld, int B, 
   p.nblk = (N + 127) / 128;
   p.sc = scale * 1.4426950408889634f;
   p.out_ld = out_ld;
-  static const bool fast_on = !(getenv("DCB_ATTN_FAST") && atoi(getenv("DCB_ATTN_FAST")) == 0);
+  const bool fast_on = !(knobs() & DCB_KNOB_ATTN_NO_FAST);
   const bool use_fast = norms_ws != nullptr && fast_on && N >= 1024;   // short sequences: two extra launches do not pay
   p.norms = use_fast ? norms_ws : nullptr;
   const size_t smem = 1024 + (2 + 2 * AT_KV_STAGES) * AT_TILE_BYTES + 256 + 2048;

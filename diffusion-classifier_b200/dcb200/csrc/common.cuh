@@ -13,6 +13,9 @@ namespace dcb {
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 int num_sms();
+// kernel-selection switches for A/B parity tests (dcb_set_knobs; include/dcb200.h DCB_KNOB_*): one relaxed atomic load per
+// launch instead of getenv() calls on the launch path
+uint32_t knobs();
 
 #define DCB_REQUIRE(cond, ...)            \
   do {                                    \

@@ -340,7 +340,7 @@ static int choose_geometry(const GemmDev& g, TcGeom* t) {
 // bf16 outputs with <= 128 output columns per tile (BN <= 128, or GEGLU's 256 -> 128); 16-byte aligned rows
 static bool staged_for(const GemmDev& g, const TcGeom& t) {
   const EpiDev& e = g.epi;
-  if (getenv("DCB_TC_DIRECT_EPILOGUE")) return false;
+  if (knobs() & DCB_KNOB_TC_DIRECT_EPILOGUE) return false;
   return e.out != nullptr && e.out_dtype == DCB_BF16 && e.mse_part == nullptr && e.n_out % 8 == 0 && e.out_ld % 8 == 0 &&
          ((uintptr_t)e.out % 16) == 0 && (t.BN <= 128 || e.act == DCB_ACT_GEGLU) &&
          (e.residual == nullptr || (e.res_dtype == DCB_BF16 && e.res_ld % 8 == 0 && ((uintptr_t)e.residual % 16) == 0));
@@ -473,7 +473,7 @@ int launch_gemm_tc(const GemmDev& g, cudaStream_t st) {
   }
   // big N<=128-wide problems: 256-pixel CTAs with split A/B rings (+ x-halo reuse for 3x3 convs), see gemm_tc2.cu
   // wide mode of gemm_tc2 (256 x 256 CTA tiles: a third less L2 -> SMEM operand traffic per FLOP for the K <= 3072
-  // projections) -- EXPERIMENT, opt-in with DCB_TC2_WIDE=1.  Measured on B200 (M = 204800): K=N=768 438 vs 950 TF/s,
+  // projections) -- EXPERIMENT, opt-in with DCB_KNOB_TC2_WIDE.  Measured on B200 (M = 204800): K=N=768 438 vs 950 TF/s,
   // N=2304 451 vs 1005, K=3072/N=768 952 vs 1138, K=512/N=1536 310 vs 614: with both 128 x 256 accumulators filling TMEM
   // there is no second accumulator stage, and the thread-per-row direct epilogue (~10k cycles per tile) serialises with
   // the MMAs.  It needs a coalesced epilogue and cta_group::2 (256 columns per CTA) to pay; kept bit-identical to the
@@ -481,7 +481,7 @@ int launch_gemm_tc(const GemmDev& g, cudaStream_t st) {
   {
     const int m_tiles = t.tiles_x * t.tiles_y * t.tiles_nb;
     const EpiDev& e = g.epi;
-    const bool wide = getenv("DCB_TC2_WIDE") && !getenv("DCB_NO_TC2") && e.N % 256 == 0 && e.N >= 512 && g.K >= 512 &&
+    const bool wide = (knobs() & DCB_KNOB_TC2_WIDE) && !(knobs() & DCB_KNOB_NO_TC2) && e.N % 256 == 0 && e.N >= 512 && g.K >= 512 &&
                       e.act != DCB_ACT_GEGLU && e.gn_part == nullptr && e.mse_part == nullptr && e.out != nullptr &&
                       e.out_dtype == DCB_BF16 && e.out_ld % 8 == 0 && ((uintptr_t)e.out % 16) == 0 && !is_conv9(g) &&
                       t.bn == 1 && (m_tiles / 2) * (e.N / 256) >= 2 * num_sms();
@@ -493,8 +493,8 @@ int launch_gemm_tc(const GemmDev& g, cudaStream_t st) {
   // (also the fused eps-MSE of conv_out -- N = out_channels, nothing stored: with 9 separately loaded taps it is bound by
   //  L2->SMEM traffic, the x-halo boxes cut that 3x)
   const bool mse_only = g.epi.mse_part != nullptr && g.epi.out == nullptr && g.epi.residual == nullptr && t.bn == 1 &&
-                        (g.OH * g.OW) % TC_BM == 0 && !getenv("DCB_NO_TC2_MSE");
-  if ((p.staged || mse_only) && t.BN <= 128 && g.epi.act != DCB_ACT_GEGLU && !getenv("DCB_NO_TC2") &&
+                        (g.OH * g.OW) % TC_BM == 0 && !(knobs() & DCB_KNOB_NO_TC2_MSE);
+  if ((p.staged || mse_only) && t.BN <= 128 && g.epi.act != DCB_ACT_GEGLU && !(knobs() & DCB_KNOB_NO_TC2) &&
       t.tiles_x * t.tiles_y * t.tiles_nb * t.n_tiles >= 4 * num_sms()) {
     rc = launch_gemm_tc2(g, st, t.bw, t.bh, t.bn, t.tiles_x, t.tiles_y, t.tiles_nb, t.BN, p.uniform, p.staged);
     if (rc != DCB_EUNSUPPORTED) return rc;

@@ -102,6 +102,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int first_tap_seg = p.halo ? 9 : 0;
+  // issue-loop experiments (tools/gemm_micro.py, profiles/r01_mma_issue_probes.txt) exist only in -DDCB_PROBES builds:
+  // the product kernel carries none of their branches
+#ifdef DCB_PROBES
+  const int dbg = p.dbg;
+#else
+  constexpr int dbg = 0;
+#endif
 
   const uint32_t a_ring0 = smem_u32(a_ring), b_ring0 = smem_u32(b_ring);
   const uint32_t a_full0 = smem_u32(a_full), a_empty0 = smem_u32(a_empty);
@@ -110,12 +117,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
     // ===================== TMA producer (warp-uniform bookkeeping, one elected lane issues) =====================
     int ai = 0, bi = 0;
     uint32_t aph = 0, bph = 0;
-    const bool no_tma = (p.dbg & 1) != 0;
-    for (int tile = blockIdx.x; tile < ((p.dbg & 8) ? 0 : p.total_tiles); tile += gridDim.x) {
+    const bool no_tma = (dbg & 1) != 0;
+    for (int tile = blockIdx.x; tile < ((dbg & 8) ? 0 : p.total_tiles); tile += gridDim.x) {
       const int tn = tile % p.n_tiles, tp = tile / p.n_tiles;
       const SubTile s0 = decode_sub(p, 2 * tp), s1 = decode_sub(p, 2 * tp + 1);
       auto load_b = [&](int kb_glob) {
-        if (p.dbg & 64) mbar_spin(b_empty0 + bi * 8, bph ^ 1); else mbar_wait(b_empty0 + bi * 8, bph ^ 1);
+        if (dbg & 64) mbar_spin(b_empty0 + bi * 8, bph ^ 1); else mbar_wait(b_empty0 + bi * 8, bph ^ 1);
         if (elect_one()) {
           const uint32_t fb = b_full0 + bi * 8;
           if (no_tma) mbar_arrive(fb);
@@ -148,7 +155,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
         const int h0 = p.halo_div > 1 ? s0.nb0 / p.halo_div : s0.nb0, h1 = p.halo_div > 1 ? s1.nb0 / p.halo_div : s1.nb0;
         for (int ky = 0; ky < 3; ++ky)
           for (int kb = 0; kb < p.nkb_conv; ++kb) {
-            if (p.dbg & 64) mbar_spin(a_empty0 + ai * 8, aph ^ 1); else mbar_wait(a_empty0 + ai * 8, aph ^ 1);
+            if (dbg & 64) mbar_spin(a_empty0 + ai * 8, aph ^ 1); else mbar_wait(a_empty0 + ai * 8, aph ^ 1);
             if (elect_one()) {
               const uint32_t fa = a_full0 + ai * 8;
               const uint32_t sa = a_ring0 + (uint32_t)(ai * p.a_slot_bytes);
@@ -215,9 +222,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
     for (int s = first_tap_seg; s < p.nseg; ++s) tap_items += p.seg[s].nkb;
     const int items = halo_items + tap_items;
     const uint32_t desc_hi = (uint32_t)(make_kmajor_sw128_desc(0) >> 32);
-    const bool no_mma = (p.dbg & 4) != 0;
-    const bool no_ring = (p.dbg & 8) != 0;   // experiment: no smem-ring handshakes at all (pure MMA issue + tile handshake)
-    const bool prof = (p.dbg & 128) != 0;    // experiment: cycle accounting of this warp's waits (block 0 prints)
+    const bool no_mma = (dbg & 4) != 0;
+    const bool no_ring = (dbg & 8) != 0;   // experiment: no smem-ring handshakes at all (pure MMA issue + tile handshake)
+    const bool prof = (dbg & 128) != 0;    // experiment: cycle accounting of this warp's waits (block 0 prints)
     long long w_te = 0, w_a = 0, w_b = 0, w_iss = 0, w_com = 0, t_all = prof ? clock64() : 0;
     // running descriptor words / barrier addresses of the current slots (no multiplications in the K loop)
     const uint32_t a_step = (uint32_t)p.a_slot_bytes >> 4, b_step = (uint32_t)b_bytes >> 4;
@@ -254,7 +261,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
             }
             const long long c_i1 = prof ? clock64() : 0;
             if (prof) w_iss += c_i1 - c_i0;
-            if (p.dbg & 32) {          // experiment: release the slots at ISSUE time (plain arrive), not at MMA completion
+            if (dbg & 32) {          // experiment: release the slots at ISSUE time (plain arrive), not at MMA completion
               mbar_arrive(b_eb);
               if (last_j) mbar_arrive(a_eb);
             } else if (!no_ring) {
@@ -288,7 +295,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
     for (int tile = blockIdx.x, it = 0; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int tn = tile % p.n_tiles, tp = tile / p.n_tiles;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.acc_stage_cols + grp * p.acc_sub_cols);
-      if (p.dbg & 2) {
+      if (dbg & 2) {
         mbar_wait(smem_u32(&tfull_bar[as * 2 + grp]), aphase);
         tc_fence_after();
         tc_fence_before();
@@ -396,13 +403,14 @@ int launch_gemm_tc2(const GemmDev& g, cudaStream_t st, int bw, int bh, int bn, i
   p.uniform = uniform;
   // measured on B200: the UMMA 128B swizzle is a pure function of the absolute smem address, so an operand that
   // starts j rows into a 1024-B-aligned swizzled box needs base_offset = 0 (setting it per the "(addr>>7)&7" rule breaks)
-  static const int base_off_env = getenv("DCB_TC2_BASE_OFFSET") ? atoi(getenv("DCB_TC2_BASE_OFFSET")) : 0;
-  p.base_off_mode = base_off_env;
+  p.base_off_mode = 0;
+#ifdef DCB_PROBES
   p.dbg = getenv("DCB_TC2_DBG") ? atoi(getenv("DCB_TC2_DBG")) : 0;
+#endif
   p.nseg = g.nseg;
 
   // x-halo mode: the first 9 segments are a stride-1 3x3 conv over one source in (ky,kx) order, full 128-px rows
-  bool halo = g.nseg >= 9 && bw == 128 && bh == 1 && bn == 1 && g.OW % 128 == 0 && !getenv("DCB_TC2_NO_HALO");
+  bool halo = g.nseg >= 9 && bw == 128 && bh == 1 && bn == 1 && g.OW % 128 == 0 && !(knobs() & DCB_KNOB_TC2_NO_HALO);
   for (int i = 0; halo && i < 9; ++i) {
     const SegDev& s = g.seg[i];
     halo = s.src == g.seg[0].src && s.C == g.seg[0].C && s.H == g.OH && s.W == g.OW && s.stride == 1 && s.c_off == 0 &&
@@ -411,7 +419,7 @@ int launch_gemm_tc2(const GemmDev& g, cudaStream_t st, int bw, int bh, int bn, i
   for (int i = 9; halo && i < g.nseg; ++i) halo = g.seg[i].src != g.seg[0].src;
   // y-halo mode: rows narrower than a tile (a sub-tile = bh full rows of one sample), sub-tile pairs stacked vertically
   bool yhalo = !halo && g.nseg >= 9 && g.OW < 128 && bw == g.OW && bn == 1 && tiles_x == 1 && tiles_y % 2 == 0 &&
-               bh * bw == TC_BM && !getenv("DCB_TC2_NO_YHALO");
+               bh * bw == TC_BM && !(knobs() & DCB_KNOB_TC2_NO_YHALO);
   for (int i = 0; yhalo && i < 9; ++i) {
     const SegDev& s = g.seg[i];
     yhalo = s.src == g.seg[0].src && s.C == g.seg[0].C && s.H == g.OH && s.W == g.OW && s.stride == 1 && s.c_off == 0 &&
@@ -502,11 +510,16 @@ int launch_gemm_tc2(const GemmDev& g, cudaStream_t st, int bw, int bh, int bn, i
     const int score = a * kb_per_a < b ? a * kb_per_a : b;
     if (score > best_score) { best_score = score; best_a = a; }
   }
-  p.a_slots = getenv("DCB_TC2_ASLOTS") ? atoi(getenv("DCB_TC2_ASLOTS")) : best_a;
+  p.a_slots = best_a;
+#ifdef DCB_PROBES
+  if (getenv("DCB_TC2_ASLOTS")) p.a_slots = atoi(getenv("DCB_TC2_ASLOTS"));
+#endif
   const int fixed = 1024 + 512 + epi_bytes + p.a_slots * p.a_slot_bytes;
   int b_slots = (TC_SMEM_LIMIT - fixed) / b_bytes;
   if (b_slots > T2_MAX_SLOTS) b_slots = T2_MAX_SLOTS;
+#ifdef DCB_PROBES
   if (getenv("DCB_TC2_BSLOTS") && atoi(getenv("DCB_TC2_BSLOTS")) < b_slots) b_slots = atoi(getenv("DCB_TC2_BSLOTS"));
+#endif
   if (b_slots < 3) return DCB_EUNSUPPORTED;
   p.b_slots = b_slots;
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);

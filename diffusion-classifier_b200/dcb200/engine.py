@@ -38,7 +38,12 @@ class GemmProfile:
     """bench.py's roofline probe: CUDA-event pairs around every tcgen05 GEMM launch + its algorithmic FLOPs."""
 
     def __init__(self):
-        self.rows = []  # (start_event, end_event, flops, tag)
+        self.rows = []     # (start_event, end_event, flops, tag)
+        self.gn_rows = []  # (start_event, end_event, algorithmic bytes) of every streaming GroupNorm-apply launch
+
+    def gn_totals(self):
+        torch.cuda.synchronize()
+        return sum(a.elapsed_time(b) for a, b, _ in self.gn_rows), sum(f for _, _, f in self.gn_rows), len(self.gn_rows)
 
     def totals(self):
         torch.cuda.synchronize()
@@ -233,9 +238,16 @@ def groupnorm(ctx, x0, C0, x1, C1, NB, HW, gamma, beta, eps, silu, G=32, div0=1,
         part = torch.empty(NB * chunks * G * 2, device=ctx.device, dtype=torch.float32)
         L.check(lib.dcb_groupnorm_stats_div(ctx.code, x0.data_ptr(), C0, div0, _p(x1), C1, div1, NB, HW, G, chunks,
                                             part.data_ptr(), ctx.stream()), "groupnorm_stats")
+    prof = PROFILE if (PROFILE is not None and ctx.code == L.BF16) else None
+    if prof is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     L.check(lib.dcb_groupnorm_apply_div(ctx.code, x0.data_ptr(), C0, div0, _p(x1), C1, div1, NB, HW, G, chunks,
                                         part.data_ptr(), gamma.data_ptr(), beta.data_ptr(), eps, int(silu),
                                         out.data_ptr(), ctx.stream()), "groupnorm_apply")
+    if prof is not None:
+        e1.record()     # algorithmic bytes: one read + one write of the normalised tensor
+        prof.gn_rows.append((e0, e1, 2.0 * NB * HW * (C0 + C1) * out.element_size()))
     return out
 
 

@@ -36,6 +36,21 @@ int64_t dcb_launch_count(void);
 /* the host replayed a CUDA graph that holds n_kernels of this library's launches (keeps dcb_launch_count honest) */
 void dcb_note_graph_replay(int64_t n_kernels);
 
+/* kernel-selection switches used by the A/B parity tests (every alternative computes bit-identical results; the default,
+ * mask 0, is the product path).  Process-wide; takes effect from the next launch. */
+enum {
+  DCB_KNOB_NO_TC2 = 1,              /* 256-pixel CTA kernel (gemm_tc2) off: everything runs on gemm_tc_kernel */
+  DCB_KNOB_TC2_NO_HALO = 2,         /* gemm_tc2 without x-halo boxes (nine separately loaded taps) */
+  DCB_KNOB_TC2_NO_YHALO = 4,        /* gemm_tc2 without y-halo boxes */
+  DCB_KNOB_NO_TC2_MSE = 8,          /* fused eps-MSE of conv_out on gemm_tc_kernel */
+  DCB_KNOB_TC2_WIDE = 16,           /* experimental single-CTA 256 x 256 tiles (measured slower; kept as an A/B) */
+  DCB_KNOB_TC_DIRECT_EPILOGUE = 32, /* thread-per-row epilogue instead of the staged (coalesced) one */
+  DCB_KNOB_ATTN_NO_TC = 64,         /* head-dim-64 attention on the mma.sync kernel */
+  DCB_KNOB_ATTN_NO_FAST = 128       /* tcgen05 attention always with the running maximum (no single-pass kernel) */
+};
+void dcb_set_knobs(uint32_t mask);
+uint32_t dcb_get_knobs(void);
+
 /* ---- (1) prologue: q_sample fused with the denoiser's input staging ------------------------------------
  * replaces DiffusionClassifier.diffuse (diffusion_classifier.py:100-117) + the first-layer unfold:
  *   eps = predrawn[u] or Philox(seed, unit_id0+u);  z = alpha[u]*x[img[u]] + sigma[u]*eps

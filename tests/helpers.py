@@ -16,66 +16,15 @@ SMALL_UNET = dict(
     up_block_types=("UpBlock2D", "CrossAttnUpBlock2D", "UpBlock2D"), mid_block_type="UNetMidBlock2DCrossAttn",
     encoder_hid_dim=128, encoder_hid_dim_type="text_proj", cross_attention_dim=128)
 
-CIFAR_UNET = dict(
-    sample_size=32, in_channels=3, out_channels=3, layers_per_block=2, block_out_channels=(128, 128, 256, 512),
-    down_block_types=("DownBlock2D", "DownBlock2D", "CrossAttnDownBlock2D", "CrossAttnDownBlock2D"),
-    up_block_types=("CrossAttnUpBlock2D", "CrossAttnUpBlock2D", "UpBlock2D", "UpBlock2D"),
-    mid_block_type="UNetMidBlock2DCrossAttn", encoder_hid_dim=128, encoder_hid_dim_type="text_proj",
-    cross_attention_dim=128)
-
-UNET128 = dict(
-    sample_size=128, in_channels=3, out_channels=3, layers_per_block=2, block_out_channels=(128, 128, 256, 512, 1024),
-    down_block_types=("DownBlock2D", "DownBlock2D", "DownBlock2D", "CrossAttnDownBlock2D", "DownBlock2D"),
-    up_block_types=("UpBlock2D", "CrossAttnUpBlock2D", "UpBlock2D", "UpBlock2D", "UpBlock2D"),
-    mid_block_type="UNetMidBlock2DCrossAttn", encoder_hid_dim=512, encoder_hid_dim_type="text_proj",
-    cross_attention_dim=512)
-
-UNET256 = dict(
-    sample_size=256, in_channels=3, out_channels=3, layers_per_block=2,
-    block_out_channels=(128, 128, 256, 256, 512, 1024),
-    down_block_types=("DownBlock2D", "DownBlock2D", "DownBlock2D", "DownBlock2D", "CrossAttnDownBlock2D", "DownBlock2D"),
-    up_block_types=("UpBlock2D", "CrossAttnUpBlock2D", "UpBlock2D", "UpBlock2D", "UpBlock2D", "UpBlock2D"),
-    mid_block_type="UNetMidBlock2DCrossAttn", encoder_hid_dim=512, encoder_hid_dim_type="text_proj",
-    cross_attention_dim=512)
-
-IPMSA5_DWT_UNET = dict(
-    sample_size=128, in_channels=40, out_channels=40, layers_per_block=(2, 2, 2, 4, 2),
-    block_out_channels=(128, 128, 256, 512, 768),
-    down_block_types=("DownBlock2D", "DownBlock2D", "DownBlock2D", "CrossAttnDownBlock2D", "DownBlock2D"),
-    up_block_types=("UpBlock2D", "CrossAttnUpBlock2D", "UpBlock2D", "UpBlock2D", "UpBlock2D"),
-    mid_block_type="UNetMidBlock2DCrossAttn", encoder_hid_dim=512, encoder_hid_dim_type="text_proj",
-    cross_attention_dim=512)
-
-DIT_B4_256 = dict(num_attention_heads=12, attention_head_dim=64, in_channels=3, out_channels=3, num_layers=12,
-                  dropout=0.0, norm_num_groups=32, attention_bias=True, sample_size=256, patch_size=4,
-                  activation_fn="gelu-approximate", num_embeds_ada_norm=1000, upcast_attention=False,
-                  norm_type="ada_norm_zero", norm_elementwise_affine=False, norm_eps=1e-5)
+# the BASELINE.json architectures live in the product (bench.py builds its workloads from them)
+from dcb200.configs import CIFAR_UNET, DIT_B4_256, IPMSA5_DWT_UNET, UNET128, UNET256  # noqa: E402,F401
 
 TINY_DIT = dict(num_attention_heads=2, attention_head_dim=64, in_channels=3, out_channels=3, num_layers=2,
                 sample_size=32, patch_size=2, norm_eps=1e-5)
 
 
-class Cfg:
-    """Duck-typed config like the experiments' (missing keys read None; dunders raise so deepcopy works)."""
-
-    def __init__(self, **kw):
-        self.__dict__["_d"] = dict(kw)
-
-    def __getattr__(self, name):
-        if name.startswith("__"):
-            raise AttributeError(name)
-        return self.__dict__["_d"].get(name)
-
-    def __setattr__(self, name, value):
-        self.__dict__["_d"][name] = value
-
-
-def base_cfg(**kw):
-    d = dict(pred_param="eps", schedule="cosine", noise_d=32, image_size=32, cfg_w=0.0, ema_beta=0.999, ema_warmup=0,
-             ema_update_freq=1, encoder_type="nn", classes=4, n_stages=1, evaluation_per_stage=[4],
-             n_keep_per_stage=[1], n_fast_classes=2, fast_classification=False)
-    d.update(kw)
-    return Cfg(**d)
+from dcb200.configs import Config as Cfg  # noqa: E402  (duck-typed config like the experiments')
+from dcb200.configs import classify_config as base_cfg  # noqa: E402,F401
 
 
 def rel_err(a, b):

@@ -272,12 +272,54 @@ def test_ema_shim_contract():
     e = dcb200.EMA(m, beta=0.5, update_after_step=0, update_every=1)
     assert set(e.state_dict()) == {"initted", "step", "online_model.weight", "online_model.bias", "ema_model.weight",
                                    "ema_model.bias"}
-    e.update()
-    with torch.no_grad():
-        m.weight.add_(1.0)
-    e.update()
-    assert torch.allclose(e.ema_model.weight, m.weight - 0.5)
     assert torch.equal(e(torch.ones(1, 4)), e.ema_model(torch.ones(1, 4)))
+
+
+def test_ema_update_schedule():
+    """ema_pytorch 0.7.7's update(): copies (without setting ``initted``) while step <= update_after_step, first
+    post-warm-up call copies + sets initted, then lerps with decay = clamp(1 - (1 + epoch) ** (-2/3), min_value, beta),
+    epoch = step_after_increment - update_after_step - 1; update_every gates everything; float buffers are averaged,
+    integer buffers are not.  Hand-derived values (inv_gamma = 1, power = 2/3)."""
+    import dcb200
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.zeros(3))
+            self.register_buffer("fb", torch.zeros(2))
+            self.register_buffer("ib", torch.zeros(2, dtype=torch.long))
+
+    m = Net()
+    e = dcb200.EMA(m, beta=0.9, update_after_step=2, update_every=1)
+
+    def bump():
+        with torch.no_grad():
+            m.w.add_(1.0)
+            m.fb.add_(2.0)
+            m.ib.add_(1)
+
+    for k in range(3):                      # steps 0, 1, 2: plain copies, still not initted
+        bump()
+        e.update()
+        assert torch.equal(e.ema_model.w, m.w) and torch.equal(e.ema_model.fb, m.fb) and not bool(e.initted)
+    bump()
+    e.update()                              # step 3: first real update -> copy, initted, lerp of equal tensors
+    assert bool(e.initted) and torch.equal(e.ema_model.w, m.w) and int(e.step) == 4
+    assert abs(e.get_current_decay() - (1 - 2 ** (-2 / 3))) < 1e-12
+    bump()
+    e.update()                              # step 4: epoch = 5 - 2 - 1 = 2 -> decay = 1 - 3^(-2/3) = 0.5192499
+    d = 1 - 3 ** (-2 / 3)
+    assert torch.allclose(e.ema_model.w, m.w - 1.0 + (1 - d), atol=1e-6)
+    assert torch.allclose(e.ema_model.fb, m.fb - 2.0 + 2 * (1 - d), atol=1e-6)
+    assert torch.equal(e.ema_model.ib, torch.zeros(2, dtype=torch.long))      # integer buffers are never touched
+    # decay is capped by beta and floored by min_value; update_every skips the steps in between
+    e2 = dcb200.EMA(Net(), beta=0.4, update_after_step=0, update_every=3, min_value=0.39)
+    for _ in range(4):
+        e2.update()                         # steps 0 (copy), 1, 2 (skipped), 3 (init + lerp)
+    assert bool(e2.initted) and int(e2.step) == 4
+    assert 0.39 <= e2.get_current_decay() <= 0.4
+    e2.step.fill_(1000)
+    assert e2.get_current_decay() == 0.4
 
 
 def _gloo_worker(rank, world, port, out):

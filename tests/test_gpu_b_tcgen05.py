@@ -352,7 +352,7 @@ def test_tc2_halo_fused_mse_is_bit_identical_to_tap_kernel(dev, S, div, H, W, Ci
     """conv_out at full resolution runs in gemm_tc2 (x-halo boxes, direct eps-MSE epilogue): same K-block order and the
     same summation order as gemm_tc_kernel with nine separately loaded taps => bit-identical per-sample errors; both
     equal the torch fp32 reduction of the written prediction."""
-    import os
+    from dcb200 import _lib as L
     from dcb200 import engine as E
     torch.manual_seed(0)
     a = _bf(S, H, W, Ci, dev=dev)
@@ -370,11 +370,8 @@ def test_tc2_halo_fused_mse_is_bit_identical_to_tap_kernel(dev, S, div, H, W, Ci
         return err
 
     e_halo = run()
-    os.environ["DCB_NO_TC2_MSE"] = "1"
-    try:
+    with L.knob("NO_TC2_MSE"):
         e_tap = run()
-    finally:
-        del os.environ["DCB_NO_TC2_MSE"]
     assert torch.equal(e_halo, e_tap)
     pred = conv_ref(a.float(), w.float(), b).reshape(S, H * W, Co)
     ref = ((scale.view(-1, 1, 1) * pred - tgt.repeat_interleave(div, 0)) ** 2).sum((1, 2))
@@ -422,12 +419,9 @@ def test_tc2_yhalo_conv3x3(dev, NB, H, W, Ci, Co, extra):
     assert out.dtype == torch.bfloat16 and rel_err(out, ref) < 5e-3
     simt = E.gemm(_ctx(dev, L.ENGINE_SIMT), segs, wp, Co, NB, H, W, **kw)
     assert rel_err(out, simt.float()) < 1e-3
-    for knob in ("DCB_TC2_NO_YHALO", "DCB_NO_TC2"):
-        os.environ[knob] = "1"
-        try:
+    for knob in ("TC2_NO_YHALO", "NO_TC2"):
+        with L.knob(knob):
             other, st2 = E.gemm(_ctx(dev), segs, wp, Co, NB, H, W, gn_stats=True, **kw)
-        finally:
-            del os.environ[knob]
         assert torch.equal(out, other), knob
         assert torch.equal(st, st2), knob
 
@@ -467,9 +461,6 @@ def test_tc2_wide_256x256_tiles(dev, M, K, N, extra):
     narrow = E.linear(_ctx(dev), x, w, N, **kw)
     assert narrow.dtype == torch.bfloat16 and rel_err(narrow, ref) < 6e-3
     n0 = L.launch_count()
-    os.environ["DCB_TC2_WIDE"] = "1"
-    try:
+    with L.knob("TC2_WIDE"):
         out = E.linear(_ctx(dev), x, w, N, **kw)
-    finally:
-        del os.environ["DCB_TC2_WIDE"]
     assert L.launch_count() == n0 + 1 and torch.equal(out, narrow)

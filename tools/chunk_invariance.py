@@ -6,6 +6,7 @@ for p in (ROOT, os.path.join(ROOT, "diffusion-classifier_b200"), os.path.join(RO
 import torch
 import dcb200
 from dcb200 import engine as E
+from dcb200 import _lib as L
 from helpers import UNET128, base_cfg
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
@@ -37,13 +38,13 @@ for name, env in (("default", {}), ("tile stats off", {"ts": False}), ("fold off
     t = run(0, share=False)
     row.append(f"share off: {'==' if torch.equal(t, b0) else 'DIFF %.1e' % float(((t - b0).abs() / b0).max())}")
     print(f"{name:22s}", "  ".join(row), flush=True)
-for knob in ("DCB_NO_TC2", "DCB_TC2_NO_HALO", "DCB_TC2_NO_YHALO", "DCB_NO_TC2_MSE"):
+for knob in ("NO_TC2", "TC2_NO_HALO", "TC2_NO_YHALO", "NO_TC2_MSE"):
     E.USE_TILE_STATS = E.FOLD_UPSAMPLE = E.USE_FUSED_SMALL_GN = True
-    os.environ[knob] = "1"
+    kn = L.knob(knob); kn.__enter__()
     b0 = run(0)
     row = [f"vs default: {'==' if torch.equal(b0, base) else 'DIFF %.1e' % float(((b0 - base).abs() / base).max())}"]
     for mb in (8, 2):
         t = run(mb)
         row.append(f"mb={mb}: {'==' if torch.equal(t, b0) else 'DIFF %.1e' % float(((t - b0).abs() / b0).max())}")
-    del os.environ[knob]
+    kn.__exit__()
     print(f"{knob:22s}", "  ".join(row), flush=True)
