@@ -19,6 +19,8 @@ SOURCES = ["api.cu", "gemm_tc.cu", "gemm_tc2.cu", "gemm_simt.cu", "norm.cu", "el
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+if os.environ.get("DCB_PROBES"):     # issue-loop experiments of tools/gemm_micro.py / epi_micro.py (never in the product build)
+    FLAGS.append("-DDCB_PROBES")
 
 
 def _stale(src, obj):

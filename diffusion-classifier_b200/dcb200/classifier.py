@@ -51,6 +51,46 @@ def combine_stage_errors(errors, slab, classes, start, end, dist=None):
     return errors
 
 
+def sync_from_rank0(dist, t, dev):
+    """``t`` as rank 0 holds it, on ``dev``.  With ``dcb_shard == 'timestep'`` every rank scores a slice of the SAME
+    (image, timestep, class) table, so everything that defines the table -- the timesteps drawn from the CPU generator
+    (:688), the fast-mode candidate classes (:671-677) and the Philox seed -- must be rank 0's: ranks seeded differently
+    (the usual seed + rank set-up) would otherwise fill different class columns and the all-reduced table would hold
+    zeros where the reference has errors.  (The reference never needed this: accelerate shards images, :613-617.)"""
+    tt = t.to(dev).contiguous()
+    if dist is not None:
+        dist.broadcast(tt, 0)
+    return tt
+
+
+class _GraphCache:
+    """LRU of captured launch sequences keyed by (kind, pack generation, shapes).  Entries of a superseded pack generation of
+    the same network are dropped first (their weights are gone); capacity grows with the number of pruning stages (each
+    stage contributes a full-chunk and a tail-chunk shape) so one classify() call never evicts its own graphs."""
+
+    def __init__(self):
+        import collections
+        self.d = collections.OrderedDict()
+        self.cap = 8
+
+    def get(self, key):
+        v = self.d.get(key)
+        if v is not None:
+            self.d.move_to_end(key)
+        return v
+
+    def put(self, key, value, net_id, gen):
+        for k in [k for k, v in self.d.items() if v["net_id"] == net_id and v["gen"] != gen]:
+            del self.d[k]
+        while len(self.d) >= self.cap:
+            self.d.popitem(last=False)
+        self.d[key] = dict(obj=value, net_id=net_id, gen=gen)
+        return value
+
+    def __len__(self):
+        return len(self.d)
+
+
 class _GraphedDenoiser:
     """One CUDA graph per (network, chunk shape): the ~500 kernel launches of a denoiser pass + fused eps-MSE are
     captured once and replayed; the prologue writes straight into the graph's fixed input buffers.  (CUDA streams and
@@ -68,10 +108,21 @@ class _GraphedDenoiser:
         self.cls = torch.empty(S, device=dev, dtype=torch.int32)
         self.scale = torch.empty(S, device=dev, dtype=torch.float32) if v_param else None
         self.err = torch.empty(S, device=dev, dtype=torch.float32)
-        self.table = None
+        self.table = None          # the graph's OWN copy of the cross-attention table (fixed address for its lifetime)
+        self._table_call = None
         self.graph = None
         self.args = (net, ctx, pk, is_dit, U, nk, H, W, (patch * patch * Cimg) if is_dit else Cimg, fused)
         self.warm = 0
+
+    def set_table(self, tb, call_id):
+        """copy this call's class table into the graph's persistent buffer (once per call)"""
+        if tb is None:
+            return
+        if self.table is None:
+            self.table = torch.empty_like(tb)
+        if self._table_call != call_id:
+            self.table.copy_(tb)
+            self._table_call = call_id
 
     def _run(self):
         net, ctx, pk, is_dit, U, nk, H, W, No, fused = self.args
@@ -135,8 +186,7 @@ class DiffusionClassifier(nn.Module):
             self.null_token = self.config.classes
         self.last_errors = None  # [BS, classes, T] fp32 table of the most recent classify() call
         self._eps_calls = 0
-        self._graphs = {}
-        self._table_buf = None
+        self._graphs = _GraphCache()
 
     # ---- schedule (diffusion_classifier.py:119-161), evaluated exactly as the reference does ------------------
     def logsnr_schedule_cosine(self, t, logsnr_min=-15, logsnr_max=15):
@@ -167,8 +217,18 @@ class DiffusionClassifier(nn.Module):
         if v:
             return int(v)
         # ~16 M pixels of denoiser batch per launch sequence (1024 samples at 128^2: the 8^2 / 16^2 layers then fill all 148
-        # SMs; peak activation footprint ~40 GB of the 180 GB)
-        return int(os.environ.get("DCB_MAX_BATCH", max(1, min(2048, (1 << 24) // (H * W)))))
+        # SMs; peak activation footprint ~40 GB of the 180 GB = ~2.5 KB per pixel of batch), bounded by half of what the
+        # device can still give us (free + cached by torch's allocator).  Results do not depend on the chunk size.
+        want = max(1, min(2048, (1 << 24) // (H * W)))
+        if "DCB_MAX_BATCH" in os.environ:
+            return int(os.environ["DCB_MAX_BATCH"])
+        try:
+            free, _ = torch.cuda.mem_get_info()
+            free += torch.cuda.memory_reserved() - torch.cuda.memory_allocated()
+            want = max(1, min(want, int(0.5 * free / (2560.0 * H * W))))
+        except RuntimeError:
+            pass
+        return want
 
     # ---- the hot path ---------------------------------------------------------------------------------------------
     @torch.no_grad()
@@ -211,12 +271,8 @@ class DiffusionClassifier(nn.Module):
         xin = x.contiguous().float()
         v_param = self.pred_param == 'v'
         table = None
-        if not is_dit:  # collapsed cross-attention bias per class, once per call (persistent buffer: graphs read it)
-            tb = net.cross_attn_table(ctx, pk, E.cast(ctx, self.encoder.weight))
-            if self._table_buf is None or self._table_buf.shape != tb.shape or self._table_buf.device != tb.device:
-                self._table_buf = torch.empty_like(tb)
-            self._table_buf.copy_(tb)
-            table = self._table_buf
+        if not is_dit:  # collapsed cross-attention bias per class, once per call (graphs keep their own copy)
+            table = net.cross_attn_table(ctx, pk, E.cast(ctx, self.encoder.weight))
         use_graph = ctx.precision == "bf16" and getattr(cfg, "dcb_cuda_graph", None) is not False \
             and os.environ.get("DCB_CUDA_GRAPH", "1") != "0"
         patch = net.config.patch_size if is_dit else 1
@@ -225,9 +281,15 @@ class DiffusionClassifier(nn.Module):
         fused = (ctx.precision == "bf16") and rows % 128 == 0 and not getattr(cfg, "dcb_unfused_mse", False)
         eps_mode = getattr(cfg, "dcb_eps", None) or "philox"
         seed = int(torch.initial_seed() & 0x7FFFFFFFFFFFFFFF) + 0x9E3779B9 * self._eps_calls
+        call_id = self._eps_calls
         self._eps_calls += 1
         dist, rank, world = self._dist()
+        if dist is not None:    # one table, scored in slices: every rank uses rank 0's draws (see sync_from_rank0)
+            seed = int(sync_from_rank0(dist, torch.tensor([seed], dtype=torch.int64), dev).item())
+            if fast:
+                classes = sync_from_rank0(dist, classes, dev)
         max_s = self._max_samples(H, W)
+        self._graphs.cap = max(self._graphs.cap, 2 * cfg.n_stages + 6)
 
         for i in range(cfg.n_stages):
             start, end = per_stage[i], per_stage[i + 1]
@@ -237,6 +299,8 @@ class DiffusionClassifier(nn.Module):
                 t_stage = torch.stack([torch.rand(BS) for _ in range(nj)])
             else:
                 t_stage = t_all[start:end].detach().cpu().float()
+            if dist is not None:
+                t_stage = sync_from_rank0(dist, t_stage, dev).cpu()
             logsnr = self.schedule(t_stage).to(dev)                 # [nj, BS]
             alpha = torch.sqrt(torch.sigmoid(logsnr)).reshape(-1).contiguous()
             sigma = torch.sqrt(torch.sigmoid(-logsnr)).reshape(-1).contiguous()
@@ -266,14 +330,12 @@ class DiffusionClassifier(nn.Module):
                            unit_id0=start * BS + u0, alpha=alpha[u0:u0 + U], sigma=sigma[u0:u0 + U], img=img,
                            want_target=True, v_param=v_param)
                 if use_graph:
-                    key = (id(net), id(pk), is_dit, U, nk, Cimg, H, W, v_param, fused, share, str(dev))
-                    gr = self._graphs.get(key)
-                    if gr is None:
-                        if len(self._graphs) >= 6:      # stale shapes / repacked weights: drop old graphs
-                            self._graphs.clear()
-                        gr = self._graphs[key] = _GraphedDenoiser(net, ctx, pk, is_dit, U, nk, Cimg, H, W, patch,
-                                                                  v_param, fused, share)
-                    gr.table = table
+                    key = ("classify", pk.gen, is_dit, U, nk, Cimg, H, W, v_param, fused, share, str(dev))
+                    hit = self._graphs.get(key)
+                    gr = hit["obj"] if hit is not None else self._graphs.put(
+                        key, _GraphedDenoiser(net, ctx, pk, is_dit, U, nk, Cimg, H, W, patch, v_param, fused, share),
+                        id(net), pk.gen)
+                    gr.set_table(table, call_id)
                     E.prologue(ctx, 1 if is_dit else 0, xin, U, 1 if share else nk, Cimg, H, W, pk.kpad_in,
                                a_out=gr.a_in, target_out=gr.target, **pro)
                     gr.logsnr.copy_(logsnr[u0:u0 + U])
@@ -407,15 +469,13 @@ class DiffusionClassifier(nn.Module):
         mode = 1 if is_dit else 0
         rows = (H // patch) * (W // patch)
         if use_graph:   # persistent buffers: a replay reads / writes fixed addresses; z is updated in place
-            key = ("sample", id(net), id(pk), B, rep, Cimg, H, W, v_param, share, str(dev))
-            st = self._graphs.get(key)
-            if st is None:
-                if len(self._graphs) >= 6:
-                    self._graphs.clear()
-                st = self._graphs[key] = dict(
-                    z=torch.empty(B, Cimg, H, W, device=dev), t=torch.empty(B, device=dev), coef=torch.empty(8, device=dev),
-                    a_in=ctx.empty((B if share else B * rep) * rows, pk.kpad_in), table=None, graph=None, warm=0, seed=0,
-                    cls=torch.empty(B * rep, device=dev, dtype=torch.int32))
+            key = ("sample", pk.gen, is_dit, B, rep, Cimg, H, W, v_param, share, str(dev))
+            hit = self._graphs.get(key)
+            st = hit["obj"] if hit is not None else self._graphs.put(key, dict(
+                z=torch.empty(B, Cimg, H, W, device=dev), t=torch.empty(B, device=dev), coef=torch.empty(8, device=dev),
+                a_in=ctx.empty((B if share else B * rep) * rows, pk.kpad_in), table=None, graph=None, warm=0, seed=0,
+                cls=torch.empty(B * rep, device=dev, dtype=torch.int32),
+                pk=pk, net=net), id(net), pk.gen)      # the graph's kernels point into pk's weights: keep them alive
             st["z"].copy_(z)
             if table is not None:
                 if st["table"] is None or st["table"].shape != table.shape:
@@ -502,17 +562,11 @@ class DiffusionClassifier(nn.Module):
         use_graph = ctx.precision == "bf16" and getattr(self.config, "dcb_cuda_graph", None) is not False \
             and os.environ.get("DCB_CUDA_GRAPH", "1") != "0"
         if use_graph:      # same captured launch sequence as classify's, with one "class" (the label) per image
-            key = ("loss", id(net), id(pk), is_dit, B, Cimg, H, W, v_param, fused, str(dev))
-            gr = self._graphs.get(key)
-            if gr is None:
-                if len(self._graphs) >= 6:
-                    self._graphs.clear()
-                gr = self._graphs[key] = _GraphedDenoiser(net, ctx, pk, is_dit, B, 1, Cimg, H, W, patch, v_param, fused,
-                                                          False)
-            if table is not None:
-                if gr.table is None or gr.table.shape != table.shape:
-                    gr.table = torch.empty_like(table)
-                gr.table.copy_(table)
+            key = ("loss", pk.gen, is_dit, B, Cimg, H, W, v_param, fused, str(dev))
+            hit = self._graphs.get(key)
+            gr = hit["obj"] if hit is not None else self._graphs.put(
+                key, _GraphedDenoiser(net, ctx, pk, is_dit, B, 1, Cimg, H, W, patch, v_param, fused, False), id(net), pk.gen)
+            gr.set_table(table, self._eps_calls)
             E.prologue(ctx, 1 if is_dit else 0, x.contiguous().float(), B, 1, Cimg, H, W, pk.kpad_in, a_out=gr.a_in,
                        target_out=gr.target, **pro)
             gr.logsnr.copy_(logsnr)

@@ -132,6 +132,7 @@ class DiT(nn.Module):
             return hit
         pk = self._pack(ctx)
         pk.version = ver
+        pk.gen = next(E.PACK_GEN)
         self._packs[key] = pk
         return pk
 

@@ -62,6 +62,7 @@ class GemmProfile:
 
 
 PROFILE = None
+PACK_GEN = __import__("itertools").count(1)   # generation counter of packed weight sets (UNetCondition2D / DiT .packed())
 USE_TILE_STATS = __import__("os").environ.get("DCB_TILE_STATS", "1") != "0"
 USE_FUSED_SMALL_GN = __import__("os").environ.get("DCB_FUSED_SMALL_GN", "1") != "0"
 FOLD_UPSAMPLE = __import__("os").environ.get("DCB_FOLD_UPSAMPLE", "1") != "0"   # A/B switch for upsample_conv

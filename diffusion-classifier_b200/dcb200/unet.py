@@ -263,6 +263,7 @@ class UNetCondition2D(nn.Module):
             return hit
         pk = self._pack(ctx)
         pk.version = ver
+        pk.gen = next(E.PACK_GEN)      # monotonic: CUDA-graph caches key on it (an id() can be reused after a repack)
         self._packs[key] = pk
         return pk
 

@@ -363,6 +363,55 @@ def test_timestep_shard_allreduce_gloo_world2(tmp_path):
                 assert torch.isinf(errors[b, c, 2:]).all()
 
 
+def _sync_worker(rank, world, port, out):
+    import torch.distributed as dist
+    from dcb200.classifier import sync_from_rank0
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    torch.manual_seed(100 + rank)                 # the usual "seed + rank" set-up: every rank draws differently
+    BS, n_cls, n_fast = 4, 7, 3
+    text = torch.tensor([1, 5, 0, 6]).view(-1, 1)
+    classes = torch.arange(n_cls).repeat(BS, 1)   # fast-mode candidate draw, as classify() / reference :671-677
+    wrong = classes[(classes == text) == False].view(BS, -1)  # noqa: E712
+    sel = torch.randint(0, wrong.shape[1], (BS, n_fast - 1))
+    mine = torch.cat((text, torch.gather(wrong, 1, sel)), dim=1)
+    t_mine = torch.stack([torch.rand(BS) for _ in range(3)])
+    seed_mine = torch.tensor([torch.initial_seed()], dtype=torch.int64)
+    got = [sync_from_rank0(dist, v.clone(), torch.device("cpu")) for v in (mine, t_mine, seed_mine)]
+    torch.save(dict(mine=(mine, t_mine, seed_mine), got=got), out + str(rank))
+    dist.destroy_process_group()
+
+
+def test_rank_consistency_sync_gloo_world2(tmp_path):
+    """dcb_shard='timestep': ranks seeded differently must score ONE table -- rank 0's timesteps, fast-mode candidate
+    classes and Philox seed reach every rank (classifier.sync_from_rank0); without it the all-reduced slab would mix
+    class columns.  Also checks that the draws really differed before the sync (the test would be vacuous otherwise)."""
+    import torch.multiprocessing as mp
+    out = str(tmp_path / "s")
+    port = 31500 + os.getpid() % 2000
+    mp.spawn(_sync_worker, args=(2, port, out), nprocs=2, join=True)
+    r0, r1 = torch.load(out + "0"), torch.load(out + "1")
+    assert not torch.equal(r0["mine"][0], r1["mine"][0]) and not torch.equal(r0["mine"][1], r1["mine"][1])
+    for a, b, m in zip(r0["got"], r1["got"], r0["mine"]):
+        assert torch.equal(a, b) and torch.equal(a, m)
+
+
+def test_graph_cache_drops_stale_pack_generations():
+    """CUDA-graph cache: keyed on a monotonic pack generation, entries of a superseded generation of the same
+    network go first, LRU otherwise; capacity is never exceeded."""
+    from dcb200.classifier import _GraphCache
+    c = _GraphCache()
+    c.cap = 4
+    for i in range(3):
+        c.put(("k", 1, i), f"g1_{i}", net_id=7, gen=1)
+    c.put(("other", 9, 0), "o", net_id=8, gen=9)
+    assert len(c) == 4 and c.get(("k", 1, 0))["obj"] == "g1_0"
+    c.put(("k", 2, 0), "g2_0", net_id=7, gen=2)          # repack of net 7: all gen-1 graphs of net 7 are dropped
+    assert len(c) == 2 and c.get(("k", 1, 0)) is None and c.get(("other", 9, 0)) is not None
+    for i in range(1, 6):
+        c.put(("k", 2, i), f"g2_{i}", net_id=7, gen=2)
+    assert len(c) == 4 and c.get(("other", 9, 0)) is None      # least recently used went first
+
+
 def test_c_abi_argument_validation_returns_codes_not_crashes():
     """error behaviour of the boundary: bad arguments are rejected with DCB_EINVAL (-1) and a message in dcb_last_error()
     before anything is launched (so this runs without a GPU); nothing throws or exits across the ABI."""
