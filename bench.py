@@ -232,7 +232,9 @@ def run_ours(args):
     arch, cfg, classes, T, gflop, ipg = build_workload(args.workload)
     if args.images:
         ipg = args.images
-    BS = ipg * world  # weak scaling: every rank owns 1/world of the (image x timestep) units of a world-x larger batch
+    # weak scaling (default): every rank owns 1/world of the (image x timestep) units of a world-x larger batch;
+    # strong scaling (--scaling strong): ONE batch of `ipg` images, its units split over the ranks (the latency case)
+    BS = ipg * (world if args.scaling == "weak" else 1)
     cfg.dcb_shard = "timestep"
     if args.max_batch:
         cfg.dcb_max_batch = args.max_batch
@@ -386,8 +388,8 @@ def run_ours(args):
     if rank == 0:
         line = {
             "metric": "denoiser evals/sec", "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "images_per_sec": value / (classes * T),
             "config": {"workload": workload_name(args.workload, classes, T), "images_per_step": BS,
                        "evals_per_step": evals_per_step, "shard": "(image x timestep) units over ranks + 1 all-reduce",
@@ -500,6 +502,8 @@ def main():
     ap.add_argument("--images", type=int, default=0, help="images per GPU per step")
     ap.add_argument("--max-batch", type=int, default=0, help="denoiser samples per launch sequence")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: images per step = --images x N (default); strong: one fixed batch split over the N ranks")
     ap.add_argument("--path", default="classify", choices=["classify", "sample", "loss", "evaluate"],
                     help="which caller of the denoiser kernels a step is (SURVEY 8f rows; default = the hot path)")
     args = ap.parse_args()

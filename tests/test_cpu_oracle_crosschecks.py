@@ -1,0 +1,143 @@
+"""Narrowing the "parity unpinned" part of the oracle (VERDICT r1 Next #6): diffusers 0.31.0 and pywt are not installable
+offline, but INDEPENDENT third-party restatements of three of their pieces ship in this image.  Each is executed from
+where it lies (nothing copied) and compared with oracle/diffusers_restated.py / oracle/haar.py and with the product's host
+code:
+
+  * TVM's port of diffusers ``get_timestep_embedding`` (tilelang/3rdparty/tvm/.../relax/frontend/nn/op.py) -- executed
+    through a numpy shim of the handful of relax ops it uses;
+  * MAE's ``get_2d_sincos_pos_embed`` in transformers (the function diffusers' PatchEmbed pos-embed was taken from) -- pins
+    the "w goes first" meshgrid order and the [sin | cos] layout of DiT's positional table;
+  * the Haar analysis bank written from pywt's documented filter coefficients (dec_lo = [1, 1]/sqrt2,
+    dec_hi = [-1, 1]/sqrt2, coefficient k = sum_j f[j] x[2k + 1 - j]) as an explicit convolution + decimation."""
+import ast
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+
+def _tvm_timestep_embedding_fn():
+    try:
+        import tilelang
+    except Exception:  # pragma: no cover
+        pytest.skip("tilelang (which vendors the TVM sources) is not importable")
+    path = os.path.join(os.path.dirname(tilelang.__file__), "3rdparty", "tvm", "python", "tvm", "relax", "frontend", "nn",
+                        "op.py")
+    if not os.path.exists(path):
+        pytest.skip("TVM sources not present")
+    tree = ast.parse(open(path).read())
+    fn = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "get_timestep_embedding"]
+    if not fn:
+        pytest.skip("TVM has no get_timestep_embedding")
+    fn[0].returns = None
+    for a in fn[0].args.args:
+        a.annotation = None
+    mod = ast.Module(body=[fn[0]], type_ignores=[])
+
+    class T:                                   # stand-in for the frontend's Tensor wrapper
+        def __init__(self, e):
+            self._expr = np.asarray(e)
+
+    class _nn:
+        @staticmethod
+        def pad(x, widths):
+            return np.pad(x, ((widths[2], widths[3]), (widths[0], widths[1])))
+
+    class _op:
+        nn = _nn
+        astype = staticmethod(lambda x, dt: np.asarray(x).astype(dt))
+        arange = staticmethod(lambda start, end, dtype: np.arange(start, end, dtype=dtype))
+        exp = staticmethod(np.exp)
+        cos = staticmethod(np.cos)
+        sin = staticmethod(np.sin)
+        expand_dims = staticmethod(lambda x, axis: np.expand_dims(x, axis))
+        concat = staticmethod(lambda xs, axis: np.concatenate(xs, axis=axis))
+
+    class rx:
+        const = staticmethod(lambda v, dt: np.asarray(v, dtype=dt))
+
+    ns = dict(_op=_op, rx=rx, math=math, get_default_dtype=lambda: "float32", wrap_nested=lambda e, name: e, Tensor=T)
+    exec(compile(mod, path, "exec"), ns)
+    return lambda t, dim, **kw: ns["get_timestep_embedding"](T(t), dim, **kw)
+
+
+@pytest.mark.parametrize("dim,flip,shift", [(128, True, 0), (256, True, 1), (64, False, 1), (33, True, 0)])
+def test_timestep_embedding_matches_tvm_port_of_diffusers(dim, flip, shift):
+    """a5.1 / a6: U-Net uses (flip_sin_to_cos=True, freq_shift=0), DiT's Timesteps(256, True, 1)."""
+    from oracle import diffusers_restated as dr
+    tvm_fn = _tvm_timestep_embedding_fn()
+    t = np.array([-14.3, -1.7, 0.0, 0.31, 2.5, 15.0], dtype=np.float32)       # logSNR-valued noise labels
+    ref = tvm_fn(t, dim, flip_sin_to_cos=flip, downscale_freq_shift=shift)
+    mine = dr.get_timestep_embedding(torch.from_numpy(t), dim, flip_sin_to_cos=flip, downscale_freq_shift=shift).numpy()
+    assert ref.shape == mine.shape == (6, dim)
+    assert np.abs(ref - mine).max() < 2e-6
+
+
+def test_dit_pos_embed_matches_mae_sincos_table():
+    try:
+        from transformers.models.vit_mae.modeling_vit_mae import get_2d_sincos_pos_embed as mae
+    except Exception:  # pragma: no cover
+        pytest.skip("transformers' MAE model is not importable")
+    from oracle import diffusers_restated as dr
+    from dcb200.dit import sincos_2d
+    for dim, g in ((768, 64), (128, 16), (64, 6)):
+        ref = mae(dim, g, add_cls_token=False)
+        a = dr.get_2d_sincos_pos_embed(dim, g, base_size=g)
+        assert ref.shape == a.shape == (g * g, dim)
+        assert np.abs(ref - a).max() < 1e-12                      # oracle == the MAE table (float64)
+        assert np.abs(ref - sincos_2d(dim, g)).max() < 1e-12      # product host code == the MAE table
+
+
+def _bank(x, f):
+    """pywt's decimating convolution for an orthogonal 2-tap bank on an even-length signal: c[k] = sum_j f[j] x[2k+1-j]"""
+    full = np.convolve(x, f)            # full[n] = sum_j f[j] x[n - j]
+    return full[1::2][: len(x) // 2]
+
+
+def test_haar_oracle_matches_filter_bank_definition():
+    from oracle import haar
+    s = 1 / np.sqrt(2.0)
+    dec_lo, dec_hi = np.array([s, s]), np.array([-s, s])           # pywt.Wavelet('haar').dec_lo / dec_hi (documented)
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal(16)
+    lo, hi = haar.dwt(x)
+    assert np.abs(lo - _bank(x, dec_lo)).max() < 1e-12 and np.abs(hi - _bank(x, dec_hi)).max() < 1e-12
+    assert np.allclose(_bank(np.array([1.0, 2, 3, 4]), dec_hi), [-s, -s])       # the documented pywt KAT
+    img = rng.standard_normal((8, 12))
+    cA, (cH, cV, cD) = haar.dwt2(img)
+    rows_lo = np.stack([_bank(c, dec_lo) for c in img.T], 1)       # along axis 0 first ...
+    rows_hi = np.stack([_bank(c, dec_hi) for c in img.T], 1)
+
+    def along1(m, f):
+        return np.stack([_bank(r, f) for r in m], 0)
+
+    # ... then axis 1; dwt2 returns (aa, (da, ad, dd)), first letter = axis 0
+    for got, want in ((cA, along1(rows_lo, dec_lo)), (cH, along1(rows_hi, dec_lo)), (cV, along1(rows_lo, dec_hi)),
+                      (cD, along1(rows_hi, dec_hi))):
+        assert np.abs(got - want).max() < 1e-12
+    back = haar.idwt2((cA, (cH, cV, cD)))
+    assert np.abs(back - img).max() < 1e-12
+    # 2x2 block closed form of SURVEY App. A.3 on random blocks
+    a, b, c, d = (img[0::2, 0::2], img[0::2, 1::2], img[1::2, 0::2], img[1::2, 1::2])
+    assert np.abs(cA - (a + b + c + d) / 2).max() < 1e-12 and np.abs(cH - (a + b - c - d) / 2).max() < 1e-12
+    assert np.abs(cV - (a - b + c - d) / 2).max() < 1e-12 and np.abs(cD - (a - b - c + d) / 2).max() < 1e-12
+
+
+def test_attention_oracle_equals_explicit_softmax():
+    """the Attention restatement (attention_processor.AttnProcessor2_0 path) against the textbook formula, incl. the
+    single-token cross-attention identity the product's collapsed attn2 relies on (softmax over one key == 1)."""
+    from oracle import diffusers_restated as dr
+    torch.manual_seed(0)
+    att = dr.Attention(64, heads=4, dim_head=16, bias=False).double()
+    x = torch.randn(2, 9, 64, dtype=torch.float64)
+    q, k, v = att.to_q(x), att.to_k(x), att.to_v(x)
+    sp = lambda t: t.reshape(2, 9, 4, 16).transpose(1, 2)
+    p = torch.softmax(sp(q) @ sp(k).transpose(-1, -2) / 4.0, -1)
+    want = att.to_out[0]((p @ sp(v)).transpose(1, 2).reshape(2, 9, 64))
+    assert (att(x) - want).abs().max() < 1e-12
+    xatt = dr.Attention(64, heads=4, dim_head=16, cross_attention_dim=24).double()
+    ctx = torch.randn(2, 1, 24, dtype=torch.float64)
+    want1 = xatt.to_out[0](xatt.to_v(ctx)).expand(2, 9, 64)
+    assert (xatt(x, ctx) - want1).abs().max() < 1e-12
