@@ -33,7 +33,8 @@ class GemmDesc(C.Structure):
                 ("rowvec_ld", c_i32), ("gate_ld", c_i32), ("rows_per_group", c_i32), ("act", c_i32),
                 ("act_post", c_i32), ("res_ld", c_i32), ("res_mod", c_i32), ("res_dtype", c_i32),
                 ("out_ld", c_i32), ("out_dtype", c_i32), ("mse_div", c_i32), ("mse_ld", c_i32), ("up_phase", c_i32),
-                ("_r2", c_i32)]
+                ("xf_silu", c_i32), ("xf_a", c_void_p), ("xf_b", c_void_p), ("xf_src1", c_void_p), ("xf_c1", c_i32),
+                ("xf_div1", c_i32)]
 
 
 _PROTOS = {
@@ -52,6 +53,9 @@ _PROTOS = {
     "dcb_struct_size": (c_int, [c_int]),
     "dcb_gemm_mse_layout": (c_int, [C.POINTER(GemmDesc), C.POINTER(c_i32), C.POINTER(c_i32)]),
     "dcb_gemm_gn_layout": (c_int, [C.POINTER(GemmDesc), C.POINTER(c_i32)]),
+    "dcb_gemm_xf_layout": (c_int, [C.POINTER(GemmDesc), C.POINTER(c_i32)]),
+    "dcb_groupnorm_coef_from_tiles": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                              c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p]),
     "dcb_groupnorm_stats_from_tiles": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                                c_void_p, c_void_p]),
     "dcb_mse_finalize": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),

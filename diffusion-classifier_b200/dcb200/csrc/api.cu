@@ -55,6 +55,14 @@ static int to_dev(const dcb_gemm_desc* d, GemmDev* g) {
     o.nb_div = s.nb_div > 1 ? s.nb_div : 1;
     K += s.kc;
   }
+  g->xf_a = d->xf_a; g->xf_b = d->xf_b; g->xf_src1 = d->xf_src1;
+  g->xf_c1 = d->xf_c1; g->xf_div1 = d->xf_div1; g->xf_silu = d->xf_silu;
+  if (d->xf_a != nullptr) {
+    DCB_REQUIRE(d->xf_b != nullptr && d->dtype == DCB_BF16 && d->nseg >= 9, "gemm: xf_a needs xf_b, bf16 and a 3x3 conv in segments 0..8");
+    DCB_REQUIRE(d->xf_c1 >= 0 && d->xf_c1 % 64 == 0 && (d->xf_c1 == 0) == (d->xf_src1 == nullptr), "gemm: xf_src1 / xf_c1 mismatch");
+    DCB_REQUIRE((((uintptr_t)d->xf_a | (uintptr_t)d->xf_b) & 15) == 0, "gemm: xf_a / xf_b must be 16-byte aligned");
+    K += 9 * d->xf_c1;
+  }
   g->K = K;
   EpiDev& e = g->epi;
   e.M = d->NB * d->OH * d->OW;
@@ -87,7 +95,7 @@ static int pick_engine(const dcb_gemm_desc* d) {
 
 using namespace dcb;
 
-extern "C" int dcb_version(void) { return 100; }
+extern "C" int dcb_version(void) { return 110; }
 extern "C" const char* dcb_last_error(void) { return g_err; }
 extern "C" int64_t dcb_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 extern "C" void dcb_note_graph_replay(int64_t n_kernels) { g_launches.fetch_add(n_kernels, std::memory_order_relaxed); }
@@ -112,6 +120,17 @@ extern "C" int dcb_gemm_gn_layout(const dcb_gemm_desc* d, int32_t* supported) {
   if (rc) return rc;
   *supported = (pick_engine(d) == DCB_ENGINE_TCGEN05 && g.K % 64 == 0 && tc_staged(g)) ? 1 : 0;
   return DCB_OK;
+}
+
+extern "C" int dcb_gemm_xf_layout(const dcb_gemm_desc* d, int32_t* supported) {
+  GemmDev g;
+  int rc = to_dev(d, &g);
+  if (rc) return rc;
+  *supported = 0;
+  if (pick_engine(d) != DCB_ENGINE_TCGEN05 || g.xf_a == nullptr || g.K % 64 != 0) return DCB_OK;
+  rc = launch_gemm_tc(g, nullptr, true);
+  if (rc == DCB_OK) *supported = 1;
+  return rc == DCB_EUNSUPPORTED ? DCB_OK : rc;
 }
 
 extern "C" int dcb_gemm_mse_layout(const dcb_gemm_desc* d, int32_t* rows_per_part, int32_t* n_tiles) {

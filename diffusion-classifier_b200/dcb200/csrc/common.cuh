@@ -66,6 +66,13 @@ __device__ __forceinline__ float gelu_tanh_fast_f(float x) {
   const float hx = 0.5f * x;
   return fmaf(hx, tanh_approx_f(u), hx);
 }
+// SiLU of the GroupNorm kernels (bf16 tensors): x * sigmoid(x), sigmoid = 0.5 tanh(0.5 x) + 0.5 -> ONE MUFU op per element.
+// gn_apply_kernel and the fused transform of gemm_tc2's XF variant must produce the same bits: both call this.
+__device__ __forceinline__ float gn_silu_bf16(float y) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * y));
+  return y * fmaf(0.5f, t, 0.5f);
+}
 __device__ __forceinline__ float rcp_approx_f(float x) {
   float y;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -181,6 +188,11 @@ struct GemmDev {
   SegDev seg[DCB_MAX_SEGS];
   const void* W;
   EpiDev epi;
+  // fused GroupNorm of the 3x3 conv in segments 0..8 (dcb_gemm_desc.xf_*)
+  const float* xf_a;
+  const float* xf_b;
+  const void* xf_src1;
+  int xf_c1, xf_div1, xf_silu;
 };
 
 // output row of GEMM row m (identity, or the strided position of a folded-upsample phase)
@@ -207,7 +219,7 @@ __device__ __forceinline__ float epi_scalar(const EpiDev& e, int m, int n, float
 
 // host entry points of the engines (gemm_simt.cu / gemm_tc.cu)
 int launch_gemm_simt(const GemmDev& g, cudaStream_t st);
-int launch_gemm_tc(const GemmDev& g, cudaStream_t st);
+int launch_gemm_tc(const GemmDev& g, cudaStream_t st, bool dry_run = false);
 int tc_geometry(const GemmDev& g, int* m_tiles, int* n_tiles, int* BN);
 bool tc_staged(const GemmDev& g);
 

@@ -386,9 +386,11 @@ static int encode_a_map(CUtensorMap* map, const SegDev& s, int NBsrc, const TcGe
 }
 
 int launch_gemm_tc2(const GemmDev& g, cudaStream_t st, int bw, int bh, int bn, int tiles_x, int tiles_y, int tiles_nb,
-                    int BN, int uniform, int staged);
+                    int BN, int uniform, int staged, bool dry_run);
 
-int launch_gemm_tc(const GemmDev& g, cudaStream_t st) {
+// dry_run: everything but the launch (dcb_gemm_xf_layout: would this descriptor run on the kernel that can apply a fused
+// GroupNorm transform?)
+int launch_gemm_tc(const GemmDev& g, cudaStream_t st, bool dry_run) {
   DCB_REQUIRE(g.dtype == DCB_BF16, "tcgen05 engine is bf16 only");
   DCB_REQUIRE(g.K % TC_BK == 0, "tcgen05 engine needs K %% 64 == 0 (K=%d)", g.K);
   DCB_REQUIRE(((uintptr_t)g.W & 15) == 0, "weights must be 16-byte aligned");
@@ -485,8 +487,8 @@ int launch_gemm_tc(const GemmDev& g, cudaStream_t st) {
                       e.act != DCB_ACT_GEGLU && e.gn_part == nullptr && e.mse_part == nullptr && e.out != nullptr &&
                       e.out_dtype == DCB_BF16 && e.out_ld % 8 == 0 && ((uintptr_t)e.out % 16) == 0 && !is_conv9(g) &&
                       t.bn == 1 && (m_tiles / 2) * (e.N / 256) >= 2 * num_sms();
-    if (wide) {
-      rc = launch_gemm_tc2(g, st, t.bw, t.bh, t.bn, t.tiles_x, t.tiles_y, t.tiles_nb, 256, p.uniform, 0);
+    if (wide && g.xf_a == nullptr) {
+      rc = launch_gemm_tc2(g, st, t.bw, t.bh, t.bn, t.tiles_x, t.tiles_y, t.tiles_nb, 256, p.uniform, 0, dry_run);
       if (rc != DCB_EUNSUPPORTED) return rc;
     }
   }
@@ -496,9 +498,14 @@ int launch_gemm_tc(const GemmDev& g, cudaStream_t st) {
                         (g.OH * g.OW) % TC_BM == 0 && !(knobs() & DCB_KNOB_NO_TC2_MSE);
   if ((p.staged || mse_only) && t.BN <= 128 && g.epi.act != DCB_ACT_GEGLU && !(knobs() & DCB_KNOB_NO_TC2) &&
       t.tiles_x * t.tiles_y * t.tiles_nb * t.n_tiles >= 4 * num_sms()) {
-    rc = launch_gemm_tc2(g, st, t.bw, t.bh, t.bn, t.tiles_x, t.tiles_y, t.tiles_nb, t.BN, p.uniform, p.staged);
+    rc = launch_gemm_tc2(g, st, t.bw, t.bh, t.bn, t.tiles_x, t.tiles_y, t.tiles_nb, t.BN, p.uniform, p.staged, dry_run);
     if (rc != DCB_EUNSUPPORTED) return rc;
   }
+  if (g.xf_a != nullptr) {
+    if (!dry_run) set_error("gemm: xf_a (fused GroupNorm) needs the x-halo mode of gemm_tc2 -- ask dcb_gemm_xf_layout first");
+    return DCB_EUNSUPPORTED;
+  }
+  if (dry_run) return DCB_OK;
   const int epi_bytes = p.staged ? 2 * TC_EPI_BYTES : 0;
   int stages = (TC_SMEM_LIMIT - 1024 - TC_BAR_BYTES - epi_bytes) / stage_bytes;
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;

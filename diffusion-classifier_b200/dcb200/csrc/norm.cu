@@ -106,11 +106,7 @@ __device__ __forceinline__ float gn_silu(float y);
 template <>
 __device__ __forceinline__ float gn_silu<float>(float y) { return silu_f(y); }
 template <>
-__device__ __forceinline__ float gn_silu<__nv_bfloat16>(float y) {
-  float t;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * y));
-  return y * fmaf(0.5f, t, 0.5f);
-}
+__device__ __forceinline__ float gn_silu<__nv_bfloat16>(float y) { return gn_silu_bf16(y); }
 
 // ---- GroupNorm apply (+SiLU), writes the concatenated normalised tensor [NB,HW,C0+C1] ----------------------
 // thread -> fixed 16-byte channel slot (coefficients live in registers), loops over pixels with 4 loads in flight
@@ -196,7 +192,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const T* __restric
     for (int i = 0; i < VN; ++i) {
       const int g = (c + i) / cpg;
       ca[i] = s_rstd[g] * gamma[c + i];
-      cbias[i] = beta[c + i] - s_mean[g] * ca[i];
+      cbias[i] = __fmaf_rn(-s_mean[g], ca[i], beta[c + i]);     // written out: gn_coef_kernel must produce the same bits
     }
     const T* base;
     int cs;
@@ -225,10 +221,16 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const T* __restric
 
 // ---- GroupNorm statistics from the producer GEMM's tile partials (dcb_gemm_desc.gn_part) -------------------
 // one block per sample; thread (slice, g) walks every 8th tile of group g's channels, fixed-order combine
+// coef_a != nullptr: also finish the statistics into the per-(sample, channel) affine y = a x + b exactly as gn_apply_kernel
+// derives it from `out` (same double-precision mean / rstd from the fp32 group sums, same fp32 products)
 __global__ void __launch_bounds__(512) gn_tiles_finalize_kernel(const float* __restrict__ p0, int C0, int div0,
                                                                 const float* __restrict__ p1, int C1, int div1, int tps,
-                                                                int G, float* __restrict__ out) {
+                                                                int G, float* __restrict__ out, int HW,
+                                                                const float* __restrict__ gamma,
+                                                                const float* __restrict__ beta, float eps,
+                                                                float* __restrict__ coef_a, float* __restrict__ coef_b) {
   __shared__ double sh[8][64][2];
+  __shared__ float s_mean[64], s_rstd[64];
   const int n = blockIdx.x, g = threadIdx.x % G, slice = threadIdx.x / G;
   const int cpg = (C0 + C1) / G;
   double s = 0.0, q = 0.0;
@@ -248,8 +250,29 @@ __global__ void __launch_bounds__(512) gn_tiles_finalize_kernel(const float* __r
   __syncthreads();
   if (slice == 0) {
     for (int k = 1; k < 8; ++k) { s += sh[k][g][0]; q += sh[k][g][1]; }
-    out[((int64_t)n * G + g) * 2] = (float)s;
-    out[((int64_t)n * G + g) * 2 + 1] = (float)q;
+    if (out) {
+      out[((int64_t)n * G + g) * 2] = (float)s;
+      out[((int64_t)n * G + g) * 2 + 1] = (float)q;
+    }
+    if (coef_a) {      // gn_apply_kernel reads the fp32 sums back: round exactly as it would see them
+      const double sf = (double)(float)s, qf = (double)(float)q;
+      const double cnt = (double)HW * cpg;
+      const double mean = sf / cnt;
+      double var = qf / cnt - mean * mean;
+      if (var < 0.0) var = 0.0;
+      s_mean[g] = (float)mean;
+      s_rstd[g] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+  }
+  if (coef_a) {
+    __syncthreads();
+    const int C = C0 + C1;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      const int gg = c / cpg;
+      const float ca = s_rstd[gg] * gamma[c];
+      coef_a[(int64_t)n * C + c] = ca;
+      coef_b[(int64_t)n * C + c] = __fmaf_rn(-s_mean[gg], ca, beta[c]);
+    }
   }
 }
 
@@ -426,8 +449,23 @@ extern "C" int dcb_groupnorm_stats_from_tiles(const float* part0, int C0, int di
   DCB_REQUIRE(part0 != nullptr && (C1 == 0) == (part1 == nullptr) && tiles_per_sample >= 1 && NB >= 1,
               "groupnorm_stats_from_tiles: bad arguments");
   gn_tiles_finalize_kernel<<<NB, 8 * G, 0, (cudaStream_t)stream>>>(part0, C0, div0 < 1 ? 1 : div0, part1, C1,
-                                                                  div1 < 1 ? 1 : div1, tiles_per_sample, G, part_out);
+                                                                  div1 < 1 ? 1 : div1, tiles_per_sample, G, part_out, 0,
+                                                                  nullptr, nullptr, 0.f, nullptr, nullptr);
   DCB_CHECK_LAUNCH("gn_tiles_finalize");
+  return DCB_OK;
+}
+
+extern "C" int dcb_groupnorm_coef_from_tiles(const float* part0, int C0, int div0, const float* part1, int C1, int div1,
+                                             int NB, int tiles_per_sample, int G, const float* gamma, const float* beta,
+                                             float eps, float* coef_a, float* coef_b, dcb_stream stream) {
+  DCB_REQUIRE(G > 0 && G <= 64 && (C0 + C1) % G == 0, "groupnorm: C=%d not divisible by G=%d (G<=64)", C0 + C1, G);
+  DCB_REQUIRE(part0 != nullptr && (C1 == 0) == (part1 == nullptr) && tiles_per_sample >= 1 && NB >= 1 &&
+                  gamma != nullptr && beta != nullptr && coef_a != nullptr && coef_b != nullptr,
+              "groupnorm_coef_from_tiles: bad arguments");
+  gn_tiles_finalize_kernel<<<NB, 8 * G, 0, (cudaStream_t)stream>>>(part0, C0, div0 < 1 ? 1 : div0, part1, C1,
+                                                                  div1 < 1 ? 1 : div1, tiles_per_sample, G, nullptr,
+                                                                  tiles_per_sample * 128, gamma, beta, eps, coef_a, coef_b);
+  DCB_CHECK_LAUNCH("gn_tiles_finalize_coef");
   return DCB_OK;
 }
 

@@ -172,6 +172,8 @@ __device__ __forceinline__ void tmem_ld_wait_dep(uint32_t* r) {
 }
 // named barrier of one epilogue group (4 warps); group g uses barrier id 1 + g
 __device__ __forceinline__ void epi_bar(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void bar_sync_n(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_arrive_n(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile(

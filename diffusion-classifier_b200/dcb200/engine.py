@@ -66,6 +66,8 @@ PACK_GEN = __import__("itertools").count(1)   # generation counter of packed wei
 USE_TILE_STATS = __import__("os").environ.get("DCB_TILE_STATS", "1") != "0"
 USE_FUSED_SMALL_GN = __import__("os").environ.get("DCB_FUSED_SMALL_GN", "1") != "0"
 FOLD_UPSAMPLE = __import__("os").environ.get("DCB_FOLD_UPSAMPLE", "1") != "0"   # A/B switch for upsample_conv
+FUSE_GN = __import__("os").environ.get("DCB_FUSE_GN", "1") != "0"   # A/B switch: GroupNorm applied inside the consumer conv
+XF_UNSUPPORTED = object()     # gemm(xf=...) sentinel: this launch cannot apply the fused transform; nothing was launched
 
 
 def _p(t):
@@ -84,7 +86,7 @@ def conv3x3_segs(src, C_, H, W, stride=1, nb_div=1):
 def gemm(ctx: Ctx, segs, W, N, NB, OH, OW, *, bias=None, rowvec=None, rowvec_ld=0, rowvec_idx=None, rows_per_group=0,
          gate=None, gate_ld=0, residual=None, res_ld=0, res_mod=0, res_idx=None, act=L.ACT_NONE, act_post=L.ACT_NONE,
          out=None, out_dtype=None, out_ld=None, mse=None, want_out=True, k_alg=None, gn_stats=False, up_phase=0,
-         gn_part=None):
+         gn_part=None, xf=None):
     """D = sum_seg A_seg . W^T with the fused epilogue; returns the [M, n_out] output (or None if want_out=False).
 
     mse = dict(target=, scale=, div=, ld=, err=[S] fp32 out) enables the fused eps-MSE epilogue (tcgen05 only).
@@ -93,6 +95,9 @@ def gemm(ctx: Ctx, segs, W, N, NB, OH, OW, *, bias=None, rowvec=None, rowvec_ld=
     produce them (fp32 verify engine, 256-wide direct-epilogue tiles).
     up_phase = 1 + 2a + b: this launch is phase (a, b) of a folded 2x nearest upsample + conv (see ``upsample_conv``);
     ``out`` ([NB*4*OH*OW, n_out]) and ``gn_part`` are then shared by the four phase launches and supplied by the caller.
+    xf = dict(a=, b=, src1=, c1=, div1=, silu=, prepare=): segments 0..8 name the RAW input of a GroupNorm(+SiLU) and the
+    kernel normalises the operand on the fly (dcb_gemm_desc.xf_a).  Returns ``XF_UNSUPPORTED`` -- before anything is
+    launched -- when this launch cannot do that; otherwise calls ``xf['prepare']()`` (fills the coefficient tables) first.
     """
     lib = L.lib()
     d = L.GemmDesc()
@@ -115,6 +120,10 @@ def gemm(ctx: Ctx, segs, W, N, NB, OH, OW, *, bias=None, rowvec=None, rowvec_ld=
     d.act, d.act_post = act, act_post
     d.up_phase = up_phase
     assert up_phase == 0 or out is not None
+    if xf is not None:
+        d.xf_a, d.xf_b, d.xf_silu = xf["a"].data_ptr(), xf["b"].data_ptr(), int(xf["silu"])
+        d.xf_src1, d.xf_c1, d.xf_div1 = _p(xf.get("src1")), xf.get("c1", 0), xf.get("div1", 1)
+        keep.append(xf.get("src1"))
     odt = out_dtype or ctx.tdtype
     if want_out and out is None:
         out = torch.empty(M, n_out if out_ld is None else out_ld, device=ctx.device, dtype=odt)
@@ -147,6 +156,12 @@ def gemm(ctx: Ctx, segs, W, N, NB, OH, OW, *, bias=None, rowvec=None, rowvec_ld=
         pps = (OH * OW) // rpp.value * nt.value
         part = torch.empty(NB * pps, device=ctx.device, dtype=torch.float32)
         d.mse_part = part.data_ptr()
+    if xf is not None:
+        ok = C.c_int32()
+        L.check(lib.dcb_gemm_xf_layout(C.byref(d), C.byref(ok)), "gemm_xf_layout")
+        if not ok.value:
+            return XF_UNSUPPORTED
+        xf["prepare"]()
     prof = PROFILE if (PROFILE is not None and ctx.code == L.BF16 and ctx.engine != L.ENGINE_SIMT) else None
     if prof is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -154,7 +169,7 @@ def gemm(ctx: Ctx, segs, W, N, NB, OH, OW, *, bias=None, rowvec=None, rowvec_ld=
     L.check(lib.dcb_gemm(C.byref(d), ctx.stream()), "gemm")
     if prof is not None:
         e1.record()
-        K = sum(sg[5] for sg in segs)
+        K = sum(sg[5] for sg in segs) + (9 * xf.get("c1", 0) if xf is not None else 0)
         prof.rows.append((e0, e1, 2.0 * M * N * (k_alg or K), f"M{M}_N{N}_K{K}_seg{len(segs)}"))
     if mse is not None:
         L.check(lib.dcb_mse_finalize(part.data_ptr(), pps, NB, mse["err"].data_ptr(), 1, ctx.stream()), "mse_finalize")
@@ -250,6 +265,33 @@ def groupnorm(ctx, x0, C0, x1, C1, NB, HW, gamma, beta, eps, silu, G=32, div0=1,
         e1.record()     # algorithmic bytes: one read + one write of the normalised tensor
         prof.gn_rows.append((e0, e1, 2.0 * NB * HW * (C0 + C1) * out.element_size()))
     return out
+
+
+def gn_conv3x3(ctx, x0, C0, x1, C1, NB, H, W, gamma, beta, eps, silu, Wt, N, *, div1=1, st0=None, st1=None, G=32,
+               extra_segs=(), **kw):
+    """conv3x3(GroupNorm(+SiLU)(cat([x0, x1], channel))) [+ extra K segments, e.g. a 1x1 shortcut over raw tensors].
+
+    Fused form (full-resolution layers: rows of >= 128 pixels, enough tiles for the 256-pixel CTA kernel, producer-written
+    tile statistics): ``dcb_groupnorm_coef_from_tiles`` turns the statistics into per-(sample, channel) coefficients and the
+    conv normalises its operand on the fly -- the normalised tensor (one HBM write + one read of every activation, the
+    ``gn_apply`` pass) never exists.  Bit-identical to the unfused form, which everything else takes."""
+    HW = H * W
+    if FUSE_GN and ctx.code == L.BF16 and ctx.engine != L.ENGINE_SIMT and st0 is not None and (x1 is None or st1 is not None) \
+            and USE_TILE_STATS and HW % 128 == 0 and W % 128 == 0 and C0 % 64 == 0 and C1 % 64 == 0:
+        ca = torch.empty(NB, C0 + C1, device=ctx.device, dtype=torch.float32)
+        cb = torch.empty(NB, C0 + C1, device=ctx.device, dtype=torch.float32)
+
+        def prepare():
+            L.check(L.lib().dcb_groupnorm_coef_from_tiles(st0.data_ptr(), C0, 1, _p(st1), C1, div1, NB, HW // 128, G,
+                                                          gamma.data_ptr(), beta.data_ptr(), eps, ca.data_ptr(),
+                                                          cb.data_ptr(), ctx.stream()), "groupnorm_coef_from_tiles")
+
+        r = gemm(ctx, conv3x3_segs(x0, C0, H, W) + list(extra_segs), Wt, N, NB, H, W,
+                 xf=dict(a=ca, b=cb, src1=x1, c1=C1, div1=div1, silu=silu, prepare=prepare), **kw)
+        if r is not XF_UNSUPPORTED:
+            return r
+    a = groupnorm(ctx, x0, C0, x1, C1, NB, HW, gamma, beta, eps, silu, G=G, div1=div1, st0=st0, st1=st1)
+    return gemm(ctx, conv3x3_segs(a, C0 + C1, H, W) + list(extra_segs), Wt, N, NB, H, W, **kw)
 
 
 def expand_samples(ctx, x, NB, div, rows_per_sample):

@@ -378,18 +378,20 @@ class UNetCondition2D(nn.Module):
         s1 = x1.st if x1 is not None else None
         C1 = x1.C if x1 is not None else 0
         tld = temb.shape[1] * (rep if unit else 1)   # per-unit layers read the unit's first sample row of temb
-        a1 = E.groupnorm(ctx, x0.t, C0, t1, C1, NB, HW, q.g1, q.b1n, q.eps, True, div1=d1, st0=x0.st, st1=s1)
-        h1, hs = E.gemm(ctx, E.conv3x3_segs(a1, q.cin, H, W), q.w1, q.cout, NB, H, W, bias=q.b1,
-                        rowvec=temb[:, q.temb_off:], rowvec_ld=tld, rows_per_group=HW, gn_stats=True)
-        a2 = E.groupnorm(ctx, h1, q.cout, None, 0, NB, HW, q.g2, q.b2n, q.eps, True, st0=hs)
-        segs = E.conv3x3_segs(a2, q.cout, H, W)
+        # norm1 + SiLU + conv1 (+ time embedding), norm2 + SiLU + conv2 (+ shortcut / residual): the GroupNorms are applied
+        # inside the convs where the launch supports it (E.gn_conv3x3), else as their own streaming pass
+        h1, hs = E.gn_conv3x3(ctx, x0.t, C0, t1, C1, NB, H, W, q.g1, q.b1n, q.eps, True, q.w1, q.cout, div1=d1,
+                              st0=x0.st, st1=s1, bias=q.b1, rowvec=temb[:, q.temb_off:], rowvec_ld=tld,
+                              rows_per_group=HW, gn_stats=True)
         if q.shortcut:
-            segs.append(E.seg(x0.t, C0, H, W))
+            extra = [E.seg(x0.t, C0, H, W)]
             if x1 is not None:
-                segs.append(E.seg(t1, C1, H, W, nb_div=d1))
-            out = E.gemm(ctx, segs, q.w2, q.cout, NB, H, W, bias=q.b2, gn_stats=True)
+                extra.append(E.seg(t1, C1, H, W, nb_div=d1))
+            out = E.gn_conv3x3(ctx, h1, q.cout, None, 0, NB, H, W, q.g2, q.b2n, q.eps, True, q.w2, q.cout, st0=hs,
+                               extra_segs=extra, bias=q.b2, gn_stats=True)
         else:
-            out = E.gemm(ctx, segs, q.w2, q.cout, NB, H, W, bias=q.b2, residual=x0.t, res_ld=C0, gn_stats=True)
+            out = E.gn_conv3x3(ctx, h1, q.cout, None, 0, NB, H, W, q.g2, q.b2n, q.eps, True, q.w2, q.cout, st0=hs,
+                               bias=q.b2, residual=x0.t, res_ld=C0, gn_stats=True)
         return _Act(out, q.cout, rep if unit else 1)
 
     def _transformer(self, ctx, q, xattn, xattn_idx, x, U, rep, H, W):
@@ -481,12 +483,12 @@ class UNetCondition2D(nn.Module):
                              h.C, 1)
         assert h.div == 1
         Ch = h.C
-        a = E.groupnorm(ctx, h.t, Ch, None, 0, S, H * W, pk.out_g, pk.out_bn, self.config.norm_eps, True, st0=h.st)
         Co = self.config.out_channels
+        gn = (ctx, h.t, Ch, None, 0, S, H, W, pk.out_g, pk.out_bn, self.config.norm_eps, True, pk.out_w, Co)
         if mse is not None and mse.get("fused", False):
-            E.gemm(ctx, E.conv3x3_segs(a, Ch, H, W), pk.out_w, Co, S, H, W, bias=pk.out_b, mse=mse, want_out=False)
+            E.gn_conv3x3(*gn, st0=h.st, bias=pk.out_b, mse=mse, want_out=False)
             return None
-        pred = E.gemm(ctx, E.conv3x3_segs(a, Ch, H, W), pk.out_w, Co, S, H, W, bias=pk.out_b, out_dtype=torch.float32)
+        pred = E.gn_conv3x3(*gn, st0=h.st, bias=pk.out_b, out_dtype=torch.float32)
         if mse is not None:
             E.eps_mse(ctx, pred, mse["target"], mse.get("scale"), S, mse.get("div", 1), H * W * Co, mse["err"])
             return None

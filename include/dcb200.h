@@ -123,7 +123,17 @@ typedef struct dcb_gemm_desc {
                                 output (Upsample2D + conv folded into four 2x2-tap convs over the LOW-resolution input):
                                 row m = (n, y, x) of the (OH, OW) grid is stored at row (n, 2y + a, 2x + b) of the
                                 (2 OH, 2 OW) output; gn_part tiles are laid out [n][phase][tile] */
-  int32_t _r2;
+  int32_t xf_silu;           /* (see xf_a) apply SiLU after the affine */
+  /* fused GroupNorm(+SiLU) of the conv's INPUT: when xf_a != NULL, segments 0..8 (a stride-1 3x3 conv) name the RAW,
+   * pre-normalisation tensor(s) -- channels [0, seg.C) from seg[0].src and, when xf_c1 > 0, channels [seg.C, seg.C + xf_c1)
+   * from xf_src1 ([ceil(NB / xf_div1), H, W, xf_c1]: the up-path skip of a concatenated GroupNorm) -- and the kernel
+   * applies y = xf_a[n][c] * x + xf_b[n][c] (then SiLU) to the operand on the fly, bit-identical to
+   * dcb_groupnorm_apply.  xf_a / xf_b: fp32 [NB][seg.C + xf_c1] from dcb_groupnorm_coef_from_tiles.  Weights span
+   * K = 9 (seg.C + xf_c1).  Only some launches support it: ask dcb_gemm_xf_layout. */
+  const float* xf_a;
+  const float* xf_b;
+  const void* xf_src1;
+  int32_t xf_c1, xf_div1;
 } dcb_gemm_desc;
 
 int dcb_gemm(const dcb_gemm_desc* d, dcb_stream stream);
@@ -131,6 +141,9 @@ int dcb_gemm(const dcb_gemm_desc* d, dcb_stream stream);
 int dcb_struct_size(int which);
 /* *supported = 1 when dcb_gemm(d) would fill d->gn_part (tcgen05 engine, staged bf16 epilogue); rows per tile = 128 */
 int dcb_gemm_gn_layout(const dcb_gemm_desc* d, int32_t* supported);
+/* *supported = 1 when dcb_gemm(d) can apply the fused GroupNorm transform d->xf_a asks for (tcgen05 engine, 256-pixel
+ * CTAs with x-halo boxes: stride-1 3x3 conv, OW a multiple of 128, at least 4 tiles per SM) */
+int dcb_gemm_xf_layout(const dcb_gemm_desc* d, int32_t* supported);
 /* rows covered by one mse_part entry for descriptor d (128 for tcgen05, 64 for SIMT), and n-tile count */
 int dcb_gemm_mse_layout(const dcb_gemm_desc* d, int32_t* rows_per_part, int32_t* n_tiles);
 /* err[s] (+)= sum of parts_per_sample consecutive partials (fixed order => deterministic) */
@@ -157,6 +170,11 @@ int dcb_groupnorm_fused(int dtype, const void* x0, int C0, int div0, const void*
  * writes part_out[NB][1][G][2] = (sum, sumsq) per group, i.e. the `part` of dcb_groupnorm_apply with chunks = 1 */
 int dcb_groupnorm_stats_from_tiles(const float* part0, int C0, int div0, const float* part1, int C1, int div1, int NB,
                                    int tiles_per_sample, int G, float* part_out, dcb_stream stream);
+/* the same reduction, finished into the per-(sample, channel) affine of the normalisation: coef_a[n][c] = rstd * gamma[c],
+ * coef_b[n][c] = beta[c] - mean * coef_a[n][c]  (fp32 [NB][C0 + C1] each) -- what dcb_gemm_desc.xf_a / xf_b consume */
+int dcb_groupnorm_coef_from_tiles(const float* part0, int C0, int div0, const float* part1, int C1, int div1, int NB,
+                                  int tiles_per_sample, int G, const float* gamma, const float* beta, float eps,
+                                  float* coef_a, float* coef_b, dcb_stream stream);
 /* same, with per-source sample divisors: sample n reads x0[n / div0] and x1[n / div1] (see dcb_seg.nb_div) */
 int dcb_groupnorm_stats_div(int dtype, const void* x0, int C0, int div0, const void* x1, int C1, int div1, int NB, int HW,
                             int G, int chunks, float* part, dcb_stream stream);

@@ -464,3 +464,94 @@ def test_tc2_wide_256x256_tiles(dev, M, K, N, extra):
     with L.knob("TC2_WIDE"):
         out = E.linear(_ctx(dev), x, w, N, **kw)
     assert L.launch_count() == n0 + 1 and torch.equal(out, narrow)
+
+
+def _tile_stats(x):
+    """per-128-row-tile, per-column (sum, sum of squares) of a [rows, C] bf16 tensor, as a producer GEMM's epilogue writes"""
+    f = x.float().reshape(-1, 128, x.shape[-1])
+    return torch.stack([f.sum(1), (f * f).sum(1)], -1).contiguous()
+
+
+@pytest.mark.parametrize("NB,H,W,C0,C1,div1,N,extra", [
+    (5, 128, 128, 128, 0, 1, 128, "rowvec"),       # resnet conv1, down path: single source, time-embedding row vector
+    (6, 128, 128, 128, 128, 2, 128, "rowvec"),     # resnet conv1, up path: cat([h, per-unit skip]) -> K = 9 * 256 (dominant conv)
+    (5, 128, 128, 128, 0, 1, 128, "residual"),     # resnet conv2 with identity shortcut
+    (5, 128, 128, 128, 0, 1, 128, "shortcut"),     # resnet conv2 + 1x1 conv_shortcut over the raw (concatenated) input
+    (6, 128, 128, 128, 0, 1, 3, "mse"),            # conv_norm_out + conv_out + fused eps-MSE (direct epilogue, 4 slots)
+    (3, 32, 256, 64, 64, 1, 64, "nosilu"),         # 256-pixel rows (two tiles per row), BN = 64, affine only
+])
+def test_gn_fused_into_conv_operand_is_bit_identical(dev, NB, H, W, C0, C1, div1, N, extra):
+    """XF variant of gemm_tc2 (transform warps rewrite every x-halo box in place: y = a[n,c] x + b[n,c], SiLU) vs the
+    separate gn_apply pass + plain conv: same coefficients, same fp32 arithmetic, same bf16 rounding, same K order =>
+    outputs and next-layer tile statistics are bit-identical; and within bf16 tolerance of torch's group_norm + conv2d."""
+    from dcb200 import _lib as L
+    from dcb200 import engine as E
+    torch.manual_seed(0)
+    ctx = _ctx(dev)
+    x0 = _bf(NB * H * W, C0, dev=dev) * 1.5 + 0.3
+    x1 = (_bf((NB // div1) * H * W, C1, dev=dev) * 0.7 - 0.2) if C1 else None
+    Ct = C0 + C1
+    gamma, beta = torch.randn(Ct, device=dev), torch.randn(Ct, device=dev) * 0.3
+    w = _bf(N, Ct, 3, 3, dev=dev, scale=0.05)
+    wp = w.permute(0, 2, 3, 1).reshape(N, -1).contiguous()
+    b = torch.randn(N, device=dev)
+    st0, st1 = _tile_stats(x0), (_tile_stats(x1) if C1 else None)
+    silu = extra != "nosilu"
+    kw = dict(bias=b)
+    extra_segs = ()
+    ws = None
+    if extra == "rowvec":
+        rv = torch.randn(NB, N, device=dev)
+        kw.update(rowvec=rv, rowvec_ld=N, rows_per_group=H * W, gn_stats=True)
+    elif extra == "residual":
+        res = _bf(NB * H * W, N, dev=dev)
+        kw.update(residual=res, res_ld=N, gn_stats=True)
+    elif extra == "shortcut":
+        xs = _bf(NB * H * W, 64, dev=dev)
+        ws = _bf(N, 64, dev=dev, scale=0.05)
+        wp = torch.cat([wp, ws], 1).contiguous()
+        extra_segs = [E.seg(xs, 64, H, W)]
+        kw.update(gn_stats=True)
+    elif extra == "mse":
+        tgt = torch.randn(NB * H * W, N, device=dev)
+        kw.update(want_out=False)
+    else:
+        kw.update(gn_stats=True)
+
+    def run(fuse):
+        E.FUSE_GN = fuse
+        if extra == "mse":
+            err = torch.empty(NB, device=dev)
+            kw["mse"] = dict(target=tgt, div=1, ld=N, err=err)
+        n0 = L.launch_count()
+        r = E.gn_conv3x3(ctx, x0, C0, x1, C1, NB, H, W, gamma, beta, 1e-5, silu, wp, N, div1=div1, st0=st0, st1=st1,
+                         extra_segs=extra_segs, **kw)
+        return (err,) if extra == "mse" else r, L.launch_count() - n0
+
+    try:
+        fused, n_f = run(True)
+        plain, n_p = run(False)
+    finally:
+        E.FUSE_GN = True
+    # fused: coefficient kernel + conv (+ mse finalize); plain: statistics finalize + gn_apply + conv (+ mse finalize)
+    assert n_f == n_p - 1, (n_f, n_p)
+    for a, c in zip(fused, plain):
+        assert torch.equal(a, c)
+    # torch fp32 reference of the whole thing
+    xin = x0.float().reshape(NB, H * W, C0)
+    if C1:
+        xin = torch.cat([xin, x1.float().reshape(NB // div1, H * W, C1).repeat_interleave(div1, 0)], -1)
+    y = F.group_norm(xin.permute(0, 2, 1).reshape(NB, Ct, H, W), 32, gamma, beta, 1e-5)
+    y = (F.silu(y) if silu else y).to(torch.bfloat16).float()
+    ref = F.conv2d(y, w.float(), b, padding=1).permute(0, 2, 3, 1).reshape(NB * H * W, N)
+    if extra == "rowvec":
+        ref = ref + rv.repeat_interleave(H * W, 0)
+    elif extra == "residual":
+        ref = ref + res.float()
+    elif extra == "shortcut":
+        ref = ref + xs.float() @ ws.float().t()
+    if extra == "mse":
+        want = ((ref - tgt) ** 2).reshape(NB, -1).sum(1)
+        assert rel_err(fused[0], want) < 2e-3
+    else:
+        assert rel_err(fused[0], ref) < 6e-3

@@ -225,7 +225,7 @@ def test_cuda_graph_replay_is_bit_identical_to_eager(dev):
     n0 = dcb200.launch_count()
     dc.classify(x, t_all=t_all, eps_all=eps_all)      # 8 chunks of 2 units: eager, eager, capture+replay, replay...
     n1 = dcb200.launch_count()
-    assert any(g.graph is not None for g in dc._graphs.values())
+    assert any(g["obj"].graph is not None for g in dc._graphs.d.values())
     assert torch.equal(dc.last_errors, eager)
     dc.classify(x, t_all=t_all, eps_all=eps_all)      # all replays
     assert torch.equal(dc.last_errors, eager)
