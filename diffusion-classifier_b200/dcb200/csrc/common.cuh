@@ -66,12 +66,15 @@ __device__ __forceinline__ float gelu_tanh_fast_f(float x) {
   const float hx = 0.5f * x;
   return fmaf(hx, tanh_approx_f(u), hx);
 }
-// SiLU of the GroupNorm kernels (bf16 tensors): x * sigmoid(x), sigmoid = 0.5 tanh(0.5 x) + 0.5 -> ONE MUFU op per element.
-// gn_apply_kernel and the fused transform of gemm_tc2's XF variant must produce the same bits: both call this.
-__device__ __forceinline__ float gn_silu_bf16(float y) {
+// Activation of the GroupNorm kernels on bf16 tensors.  The normalisation is y = a x + b; with SiLU the kernels carry the
+// HALVED coefficients, h = (a/2) x + (b/2) = y/2 (exact), and SiLU(y) = y sigmoid(y) = y (0.5 tanh(y/2) + 0.5) = h tanh(h) + h:
+// one FMA, one MUFU op, one FMA per element.  gn_apply_kernel and the fused transform of gemm_tc2x_kernel must produce the
+// same bits: both call this on h.
+__device__ __forceinline__ float gn_act_bf16(float h, int silu) {
+  if (!silu) return h;
   float t;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * y));
-  return y * fmaf(0.5f, t, 0.5f);
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
 }
 __device__ __forceinline__ float rcp_approx_f(float x) {
   float y;

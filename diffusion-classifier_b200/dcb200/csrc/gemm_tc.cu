@@ -39,6 +39,7 @@ struct TcParams {
   uint32_t idesc;
   int conv9, nkb_conv;  // segments 0..8 are the taps of one 3x3 conv (any stride): issue them (ky, channel block, kx)
   int kx_outer;         // ... or (kx, channel block, ky): stride-1 convs with OW < 128, the order of gemm_tc2's y-halo mode
+  int kb_outer;         // ... or (channel block, ky, kx): stride-1 convs with OW >= 128, the order of gemm_tc2x's row boxes
   int staged;   // epilogue through the swizzled smem staging tile + coalesced second pass
   int uniform;  // every row of an M tile belongs to one rowvec/gate group (tile-constant vectors live in smem)
 };
@@ -128,6 +129,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           for (int kx = 0; kx < 3; ++kx)
             for (int kb = 0; kb < p.nkb_conv; ++kb)
               for (int ky = 0; ky < 3; ++ky) issue(p.seg[ky * 3 + kx], nbs, kb, (ky * 3 + kx) * p.nkb_conv + kb);
+        } else if (p.kb_outer) {
+          for (int kb = 0; kb < p.nkb_conv; ++kb)
+            for (int ky = 0; ky < 3; ++ky)
+              for (int kx = 0; kx < 3; ++kx) issue(p.seg[ky * 3 + kx], nbs, kb, (ky * 3 + kx) * p.nkb_conv + kb);
         } else {
           for (int ky = 0; ky < 3; ++ky)
             for (int kb = 0; kb < p.nkb_conv; ++kb)
@@ -294,6 +299,9 @@ bool is_conv9(const GemmDev& g) {
 // gemm_tc2 then serves the three ky taps of a (kx, channel block) from one y-halo box -- else (ky, channel block, kx), the
 // order of its x-halo boxes.  Every tcgen05 code path follows the same rule, so results do not depend on the kernel chosen.
 bool conv9_kx_outer(const GemmDev& g) { return is_conv9(g) && g.seg[0].stride == 1 && g.OW < 128; }
+// ... and (channel block, ky, kx) when the rows fill whole tiles (stride 1, OW >= 128): gemm_tc2x then keeps the four input
+// rows of a channel block that two vertically adjacent output rows need in shared memory and serves all nine taps from them
+bool conv9_kb_outer(const GemmDev& g) { return is_conv9(g) && g.seg[0].stride == 1 && g.OW >= 128; }
 
 struct TcGeom {
   int bw, bh, bn, tiles_x, tiles_y, tiles_nb, BN, n_tiles;
@@ -386,7 +394,8 @@ static int encode_a_map(CUtensorMap* map, const SegDev& s, int NBsrc, const TcGe
 }
 
 int launch_gemm_tc2(const GemmDev& g, cudaStream_t st, int bw, int bh, int bn, int tiles_x, int tiles_y, int tiles_nb,
-                    int BN, int uniform, int staged, bool dry_run);
+                    int BN, int uniform, int staged);
+int launch_gemm_tc2x(const GemmDev& g, cudaStream_t st, int tiles_x, int BN, int uniform, int staged, bool dry_run);
 
 // dry_run: everything but the launch (dcb_gemm_xf_layout: would this descriptor run on the kernel that can apply a fused
 // GroupNorm transform?)
@@ -442,6 +451,7 @@ int launch_gemm_tc(const GemmDev& g, cudaStream_t st, bool dry_run) {
   for (int j = nmaps; j < 3; ++j) maps[j] = maps[0];
   p.conv9 = is_conv9(g);
   p.kx_outer = conv9_kx_outer(g);
+  p.kb_outer = conv9_kb_outer(g);
   p.nkb_conv = p.conv9 ? g.seg[0].kc / TC_BK : 0;
 
   CUtensorMap mapB;
@@ -487,8 +497,8 @@ int launch_gemm_tc(const GemmDev& g, cudaStream_t st, bool dry_run) {
                       e.act != DCB_ACT_GEGLU && e.gn_part == nullptr && e.mse_part == nullptr && e.out != nullptr &&
                       e.out_dtype == DCB_BF16 && e.out_ld % 8 == 0 && ((uintptr_t)e.out % 16) == 0 && !is_conv9(g) &&
                       t.bn == 1 && (m_tiles / 2) * (e.N / 256) >= 2 * num_sms();
-    if (wide && g.xf_a == nullptr) {
-      rc = launch_gemm_tc2(g, st, t.bw, t.bh, t.bn, t.tiles_x, t.tiles_y, t.tiles_nb, 256, p.uniform, 0, dry_run);
+    if (wide && g.xf_a == nullptr && !dry_run) {
+      rc = launch_gemm_tc2(g, st, t.bw, t.bh, t.bn, t.tiles_x, t.tiles_y, t.tiles_nb, 256, p.uniform, 0);
       if (rc != DCB_EUNSUPPORTED) return rc;
     }
   }
@@ -498,11 +508,18 @@ int launch_gemm_tc(const GemmDev& g, cudaStream_t st, bool dry_run) {
                         (g.OH * g.OW) % TC_BM == 0 && !(knobs() & DCB_KNOB_NO_TC2_MSE);
   if ((p.staged || mse_only) && t.BN <= 128 && g.epi.act != DCB_ACT_GEGLU && !(knobs() & DCB_KNOB_NO_TC2) &&
       t.tiles_x * t.tiles_y * t.tiles_nb * t.n_tiles >= 4 * num_sms()) {
-    rc = launch_gemm_tc2(g, st, t.bw, t.bh, t.bn, t.tiles_x, t.tiles_y, t.tiles_nb, t.BN, p.uniform, p.staged, dry_run);
-    if (rc != DCB_EUNSUPPORTED) return rc;
+    if (g.xf_a != nullptr) {     // fused GroupNorm: the row-box kernel (gemm_tc2x.cu) or nothing
+      if (t.bw == 128 && t.bh == 1 && t.bn == 1) {
+        rc = launch_gemm_tc2x(g, st, t.tiles_x, t.BN, p.uniform, p.staged, dry_run);
+        if (rc != DCB_EUNSUPPORTED) return rc;
+      }
+    } else if (!dry_run) {
+      rc = launch_gemm_tc2(g, st, t.bw, t.bh, t.bn, t.tiles_x, t.tiles_y, t.tiles_nb, t.BN, p.uniform, p.staged);
+      if (rc != DCB_EUNSUPPORTED) return rc;
+    }
   }
   if (g.xf_a != nullptr) {
-    if (!dry_run) set_error("gemm: xf_a (fused GroupNorm) needs the x-halo mode of gemm_tc2 -- ask dcb_gemm_xf_layout first");
+    if (!dry_run) set_error("gemm: xf_a (fused GroupNorm) needs the row-box kernel -- ask dcb_gemm_xf_layout first");
     return DCB_EUNSUPPORTED;
   }
   if (dry_run) return DCB_OK;

@@ -19,11 +19,6 @@ namespace dcb {
 constexpr int T2_THREADS = 352;  // TMA warp, 2 MMA warps (one per sub-tile), 2 epilogue groups x 4 warps (group g drains sub-tile g)
 constexpr int T2_MAX_SLOTS = 8;
 constexpr int T2_HALO_SUB = 17 * 1024;  // 130 rows x 128 B = 16640 B, padded to the 1024-B swizzle repeat
-// XF variant (fused GroupNorm): 8 more warps (two groups of 4, one per sub-tile) rewrite every x-halo box in place --
-// y = a[n, c] x + b[n, c] (+ SiLU), the arithmetic of gn_apply_kernel -- between the TMA landing and the MMAs, so the
-// normalised tensor is never written to / re-read from HBM (dcb_gemm_desc.xf_a).
-constexpr int T2_XF_WARPS = 8;
-constexpr int T2_THREADS_XF = T2_THREADS + 32 * T2_XF_WARPS;   // 608
 
 struct Tc2Params {
   int nseg;
@@ -35,6 +30,7 @@ struct Tc2Params {
   int halo_jstep;   // descriptor-word step between the three taps served by one box: 8 (one 128-B row) or OW * 8
   int halo_bytes;   // bytes of one halo item (expect_tx)
   int kx_outer;     // conv9 issued (kx, channel block, ky) (see conv9_kx_outer in gemm_tc.cu)
+  int kb_outer;     // conv9 issued (channel block, ky, kx) (see conv9_kb_outer in gemm_tc.cu)
   int nkb_conv;  // K blocks per tap of that conv (Cin / 64)
   int halo_div;  // nb_div of the halo source
   int conv9;     // segments 0..8 are one 3x3 conv (halo or not): K blocks are issued in (ky, channel block, kx) order
@@ -47,14 +43,6 @@ struct Tc2Params {
                                                   // mode, BN = 256) 1 stage x 2 sub-tiles x 256 columns
   int staged;    // 0: direct epilogue (fused eps-MSE of conv_out: nothing is written but per-tile partial sums)
   int dbg;  // experiments: 1 = no TMA traffic (barriers only), 2 = no epilogue work, 4 = no MMA issue
-  // XF variant only
-  const float* xf_a;   // [NB][xf_C] per-(sample, channel) scale / offset of the fused GroupNorm
-  const float* xf_b;
-  int xf_C;            // channels of the (concatenated) normalised tensor = nkb_conv * 64
-  int xf_nkb0;         // channel blocks read from halo source 0 (map 0); blocks >= xf_nkb0 come from source 1 (map 1)
-  int xf_div1;         // nb_div of halo source 1
-  int xf_silu;
-  int single_stg;      // both epilogue groups share ONE staging tile (ping-pong): room for a third activation slot
 };
 
 struct SubTile {
@@ -74,8 +62,7 @@ __device__ __forceinline__ SubTile decode_sub(const Tc2Params& p, int tm_lin) {
   return s;
 }
 
-template <bool XF>
-__global__ void __launch_bounds__(XF ? T2_THREADS_XF : T2_THREADS, 1)
+__global__ void __launch_bounds__(T2_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                 const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB,
                 const __grid_constant__ Tc2Params p, const __grid_constant__ EpiDev e) {
@@ -93,7 +80,6 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
   uint64_t* tempty_bar = tfull_bar + 4;            // [2 TMEM stages][2 sub-tiles]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 4);
   float* mse_smem = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 384);  // [2 groups][4 warps]
-  uint64_t* a_ready = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(bars) + 416);  // [T2_MAX_SLOTS], XF only
   uint8_t* stg8 = reinterpret_cast<uint8_t*>(bars) + 512;
 
   // warp-uniform role dispatch (see gemm_tc.cu): loop state and descriptors stay in uniform registers
@@ -105,8 +91,6 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
     for (int i = 0; i < p.a_slots; ++i) { mbar_init(smem_u32(&a_full[i]), 1); mbar_init(smem_u32(&a_empty[i]), 2); }
     for (int i = 0; i < p.b_slots; ++i) { mbar_init(smem_u32(&b_full[i]), 1); mbar_init(smem_u32(&b_empty[i]), 2); }
     for (int i = 0; i < 4; ++i) { mbar_init(smem_u32(&tfull_bar[i]), 1); mbar_init(smem_u32(&tempty_bar[i]), 4); }
-    if (XF)   // one arrive per transform warp once the slot holds the normalised operand
-      for (int i = 0; i < p.a_slots; ++i) mbar_init(smem_u32(&a_ready[i]), T2_XF_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -170,26 +154,19 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
           }
       } else if (p.halo) {
         const int h0 = p.halo_div > 1 ? s0.nb0 / p.halo_div : s0.nb0, h1 = p.halo_div > 1 ? s1.nb0 / p.halo_div : s1.nb0;
-        for (int ky = 0; ky < 3; ++ky)
-          for (int kb = 0; kb < p.nkb_conv; ++kb) {
+        // items in (channel block, ky) order when kb_outer (stride 1, OW >= 128: always true here), else (ky, channel block)
+        const int n_items = 3 * p.nkb_conv;
+        for (int it = 0; it < n_items; ++it) {
+            const int ky = p.kb_outer ? it % 3 : it / p.nkb_conv, kb = p.kb_outer ? it / 3 : it % p.nkb_conv;
             if (dbg & 64) mbar_spin(a_empty0 + ai * 8, aph ^ 1); else mbar_wait(a_empty0 + ai * 8, aph ^ 1);
-            // XF: the normalised tensor may be the concatenation of two raw sources (up-path skip): channel blocks
-            // >= xf_nkb0 are read from the second one (map 1, its own sample divisor)
-            const bool second = XF && kb >= p.xf_nkb0;
             if (elect_one()) {
               const uint32_t fa = a_full0 + ai * 8;
               const uint32_t sa = a_ring0 + (uint32_t)(ai * p.a_slot_bytes);
               if (no_tma) mbar_arrive(fa);
               else {
                 mbar_expect_tx(fa, 2u * 130u * 128u);
-                if (second) {
-                  const int g0 = p.xf_div1 > 1 ? s0.nb0 / p.xf_div1 : s0.nb0, g1 = p.xf_div1 > 1 ? s1.nb0 / p.xf_div1 : s1.nb0;
-                  tma_load_5d(sa, &mapA1, fa, (kb - p.xf_nkb0) * TC_BK, s0.x0 - 1, 0, s0.y0 + ky - 1, g0);
-                  tma_load_5d(sa + T2_HALO_SUB, &mapA1, fa, (kb - p.xf_nkb0) * TC_BK, s1.x0 - 1, 0, s1.y0 + ky - 1, g1);
-                } else {
-                  tma_load_5d(sa, &mapA0, fa, kb * TC_BK, s0.x0 - 1, 0, s0.y0 + ky - 1, h0);
-                  tma_load_5d(sa + T2_HALO_SUB, &mapA0, fa, kb * TC_BK, s1.x0 - 1, 0, s1.y0 + ky - 1, h1);
-                }
+                tma_load_5d(sa, &mapA0, fa, kb * TC_BK, s0.x0 - 1, 0, s0.y0 + ky - 1, h0);
+                tma_load_5d(sa + T2_HALO_SUB, &mapA0, fa, kb * TC_BK, s1.x0 - 1, 0, s1.y0 + ky - 1, h1);
               }
             }
             __syncwarp();
@@ -222,6 +199,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
           for (int kx = 0; kx < 3; ++kx)
             for (int kb = 0; kb < p.nkb_conv; ++kb)
               for (int ky = 0; ky < 3; ++ky) issue_tap(p.seg[ky * 3 + kx], kb, (ky * 3 + kx) * p.nkb_conv + kb);
+        } else if (p.kb_outer) {
+          for (int kb = 0; kb < p.nkb_conv; ++kb)
+            for (int ky = 0; ky < 3; ++ky)
+              for (int kx = 0; kx < 3; ++kx) issue_tap(p.seg[ky * 3 + kx], kb, (ky * 3 + kx) * p.nkb_conv + kb);
         } else {
           for (int ky = 0; ky < 3; ++ky)
             for (int kb = 0; kb < p.nkb_conv; ++kb)
@@ -259,9 +240,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
     const uint32_t a_lo_tap_base = (((a_ring0 + (uint32_t)sub * (uint32_t)TC_A_BYTES) & 0x3FFFFu) >> 4) | (1u << 16);
     const uint32_t b_lo_base = ((b_ring0 & 0x3FFFFu) >> 4) | (1u << 16);
     uint32_t a_off = 0, b_lo = b_lo_base;           // a_off: (slot index * slot bytes) >> 4
-    // XF: the activation slot is ready when the transform warps have rewritten it (they wait for the TMA themselves)
-    const uint32_t a_wait0 = XF ? smem_u32(a_ready) : a_full0;
-    uint32_t a_fb = a_wait0, a_eb = a_empty0, b_fb = b_full0, b_eb = b_empty0;
+    uint32_t a_fb = a_full0, a_eb = a_empty0, b_fb = b_full0, b_eb = b_empty0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       { long long c0 = prof ? clock64() : 0; mbar_wait(smem_u32(&tempty_bar[as * 2 + sub]), aphase ^ 1); if (prof) w_te += clock64() - c0; }
       const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.acc_stage_cols + sub * p.acc_sub_cols);
@@ -305,22 +284,18 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
           if (++bi == p.b_slots) { bi = 0; bph ^= 1; b_lo = b_lo_base; b_fb = b_full0; b_eb = b_empty0; }
         }
         a_off += a_step; a_fb += 8; a_eb += 8;
-        if (++ai == p.a_slots) { ai = 0; aph ^= 1; a_off = 0; a_fb = a_wait0; a_eb = a_empty0; }
+        if (++ai == p.a_slots) { ai = 0; aph ^= 1; a_off = 0; a_fb = a_full0; a_eb = a_empty0; }
       }
       if (++as == p.acc_stages) { as = 0; aphase ^= 1; }
     }
     if (prof && (blockIdx.x % 21 == 0) && lane == 0)
       printf("tc2 block %d mma warp %d: total %lld cycles, waits: tempty %lld a_full %lld b_full %lld; mma issue %lld commits %lld (tiles %d, k-blocks/tile %d)\n", (int)blockIdx.x, sub,
              clock64() - t_all, w_te, w_a, w_b, w_iss, w_com, (p.total_tiles + (int)gridDim.x - 1) / (int)gridDim.x, items + 2 * halo_items);
-  } else if (!XF || warp <= 10) {
+  } else {
     // ===================== epilogue: warps 3..6 drain sub-tile 0, warps 7..10 sub-tile 1, concurrently =====================
     const int q = warp & 3;             // TMEM lane quarter this warp may access
     const int grp = (warp - 3) >> 2;    // epilogue group == sub-tile == accumulator half
-    // XF: ONE staging tile, used alternately (group 0 of tile k, group 1 of tile k, group 0 of tile k + 1, ...; named
-    // barriers 3 / 4 hand it over) -- the 36 KB this frees hold the third activation slot the transform stage needs.
-    // Two serialised epilogues (~6 k cycles) still fit under the >= 9 k cycle main loop of a K >= 1152 tile.
-    const bool pingpong = XF && p.single_stg && p.staged;
-    uint8_t* my_stg = stg8 + (pingpong ? 0 : grp * TC_EPI_BYTES);
+    uint8_t* my_stg = stg8 + grp * TC_EPI_BYTES;
     EpiGeom gq{p.tiles_x, p.tiles_y, p.bw, p.bh, p.bn, p.OW, p.OH, p.NB, p.uniform};
     int as = 0;
     uint32_t aphase = 0;
@@ -337,13 +312,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
         continue;
       }
       if (p.staged) {
-        if (pingpong && (grp == 1 || it > 0)) bar_sync_n(grp == 0 ? 4 : 3, 256);    // the other group has left the tile
         staged_epilogue(gq, e, my_stg, it & 1, 2 * tp + grp, tn, p.BN, taddr, smem_u32(&tfull_bar[as * 2 + grp]), aphase, true,
                         smem_u32(&tempty_bar[as * 2 + grp]), true, 1 + grp);
-        if (pingpong) {
-          epi_bar(1 + grp);                          // every thread of this group is done with the staging tile
-          if (grp == 1 ? (tile + (int)gridDim.x < p.total_tiles) : true) bar_arrive_n(grp == 0 ? 3 : 4, 256);
-        }
       } else {
         // direct epilogue (same arithmetic and summation order as gemm_tc_kernel's): thread-per-row over the BN columns,
         // fused eps-MSE -> one partial per 128-row sub-tile
@@ -383,72 +353,6 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
       }
       if (++as == p.acc_stages) { as = 0; aphase ^= 1; }
     }
-  } else {
-    // ===================== XF: GroupNorm(+SiLU) transform of the landed x-halo boxes, in place =====================
-    // warps 11..14 rewrite sub-tile 0's box, warps 15..18 sub-tile 1's: thread t of a group owns the logical 16-byte chunk
-    // l = t & 7 (channels c0 + 8 l .. + 7: its 16 coefficients stay in registers for the whole box) of rows t >> 3,
-    // + 16, ...; the 128-byte swizzle puts that chunk at physical chunk l ^ (row & 7).  Rows outside the image (the x
-    // halo at the borders, whole boxes above / below it, the odd tail sub-tile) must stay zero = the conv padding.
-    const int tw = warp - 11;
-    const int sub = tw >> 2;
-    const int t = ((tw & 3) << 5) + lane;
-    const int l = t & 7, r0 = t >> 3;
-    const uint32_t a_ready0 = smem_u32(a_ready);
-    int ai = 0;
-    uint32_t aph = 0;
-    int tap_items = 0;
-    for (int s = first_tap_seg; s < p.nseg; ++s) tap_items += p.seg[s].nkb;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const int tp = tile / p.n_tiles;
-      const int tm_lin = 2 * tp + sub;
-      const SubTile st = decode_sub(p, tm_lin);
-      const bool tile_ok = tm_lin < p.m_tiles;
-      for (int ky = 0; ky < 3; ++ky) {
-        const int y = st.y0 + ky - 1;
-        const bool box_ok = tile_ok && y >= 0 && y < p.OH;
-        for (int kb = 0; kb < p.nkb_conv; ++kb) {
-          float ca[8], cb[8];
-          if (box_ok) {      // issued ahead of the wait: the loads fly while the TMA lands
-            const float4* pa = reinterpret_cast<const float4*>(p.xf_a + (int64_t)st.nb0 * p.xf_C + kb * TC_BK + l * 8);
-            const float4* pb = reinterpret_cast<const float4*>(p.xf_b + (int64_t)st.nb0 * p.xf_C + kb * TC_BK + l * 8);
-            const float4 a0 = __ldg(pa), a1 = __ldg(pa + 1), b0 = __ldg(pb), b1 = __ldg(pb + 1);
-            ca[0] = a0.x; ca[1] = a0.y; ca[2] = a0.z; ca[3] = a0.w; ca[4] = a1.x; ca[5] = a1.y; ca[6] = a1.z; ca[7] = a1.w;
-            cb[0] = b0.x; cb[1] = b0.y; cb[2] = b0.z; cb[3] = b0.w; cb[4] = b1.x; cb[5] = b1.y; cb[6] = b1.z; cb[7] = b1.w;
-          }
-          mbar_wait(a_full0 + ai * 8, aph);
-          if (box_ok) {
-            const uint32_t base = a_ring0 + (uint32_t)(ai * p.a_slot_bytes) + (uint32_t)sub * (uint32_t)T2_HALO_SUB;
-#pragma unroll 3
-            for (int r = r0; r < 130; r += 16) {
-              const int x = st.x0 - 1 + r;
-              if (x < 0 || x >= p.OW) continue;
-              const uint32_t addr = base + (uint32_t)(r * 128) + (uint32_t)((l ^ (r & 7)) << 4);
-              uint4 v;
-              asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
-              float f[8];
-              unpack_bf16x8(v, f);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float yv = fmaf(f[i], ca[i], cb[i]);
-                f[i] = p.xf_silu ? gn_silu_bf16(yv) : yv;
-              }
-              v = pack_bf16x8(f);
-              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA's reads
-          }
-          __syncwarp();
-          if (lane == 0) mbar_arrive(a_ready0 + ai * 8);
-          if (++ai == p.a_slots) { ai = 0; aph ^= 1; }
-        }
-      }
-      for (int k = 0; k < tap_items; ++k) {      // plain tap segments (1x1 shortcut over raw tensors): pass through
-        mbar_wait(a_full0 + ai * 8, aph);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(a_ready0 + ai * 8);
-        if (++ai == p.a_slots) { ai = 0; aph ^= 1; }
-      }
-    }
   }
 
   tc_fence_before();
@@ -463,6 +367,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
 PFN_cuTensorMapEncodeTiled_v12000 tc_encode_fn();
 bool is_conv9(const GemmDev& g);
 bool conv9_kx_outer(const GemmDev& g);
+bool conv9_kb_outer(const GemmDev& g);
 
 static int encode_map(CUtensorMap* map, const SegDev& s, int NBsrc, int bx, int by, int bnb) {
   auto enc = tc_encode_fn();
@@ -487,12 +392,11 @@ static int encode_map(CUtensorMap* map, const SegDev& s, int NBsrc, int bx, int 
 
 // returns DCB_EUNSUPPORTED when the descriptor does not fit this kernel (the caller falls back to gemm_tc_kernel)
 int launch_gemm_tc2(const GemmDev& g, cudaStream_t st, int bw, int bh, int bn, int tiles_x, int tiles_y, int tiles_nb,
-                    int BN, int uniform, int staged, bool dry_run) {
+                    int BN, int uniform, int staged) {
   const EpiDev& e = g.epi;
   Tc2Params p;
   memset(&p, 0, sizeof(p));
   p.staged = staged;
-  const bool xf = g.xf_a != nullptr;    // fused GroupNorm: only the x-halo mode of this kernel can apply it
   // wide mode (BN = 256): two 128 x 256 accumulators fill the 512 TMEM columns, so there is one accumulator stage -- the
   // MMAs of the next tile wait for the epilogue -- in exchange for 64 instead of 94 B/clk/SM of operand traffic
   DCB_REQUIRE(BN <= 128 || (BN == 256 && !staged), "gemm_tc2: BN = 256 needs the direct epilogue");
@@ -521,7 +425,6 @@ int launch_gemm_tc2(const GemmDev& g, cudaStream_t st, int bw, int bh, int bn, i
            s.kc == s.C && s.dy == i / 3 - 1 && s.dx == i % 3 - 1 && s.nb_div == g.seg[0].nb_div;
   }
   for (int i = 9; halo && i < g.nseg; ++i) halo = g.seg[i].src != g.seg[0].src;
-  if (xf && !halo) return DCB_EUNSUPPORTED;
   // y-halo mode: rows narrower than a tile (a sub-tile = bh full rows of one sample), sub-tile pairs stacked vertically
   bool yhalo = !halo && g.nseg >= 9 && g.OW < 128 && bw == g.OW && bn == 1 && tiles_x == 1 && tiles_y % 2 == 0 &&
                bh * bw == TC_BM && !(knobs() & DCB_KNOB_TC2_NO_YHALO);
@@ -536,17 +439,10 @@ int launch_gemm_tc2(const GemmDev& g, cudaStream_t st, int bw, int bh, int bn, i
   p.halo_bytes = yhalo ? (2 * bh + 2) * g.OW * 128 : 2 * 130 * 128;
   halo = halo || yhalo;
   p.kx_outer = conv9_kx_outer(g);
+  p.kb_outer = conv9_kb_outer(g);
   p.conv9 = is_conv9(g);
   p.nkb_conv = (halo || p.conv9) ? g.seg[0].kc / TC_BK : 0;
   p.halo_div = halo ? g.seg[0].nb_div : 1;
-  if (xf) {
-    p.xf_nkb0 = p.nkb_conv;
-    p.nkb_conv += g.xf_c1 / TC_BK;       // K blocks per tap over the concatenated (source 0 | source 1) channels
-    p.xf_a = g.xf_a; p.xf_b = g.xf_b;
-    p.xf_C = p.nkb_conv * TC_BK;
-    p.xf_div1 = g.xf_div1 > 1 ? g.xf_div1 : 1;
-    p.xf_silu = g.xf_silu;
-  }
 
   CUtensorMap maps[3];
   memset(maps, 0, sizeof(maps));
@@ -560,15 +456,6 @@ int launch_gemm_tc2(const GemmDev& g, cudaStream_t st, int bw, int bh, int bn, i
     map_key[0] = g.seg[0];
     map_key[0].src = nullptr;  // never matches a tap segment: the halo map has a different box
     nmaps = 1;
-    if (xf && g.xf_c1 > 0) {   // second raw source of the concatenated normalised tensor: its own halo map (map 1)
-      SegDev s1 = g.seg[0];
-      s1.src = g.xf_src1; s1.C = g.xf_c1; s1.kc = g.xf_c1; s1.nb_div = p.xf_div1;
-      rc = encode_map(&maps[1], s1, (g.NB + p.xf_div1 - 1) / p.xf_div1, 130, 1, 1);
-      if (rc) return rc;
-      map_key[1] = s1;
-      map_key[1].src = nullptr;
-      nmaps = 2;
-    }
   }
   for (int i = halo ? 9 : 0; i < g.nseg; ++i) {
     const SegDev& s = g.seg[i];
@@ -622,9 +509,7 @@ int launch_gemm_tc2(const GemmDev& g, cudaStream_t st, int bw, int bh, int bn, i
   // (6 K blocks) + 5 B slots, but tap-mode GEMMs (the K <= 768 projections) were A-ring bound with 2 slots -- with 3 + 3
   // the same kernel moves 20 % more (measured: 782 -> 941 TF/s at M=204800, K=N=768).
   const int kb_per_a = halo ? 3 : 1;
-  // (XF: one staging tile shared by the two epilogue groups -- the transform stage needs a third activation slot)
-  p.single_stg = xf ? 1 : 0;
-  const int epi_bytes = staged ? (xf ? 1 : 2) * TC_EPI_BYTES : 0;   // the direct epilogues need no staging tiles: deeper rings
+  const int epi_bytes = staged ? 2 * TC_EPI_BYTES : 0;   // the direct epilogues need no staging tiles: deeper rings
   const int ring_bytes = TC_SMEM_LIMIT - (1024 + 512 + epi_bytes);
   int best_a = 2, best_score = -1;
   for (int a = 2; a <= 4; ++a) {
@@ -635,7 +520,6 @@ int launch_gemm_tc2(const GemmDev& g, cudaStream_t st, int bw, int bh, int bn, i
     if (score > best_score) { best_score = score; best_a = a; }
   }
   p.a_slots = best_a;
-  if (xf) p.a_slots = staged ? 3 : 4;     // TMA landing | being transformed | being consumed (+1 when smem allows)
 #ifdef DCB_PROBES
   if (getenv("DCB_TC2_ASLOTS")) p.a_slots = atoi(getenv("DCB_TC2_ASLOTS"));
 #endif
@@ -650,16 +534,13 @@ int launch_gemm_tc2(const GemmDev& g, cudaStream_t st, int bw, int bh, int bn, i
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
 
   const size_t smem = (size_t)fixed + (size_t)b_slots * b_bytes;
-  if (dry_run) return DCB_OK;
   static std::once_flag attr_once;
   std::call_once(attr_once, [] {
-    cudaFuncSetAttribute(gemm_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT);
-    cudaFuncSetAttribute(gemm_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT);
+    cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT);
   });
   const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-  if (xf) gemm_tc2_kernel<true><<<grid, T2_THREADS_XF, smem, st>>>(maps[0], maps[1], maps[2], mapB, p, e);
-  else gemm_tc2_kernel<false><<<grid, T2_THREADS, smem, st>>>(maps[0], maps[1], maps[2], mapB, p, e);
-  DCB_CHECK_LAUNCH(xf ? "gemm_tc2<xf>" : "gemm_tc2");
+  gemm_tc2_kernel<<<grid, T2_THREADS, smem, st>>>(maps[0], maps[1], maps[2], mapB, p, e);
+  DCB_CHECK_LAUNCH("gemm_tc2");
   return DCB_OK;
 }
 

@@ -99,14 +99,20 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const T* __restric
   if (threadIdx.x < G) { out[threadIdx.x * 2] = gsum; out[threadIdx.x * 2 + 1] = gsq; }
 }
 
-// SiLU for the bf16 path: x * sigmoid(x) with sigmoid = 0.5*tanh(0.5x)+0.5 -> ONE MUFU op per element (the exp+rcp
-// form needs two and made this kernel SFU-bound: 16 MUFU/clk/SM); tanh.approx error (~2^-11) is below bf16 rounding.
+// bf16 tensors: y = a x + b, then SiLU through gn_act_bf16 on HALVED coefficients (common.cuh; one MUFU op per element --
+// the exp + rcp form needs two and made this kernel SFU-bound); fp32 (verify engine) keeps the exact form
 template <typename T>
-__device__ __forceinline__ float gn_silu(float y);
+struct GnAct;
 template <>
-__device__ __forceinline__ float gn_silu<float>(float y) { return silu_f(y); }
+struct GnAct<float> {
+  static constexpr bool HALVE = false;
+  __device__ static float apply(float y, int silu) { return silu ? silu_f(y) : y; }
+};
 template <>
-__device__ __forceinline__ float gn_silu<__nv_bfloat16>(float y) { return gn_silu_bf16(y); }
+struct GnAct<__nv_bfloat16> {
+  static constexpr bool HALVE = true;
+  __device__ static float apply(float h, int silu) { return gn_act_bf16(h, silu); }
+};
 
 // ---- GroupNorm apply (+SiLU), writes the concatenated normalised tensor [NB,HW,C0+C1] ----------------------
 // thread -> fixed 16-byte channel slot (coefficients live in registers), loops over pixels with 4 loads in flight
@@ -192,7 +198,8 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const T* __restric
     for (int i = 0; i < VN; ++i) {
       const int g = (c + i) / cpg;
       ca[i] = s_rstd[g] * gamma[c + i];
-      cbias[i] = __fmaf_rn(-s_mean[g], ca[i], beta[c + i]);     // written out: gn_coef_kernel must produce the same bits
+      cbias[i] = __fmaf_rn(-s_mean[g], ca[i], beta[c + i]);     // written out: gn_tiles_finalize_kernel must produce the same bits
+      if (GnAct<T>::HALVE && silu) { ca[i] *= 0.5f; cbias[i] *= 0.5f; }
     }
     const T* base;
     int cs;
@@ -209,8 +216,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const T* __restric
         if (p + u * nrows < p1) {
 #pragma unroll
           for (int i = 0; i < VN; ++i) {
-            const float y = fmaf(f[u][i], ca[i], cbias[i]);
-            f[u][i] = silu ? gn_silu<T>(y) : y;
+            f[u][i] = GnAct<T>::apply(fmaf(f[u][i], ca[i], cbias[i]), silu);
           }
           Vec<T>::store(obase + (int64_t)(p + u * nrows) * C, f[u]);
         }

@@ -478,7 +478,7 @@ def _tile_stats(x):
     (5, 128, 128, 128, 0, 1, 128, "residual"),     # resnet conv2 with identity shortcut
     (5, 128, 128, 128, 0, 1, 128, "shortcut"),     # resnet conv2 + 1x1 conv_shortcut over the raw (concatenated) input
     (6, 128, 128, 128, 0, 1, 3, "mse"),            # conv_norm_out + conv_out + fused eps-MSE (direct epilogue, 4 slots)
-    (3, 32, 256, 64, 64, 1, 64, "nosilu"),         # 256-pixel rows (two tiles per row), BN = 64, affine only
+    (10, 32, 256, 64, 64, 1, 64, "nosilu"),        # 256-pixel rows (two tiles per row), BN = 64, affine only
 ])
 def test_gn_fused_into_conv_operand_is_bit_identical(dev, NB, H, W, C0, C1, div1, N, extra):
     """XF variant of gemm_tc2 (transform warps rewrite every x-halo box in place: y = a[n,c] x + b[n,c], SiLU) vs the
