@@ -11,7 +11,10 @@
 // (conv9_kb_outer in gemm_tc.cu).  Compared with per-(ky) halo boxes (gemm_tc2's x-halo mode) the activation traffic
 // L2 -> SMEM and the transform work drop by a third (4 instead of 6 boxes per channel block).
 //
-//   warp 0        TMA producer (row boxes, weight blocks, plain tap tiles of trailing 1x1 segments)
+//   warp 0        TMA producer of the activations (row boxes, plain tap tiles of trailing 1x1 segments)
+//   warp 19       TMA producer of the weight blocks -- its own warp: with one in-order producer the weight ring's depth
+//                 (5 blocks = 2.5 k cycles) also capped how far ahead of the MMAs a row box could be requested, and a box
+//                 needs TMA latency + the transform before it is usable (measured: 737 -> see DESIGN.md)
 //   warps 1, 2    MMA issuers, one per output row (accumulator); tcgen05.commit releases boxes / weight blocks
 //   warps 3..10   two epilogue groups (staged epilogue of tc_common.cuh through ONE shared staging tile, handed over by
 //                 named barriers -- the freed 36 KB are two more row boxes -- or the direct eps-MSE epilogue of conv_out)
@@ -25,7 +28,7 @@
 
 namespace dcb {
 
-constexpr int TX_THREADS = 608;
+constexpr int TX_THREADS = 640;
 constexpr int TX_MAX_SLOTS = 8;
 constexpr int TX_BOX = 17 * 1024;      // 130 rows x 128 B = 16640 B, padded to the 1024-B swizzle repeat
 constexpr int TX_XF_WARPS = 8;
@@ -39,6 +42,8 @@ struct TxParams {
   int nbox, b_slots;
   uint32_t idesc;
   int uniform, staged, silu, xf_C;
+  int two_stg;                 // each epilogue group has its own staging tile (no hand-over)
+  int dbg;                     // -DDCB_PROBES builds only: 1 = no transform arithmetic, 2 = no epilogue work
   const float* xf_a;           // [NB][xf_C]
   const float* xf_b;
 };
@@ -101,6 +106,11 @@ gemm_tc2x_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+#ifdef DCB_PROBES
+  const int dbg = p.dbg;
+#else
+  constexpr int dbg = 0;
+#endif
 
   const uint32_t a_ring0 = smem_u32(a_ring), b_ring0 = smem_u32(b_ring);
   const uint32_t a_full0 = smem_u32(a_full), a_ready0 = smem_u32(a_ready), a_empty0 = smem_u32(a_empty);
@@ -110,21 +120,10 @@ gemm_tc2x_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    int ai = 0, bi = 0;
-    uint32_t aph = 0, bph = 0;
+    int ai = 0;
+    uint32_t aph = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const int tn = tile % p.n_tiles;
       const TxPair t = decode_pair(p, tile / p.n_tiles);
-      auto load_b = [&](int kb_glob) {
-        mbar_wait(b_empty0 + bi * 8, bph ^ 1);
-        if (elect_one()) {
-          const uint32_t fb = b_full0 + bi * 8;
-          mbar_expect_tx(fb, (uint32_t)b_bytes);
-          tma_load_2d(b_ring0 + (uint32_t)(bi * b_bytes), &mapB, fb, kb_glob * TC_BK, tn * p.BN);
-        }
-        __syncwarp();
-        if (++bi == p.b_slots) { bi = 0; bph ^= 1; }
-      };
       for (int kb = 0; kb < p.nkb_conv; ++kb) {
         const bool second = kb >= p.nkb0;
         const CUtensorMap* mp = second ? &mapA1 : &mapA0;
@@ -141,21 +140,13 @@ gemm_tc2x_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
           __syncwarp();
           if (++ai == p.nbox) { ai = 0; aph ^= 1; }
         };
-        // what MMA step ky needs (boxes ky, ky + 1 and the three weight blocks of ky) is always issued before anything later
-        load_box(0);
-        load_box(1);
-        for (int kx = 0; kx < 3; ++kx) load_b(kx * p.nkb_conv + kb);
-        load_box(2);
-        for (int kx = 0; kx < 3; ++kx) load_b((3 + kx) * p.nkb_conv + kb);
-        load_box(3);
-        for (int kx = 0; kx < 3; ++kx) load_b((6 + kx) * p.nkb_conv + kb);
+        for (int j = 0; j < 4; ++j) load_box(j);
       }
-      int kb_glob = 9 * p.nkb_conv;
       for (int s = 0; s < p.ntap; ++s) {
         const TcSeg sg = p.tap[s];
         const CUtensorMap* mp = sg.map == 0 ? &mapA0 : (sg.map == 1 ? &mapA1 : &mapA2);
         const int smp = sg.div > 1 ? t.nb / sg.div : t.nb;
-        for (int kb = 0; kb < sg.nkb; ++kb, ++kb_glob) {
+        for (int kb = 0; kb < sg.nkb; ++kb) {
           for (int sub = 0; sub < 2; ++sub) {       // one [128 px x 64 ch] tile per output row, in two consecutive slots
             mbar_wait(a_empty0 + ai * 8, aph ^ 1);
             if (elect_one()) {
@@ -166,8 +157,27 @@ gemm_tc2x_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
             __syncwarp();
             if (++ai == p.nbox) { ai = 0; aph ^= 1; }
           }
-          load_b(kb_glob);
         }
+      }
+    }
+  } else if (warp == 19) {
+    // ===================== TMA producer of the weight blocks, in the MMAs' (channel block, ky, kx) order =====================
+    int bi = 0;
+    uint32_t bph = 0;
+    prefetch_tmap(&mapB);
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int tn = tile % p.n_tiles;
+      const int conv_blocks = 9 * p.nkb_conv;
+      for (int i = 0; i < conv_blocks + tap_items; ++i) {
+        const int kb_glob = i < conv_blocks ? (i % 9) * p.nkb_conv + i / 9 : i;
+        mbar_wait(b_empty0 + bi * 8, bph ^ 1);
+        if (elect_one()) {
+          const uint32_t fb = b_full0 + bi * 8;
+          mbar_expect_tx(fb, (uint32_t)b_bytes);
+          tma_load_2d(b_ring0 + (uint32_t)(bi * b_bytes), &mapB, fb, kb_glob * TC_BK, tn * p.BN);
+        }
+        __syncwarp();
+        if (++bi == p.b_slots) { bi = 0; bph ^= 1; }
       }
     }
   } else if (warp <= 2) {
@@ -258,7 +268,16 @@ gemm_tc2x_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
       const TxPair t = decode_pair(p, tile / p.n_tiles);
       const int tm_lin = t.tm0 + grp * p.tiles_x;        // output row y0 + grp
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 256 + grp * 128);
-      if (p.staged) {
+      if (dbg & 2) {
+        mbar_wait(smem_u32(&tfull_bar[as * 2 + grp]), aphase);
+        tc_fence_after();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[as * 2 + grp]));
+      } else if (p.staged && p.two_stg) {
+        staged_epilogue(gq, e, stg8 + grp * TC_EPI_BYTES, it & 1, tm_lin, tn, p.BN, taddr, smem_u32(&tfull_bar[as * 2 + grp]),
+                        aphase, true, smem_u32(&tempty_bar[as * 2 + grp]), true, 1 + grp);
+      } else if (p.staged) {
         // ONE staging tile, used alternately (group 0 of tile k, group 1 of tile k, group 0 of tile k + 1, ...): two
         // serialised epilogues (~6 k cycles) still fit under the >= 9 k cycle main loop of a K >= 1152 tile
         if (grp == 1 || it > 0) bar_sync_n(grp == 0 ? 4 : 3, 256);
@@ -301,7 +320,7 @@ gemm_tc2x_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
       }
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
-  } else {
+  } else if (warp <= 18) {
     // ===================== GroupNorm(+SiLU) transform of the landed row boxes, in place =====================
     const int t = ((warp - 11) << 5) + lane;      // 0..255
     const int l = t & 7, r0 = t >> 3;             // logical 16-byte chunk, first box row
@@ -327,7 +346,7 @@ gemm_tc2x_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
         for (int j = 0; j < 4; ++j) {
           const int y = tp.y0 - 1 + j;
           mbar_wait(a_full0 + ai * 8, aph);
-          if (y >= 0 && y < p.OH) {       // rows outside the image stay zero (TMA fill) = the conv padding
+          if (y >= 0 && y < p.OH && !(dbg & 1)) {       // rows outside the image stay zero (TMA fill) = the conv padding
             const uint32_t base = a_ring0 + (uint32_t)(ai * TX_BOX);
 #pragma unroll
             for (int rr = 0; rr < 5; ++rr) {
@@ -454,8 +473,16 @@ int launch_gemm_tc2x(const GemmDev& g, cudaStream_t st, int tiles_x, int BN, int
 
   // rings: one staging tile (staged epilogue) or none; at least 6 row boxes (1.5 channel blocks in flight), the rest weights
   const int b_bytes = BN * TC_BK * 2;
-  const int fixed = 1024 + 512 + (staged ? TC_EPI_BYTES : 0);
-  int nbox = staged ? 6 : 8;
+  p.two_stg = 0;
+#ifdef DCB_PROBES
+  p.dbg = getenv("DCB_TX_DBG") ? atoi(getenv("DCB_TX_DBG")) : 0;
+  p.two_stg = (p.dbg & 4) ? 1 : 0;
+#endif
+  const int fixed = 1024 + 512 + (staged ? (p.two_stg ? 2 : 1) * TC_EPI_BYTES : 0);
+  int nbox = staged ? (p.two_stg ? 5 : 6) : 8;
+#ifdef DCB_PROBES
+  if (getenv("DCB_TX_NBOX")) nbox = atoi(getenv("DCB_TX_NBOX"));
+#endif
   int b_slots = (TC_SMEM_LIMIT - fixed - nbox * TX_BOX) / b_bytes;
   if (b_slots > TX_MAX_SLOTS) b_slots = TX_MAX_SLOTS;
   if (b_slots < 4) return DCB_EUNSUPPORTED;

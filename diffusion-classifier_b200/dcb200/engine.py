@@ -67,6 +67,9 @@ USE_TILE_STATS = __import__("os").environ.get("DCB_TILE_STATS", "1") != "0"
 USE_FUSED_SMALL_GN = __import__("os").environ.get("DCB_FUSED_SMALL_GN", "1") != "0"
 FOLD_UPSAMPLE = __import__("os").environ.get("DCB_FOLD_UPSAMPLE", "1") != "0"   # A/B switch for upsample_conv
 FUSE_GN = __import__("os").environ.get("DCB_FUSE_GN", "1") != "0"   # A/B switch: GroupNorm applied inside the consumer conv
+# ... only for convs over at least this many input channels: the fused kernel's two epilogue groups share one staging tile,
+# which a K = 9 x 128 main loop is too short to hide (measured, profiles/r02_gn_fusion.md); K = 9 x 256 gains 15 %
+FUSE_GN_MIN_C = int(__import__("os").environ.get("DCB_FUSE_GN_MIN_C", "256"))
 XF_UNSUPPORTED = object()     # gemm(xf=...) sentinel: this launch cannot apply the fused transform; nothing was launched
 
 
@@ -277,7 +280,8 @@ def gn_conv3x3(ctx, x0, C0, x1, C1, NB, H, W, gamma, beta, eps, silu, Wt, N, *, 
     ``gn_apply`` pass) never exists.  Bit-identical to the unfused form, which everything else takes."""
     HW = H * W
     if FUSE_GN and ctx.code == L.BF16 and ctx.engine != L.ENGINE_SIMT and st0 is not None and (x1 is None or st1 is not None) \
-            and USE_TILE_STATS and HW % 128 == 0 and W % 128 == 0 and C0 % 64 == 0 and C1 % 64 == 0:
+            and USE_TILE_STATS and HW % 128 == 0 and W % 128 == 0 and C0 % 64 == 0 and C1 % 64 == 0 \
+            and C0 + C1 >= FUSE_GN_MIN_C:
         ca = torch.empty(NB, C0 + C1, device=ctx.device, dtype=torch.float32)
         cb = torch.empty(NB, C0 + C1, device=ctx.device, dtype=torch.float32)
 
