@@ -16,8 +16,9 @@
 //                 (5 blocks = 2.5 k cycles) also capped how far ahead of the MMAs a row box could be requested, and a box
 //                 needs TMA latency + the transform before it is usable (measured: 737 -> see DESIGN.md)
 //   warps 1, 2    MMA issuers, one per output row (accumulator); tcgen05.commit releases boxes / weight blocks
-//   warps 3..10   two epilogue groups (staged epilogue of tc_common.cuh through ONE shared staging tile, handed over by
-//                 named barriers -- the freed 36 KB are two more row boxes -- or the direct eps-MSE epilogue of conv_out)
+//   warps 3..10   two epilogue groups, each with a HALF-width staging tile (staged_epilogue_half: 64 columns at a time; two
+//                 full tiles would cost two row boxes, one shared tile serialises the groups: +0.5 ms on a K = 1152 conv,
+//                 profiles/r02_gn_fusion.md), or the direct eps-MSE epilogue of conv_out
 //   warps 11..18  transform: thread t owns logical 16-byte chunk t & 7 (8 channels: 16 coefficients in registers for the
 //                 whole channel block) of box rows t >> 3, + 32, ...
 #include <cudaTypedefs.h>
@@ -42,7 +43,6 @@ struct TxParams {
   int nbox, b_slots;
   uint32_t idesc;
   int uniform, staged, silu, xf_C;
-  int two_stg;                 // each epilogue group has its own staging tile (no hand-over)
   int dbg;                     // -DDCB_PROBES builds only: 1 = no transform arithmetic, 2 = no epilogue work
   const float* xf_a;           // [NB][xf_C]
   const float* xf_b;
@@ -274,17 +274,10 @@ gemm_tc2x_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[as * 2 + grp]));
-      } else if (p.staged && p.two_stg) {
-        staged_epilogue(gq, e, stg8 + grp * TC_EPI_BYTES, it & 1, tm_lin, tn, p.BN, taddr, smem_u32(&tfull_bar[as * 2 + grp]),
-                        aphase, true, smem_u32(&tempty_bar[as * 2 + grp]), true, 1 + grp);
       } else if (p.staged) {
-        // ONE staging tile, used alternately (group 0 of tile k, group 1 of tile k, group 0 of tile k + 1, ...): two
-        // serialised epilogues (~6 k cycles) still fit under the >= 9 k cycle main loop of a K >= 1152 tile
-        if (grp == 1 || it > 0) bar_sync_n(grp == 0 ? 4 : 3, 256);
-        staged_epilogue(gq, e, stg8, it & 1, tm_lin, tn, p.BN, taddr, smem_u32(&tfull_bar[as * 2 + grp]), aphase, true,
-                        smem_u32(&tempty_bar[as * 2 + grp]), true, 1 + grp);
-        epi_bar(1 + grp);                               // every thread of this group has left the staging tile
-        if (grp == 0 || tile + (int)gridDim.x < p.total_tiles) bar_arrive_n(grp == 0 ? 3 : 4, 256);
+        // each group drains its accumulator through its own HALF-width staging tile (64 columns at a time)
+        staged_epilogue_half(gq, e, stg8 + grp * TC_EPI_HALF_BYTES, it & 1, tm_lin, tn, p.BN, taddr,
+                             smem_u32(&tfull_bar[as * 2 + grp]), aphase, smem_u32(&tempty_bar[as * 2 + grp]), 1 + grp);
       } else {
         // direct epilogue (same arithmetic and summation order as gemm_tc_kernel's): fused eps-MSE, one partial per row tile
         const int rr = q * 32 + lane;
@@ -471,22 +464,21 @@ int launch_gemm_tc2x(const GemmDev& g, cudaStream_t st, int tiles_x, int BN, int
     DCB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(W/tc2x) failed: %d", (int)r);
   }
 
-  // rings: one staging tile (staged epilogue) or none; at least 6 row boxes (1.5 channel blocks in flight), the rest weights
+  // rings: two half-width staging tiles (staged epilogue) or none; 6 row boxes (1.5 channel blocks in flight), the rest weights
   const int b_bytes = BN * TC_BK * 2;
-  p.two_stg = 0;
 #ifdef DCB_PROBES
   p.dbg = getenv("DCB_TX_DBG") ? atoi(getenv("DCB_TX_DBG")) : 0;
-  p.two_stg = (p.dbg & 4) ? 1 : 0;
 #endif
-  const int fixed = 1024 + 512 + (staged ? (p.two_stg ? 2 : 1) * TC_EPI_BYTES : 0);
-  int nbox = staged ? (p.two_stg ? 5 : 6) : 8;
+  const int fixed = 1024 + 512 + (staged ? 2 * TC_EPI_HALF_BYTES : 0);
+  // (measured, tools/xf_micro.py: 7 boxes + 4 weight slots beat 6 + 5 on the residual / shortcut convs by 10 % and 8 + 8 on
+  //  conv_out by 25 %; a ring that is a multiple of the 4 boxes per channel block does worst)
+  int nbox = 7;
 #ifdef DCB_PROBES
   if (getenv("DCB_TX_NBOX")) nbox = atoi(getenv("DCB_TX_NBOX"));
 #endif
   int b_slots = (TC_SMEM_LIMIT - fixed - nbox * TX_BOX) / b_bytes;
   if (b_slots > TX_MAX_SLOTS) b_slots = TX_MAX_SLOTS;
   if (b_slots < 4) return DCB_EUNSUPPORTED;
-  while (nbox < TX_MAX_SLOTS && fixed + (nbox + 1) * TX_BOX + b_slots * b_bytes <= TC_SMEM_LIMIT) ++nbox;
   p.nbox = nbox; p.b_slots = b_slots;
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
   if (dry_run) return DCB_OK;

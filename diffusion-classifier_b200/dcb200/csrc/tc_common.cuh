@@ -475,9 +475,12 @@ __device__ __forceinline__ void staged_epilogue(const EpiGeom& gq, const EpiDev&
     if (do_release && lane == 0) mbar_arrive(empty_bar);
     epi_bar(bar_id);
     // ---- coalesced copy-out (+ per-column sum / sum of squares of the stored values for the next GroupNorm) ----
-    float cs[8], cq[8];
+    // Canonical summation tree of a column over the tile's 128 rows (every staged epilogue follows it, so a layer's
+    // statistics do not depend on which kernel wrote it): P[k] = rows k, k + 16, ..., k + 112 in order (k = 0..15);
+    // Q[k] = P[k] + P[k + 8]; S[w] = Q[2w] + Q[2w + 1]; total = (S[0] + S[1]) + (S[2] + S[3]).
+    float cs[8], cq[8], ds[8], dq[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) cs[i] = cq[i] = 0.f;
+    for (int i = 0; i < 8; ++i) cs[i] = cq[i] = ds[i] = dq[i] = 0.f;
     if (cc_ok) {
       __nv_bfloat16* obase = (__nv_bfloat16*)e.out + ocol0 + cc * 8;
 #pragma unroll
@@ -490,12 +493,19 @@ __device__ __forceinline__ void staged_epilogue(const EpiGeom& gq, const EpiDev&
           if (e.gn_part) {
             float f[8];
             unpack_bf16x8(val, f);
+            if (i & 1) {        // rows rr0 + 8 + 16 j: P[rr0 + 8]
 #pragma unroll
-            for (int j = 0; j < 8; ++j) { cs[j] += f[j]; cq[j] = fmaf(f[j], f[j], cq[j]); }
+              for (int j = 0; j < 8; ++j) { ds[j] += f[j]; dq[j] = fmaf(f[j], f[j], dq[j]); }
+            } else {            // rows rr0 + 16 j: P[rr0]
+#pragma unroll
+              for (int j = 0; j < 8; ++j) { cs[j] += f[j]; cq[j] = fmaf(f[j], f[j], cq[j]); }
+            }
           }
         }
       }
     }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { cs[j] += ds[j]; cq[j] += dq[j]; }     // Q[rr0]
     if (e.gn_part) {
       // fixed-order reduction over the 8 row-slices: lanes cc / cc+16 by shuffle, the 4 warps through the (now free)
       // staging tile; thread c then owns output column c of this tile
@@ -526,6 +536,199 @@ __device__ __forceinline__ void staged_epilogue(const EpiGeom& gq, const EpiDev&
         gp[1] = q4;
       }
     }
+}
+
+
+// ---- staged epilogue through a HALF-width staging tile (64 output columns at a time, 16 KB + constants per group) --------
+// Same arithmetic, same stores and the same statistics tree as staged_epilogue (no GEGLU): gemm_tc2x_kernel uses it so that
+// both epilogue groups own a staging tile next to six row boxes.  stg8: TC_EPI_HALF_BYTES of smem per group.
+constexpr int TC_EPI_HALF_BYTES = 128 * 64 * 2 + 512 * 4 + 4 * 128 * 4;
+
+__device__ __forceinline__ void staged_epilogue_half(const EpiGeom& gq, const EpiDev& e, uint8_t* stg8, int parity, int tm_lin,
+                                                     int tn, int BN, uint32_t taddr, uint32_t full_bar, uint32_t full_parity,
+                                                     uint32_t empty_bar, int bar_id) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = warp & 3;
+  const int r = q * 32 + lane;           // accumulator row (TMEM lane) owned in the thread-per-row pass
+  const int et = (threadIdx.x & 127);
+  int tm = tm_lin;
+  const int tx = tm % gq.tiles_x;
+  tm /= gq.tiles_x;
+  const int ty = tm % gq.tiles_y;
+  const int tb = tm / gq.tiles_y;
+  const int xl = r % gq.bw, yl = (r / gq.bw) % gq.bh, nl = r / (gq.bw * gq.bh);
+  const int x = tx * gq.bw + xl, y = ty * gq.bh + yl, nb = tb * gq.bn + nl;
+  const bool row_ok = x < gq.OW && y < gq.OH && nb < gq.NB;
+  const int m = nb * e.rows_per_sample + y * gq.OW + x;
+  float* s_bias = reinterpret_cast<float*>(stg8 + 128 * 128);  // [256]
+  float* s_gate = s_bias + 256 + 128;                          // [128]
+  int* s_m = reinterpret_cast<int*>(s_gate + 128) + parity * 128;
+  int* s_res = reinterpret_cast<int*>(s_gate + 128) + 256 + parity * 128;
+  const int wrow0 = tn * BN;
+  const int ncols_out = BN;
+  const int ocol0 = tn * BN;
+  const int up_a = (e.up_phase - 1) >> 1, up_b = (e.up_phase - 1) & 1;
+  const int m_out = e.up_phase ? ((nb * 2 * gq.OH + 2 * y + up_a) * (2 * gq.OW) + 2 * x + up_b) : m;
+  s_m[r] = row_ok ? m_out : -1;
+  if (e.residual) s_res[r] = row_ok ? (e.res_idx ? e.res_idx[m] : (e.res_mod > 0 ? m % e.res_mod : m)) : -1;
+  const bool rv_folded = gq.uniform && e.rowvec != nullptr;
+  for (int c = et; c < BN; c += 128) s_bias[c] = (e.bias && wrow0 + c < e.N) ? e.bias[wrow0 + c] : 0.f;
+  if (gq.uniform && (e.rowvec || e.gate) && et < ncols_out) {
+    const int m0 = (tb * gq.bn) * e.rows_per_sample + (ty * gq.bh) * gq.OW + tx * gq.bw;
+    const int grp0 = m0 / e.rows_per_group;
+    const bool ok = ocol0 + et < e.n_out;
+    if (e.rowvec) s_bias[et] += ok ? e.rowvec[(int64_t)(e.rowvec_idx ? e.rowvec_idx[grp0] : grp0) * e.rowvec_ld + ocol0 + et] : 0.f;
+    if (e.gate) s_gate[et] = ok ? e.gate[(int64_t)grp0 * e.gate_ld + ocol0 + et] : 0.f;
+  }
+  epi_bar(bar_id);  // ids / constants visible; the previous tile's copy-out is complete
+  const int cc = et & 7, rr0 = et >> 3;     // coalesced role: 16-byte chunk cc of rows rr0, rr0 + 16, ...
+  const int grp = (!gq.uniform && e.rows_per_group > 0 && row_ok) ? m / e.rows_per_group : 0;
+  bool waited = false;
+  for (int h0 = 0; h0 < ncols_out; h0 += 64) {
+    const bool cc_ok = h0 + cc * 8 < ncols_out && ocol0 + h0 + cc * 8 + 8 <= e.n_out;
+    if (h0 > 0) epi_bar(bar_id);            // the previous half has been copied out (and its statistics scratch read)
+    if (e.residual && cc_ok) {
+      const __nv_bfloat16* rbase = (const __nv_bfloat16*)e.residual + ocol0 + h0 + cc * 8;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int row = rr0 + 16 * i;
+        const int rrow = s_res[row];
+        if (rrow >= 0)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(stg8 + row * 128 + ((cc ^ (row & 7)) << 4))),
+                       "l"(rbase + (int64_t)rrow * e.res_ld)
+                       : "memory");
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    if (!waited) {
+      mbar_wait(full_bar, full_parity);
+      tc_fence_after();
+      waited = true;
+    }
+    if (e.residual) {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      epi_bar(bar_id);
+    }
+    auto process = [&](int c, const uint32_t (&ra)[16]) {     // c: column inside this half
+      float v[16], bz[16];
+      lds16f(smem_u32(s_bias + h0 + c), bz);
+      if (e.rowvec && !rv_folded && row_ok) {
+        const float* rv = e.rowvec + (int64_t)(e.rowvec_idx ? e.rowvec_idx[grp] : grp) * e.rowvec_ld + ocol0 + h0 + c;
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (ocol0 + h0 + c + i < e.n_out) bz[i] += rv[i];
+      }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(ra[i]) + bz[i];
+      if (e.act == DCB_ACT_SILU || e.act == DCB_ACT_GELU_TANH) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = apply_act_fast(e.act, v[i]);
+      }
+      if (e.gate) {
+        if (gq.uniform) {
+          float gvv[16];
+          lds16f(smem_u32(s_gate + h0 + c), gvv);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] *= gvv[i];
+        } else if (row_ok) {
+          const float* gt = e.gate + (int64_t)grp * e.gate_ld + ocol0 + h0 + c;
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (ocol0 + h0 + c + i < e.n_out) v[i] *= gt[i];
+        }
+      }
+      uint4* s0 = reinterpret_cast<uint4*>(stg8 + r * 128 + ((((c >> 3)) ^ (r & 7)) << 4));
+      uint4* s1 = reinterpret_cast<uint4*>(stg8 + r * 128 + ((((c >> 3) + 1) ^ (r & 7)) << 4));
+      if (e.residual && row_ok) {
+        float f[8];
+        unpack_bf16x8(*s0, f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] += f[i];
+        unpack_bf16x8(*s1, f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[8 + i] += f[i];
+      }
+      if (e.act_post != DCB_ACT_NONE) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = apply_act_fast(e.act_post, v[i]);
+      }
+      *s0 = pack_bf16x8(v);
+      *s1 = pack_bf16x8(v + 8);
+    };
+    {
+      const int ncol_h = min(64, ncols_out - h0);
+      uint32_t ra[16], rb[16];
+      tmem_ld16_nowait(taddr + (uint32_t)h0, ra);
+      for (int c = 0; c < ncol_h; c += 32) {
+        tmem_ld_wait_dep(ra);
+        const bool more1 = c + 16 < ncol_h;
+        if (more1) tmem_ld16_nowait(taddr + (uint32_t)(h0 + c + 16), rb);
+        process(c, ra);
+        if (more1) {
+          tmem_ld_wait_dep(rb);
+          if (c + 32 < ncol_h) tmem_ld16_nowait(taddr + (uint32_t)(h0 + c + 32), ra);
+          process(c + 16, rb);
+        }
+      }
+    }
+    if (h0 + 64 >= ncols_out) {     // accumulator fully drained: hand the TMEM stage back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty_bar);
+    }
+    epi_bar(bar_id);
+    // ---- coalesced copy-out of this half + P[rr0] of the canonical statistics tree (see staged_epilogue) ----
+    float cs[8], cq[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) cs[i] = cq[i] = 0.f;
+    if (cc_ok) {
+      __nv_bfloat16* obase = (__nv_bfloat16*)e.out + ocol0 + h0 + cc * 8;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int row = rr0 + 16 * i;
+        const int mm = s_m[row];
+        if (mm >= 0) {
+          const uint4 val = *reinterpret_cast<const uint4*>(stg8 + row * 128 + ((cc ^ (row & 7)) << 4));
+          *reinterpret_cast<uint4*>(obase + (int64_t)mm * e.out_ld) = val;
+          if (e.gn_part) {
+            float f[8];
+            unpack_bf16x8(val, f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { cs[j] += f[j]; cq[j] = fmaf(f[j], f[j], cq[j]); }
+          }
+        }
+      }
+    }
+    if (e.gn_part) {
+      epi_bar(bar_id);  // every thread has read its rows out of the staging tile
+      float* red = reinterpret_cast<float*>(stg8);  // [16 row classes][64 columns][2]
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        red[((rr0 * 64) + cc * 8 + j) * 2] = cs[j];
+        red[((rr0 * 64) + cc * 8 + j) * 2 + 1] = cq[j];
+      }
+      epi_bar(bar_id);
+      if (et < 64 && h0 + et < ncols_out && ocol0 + h0 + et < e.n_out && tb * gq.bn < gq.NB) {
+        float S[4], Q4[4];
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          const float qa = red[((2 * w) * 64 + et) * 2] + red[((2 * w + 8) * 64 + et) * 2];
+          const float qb = red[((2 * w + 1) * 64 + et) * 2] + red[((2 * w + 9) * 64 + et) * 2];
+          S[w] = qa + qb;
+          const float ra_ = red[((2 * w) * 64 + et) * 2 + 1] + red[((2 * w + 8) * 64 + et) * 2 + 1];
+          const float rb_ = red[((2 * w + 1) * 64 + et) * 2 + 1] + red[((2 * w + 9) * 64 + et) * 2 + 1];
+          Q4[w] = ra_ + rb_;
+        }
+        const float s4 = (S[0] + S[1]) + (S[2] + S[3]);
+        const float q4 = (Q4[0] + Q4[1]) + (Q4[2] + Q4[3]);
+        const int tps = gq.tiles_x * gq.tiles_y;
+        const int64_t gtile = e.up_phase ? ((int64_t)(tb * 4 + e.up_phase - 1) * tps + (tm_lin - tb * tps)) : (int64_t)tm_lin;
+        float* gp = e.gn_part + (gtile * e.n_out + ocol0 + h0 + et) * 2;
+        gp[0] = s4;
+        gp[1] = q4;
+      }
+    }
+  }
 }
 
 }  // namespace dcb

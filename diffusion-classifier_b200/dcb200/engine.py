@@ -67,9 +67,9 @@ USE_TILE_STATS = __import__("os").environ.get("DCB_TILE_STATS", "1") != "0"
 USE_FUSED_SMALL_GN = __import__("os").environ.get("DCB_FUSED_SMALL_GN", "1") != "0"
 FOLD_UPSAMPLE = __import__("os").environ.get("DCB_FOLD_UPSAMPLE", "1") != "0"   # A/B switch for upsample_conv
 FUSE_GN = __import__("os").environ.get("DCB_FUSE_GN", "1") != "0"   # A/B switch: GroupNorm applied inside the consumer conv
-# ... only for convs over at least this many input channels: the fused kernel's two epilogue groups share one staging tile,
-# which a K = 9 x 128 main loop is too short to hide (measured, profiles/r02_gn_fusion.md); K = 9 x 256 gains 15 %
-FUSE_GN_MIN_C = int(__import__("os").environ.get("DCB_FUSE_GN_MIN_C", "256"))
+# ... only for convs over at least this many input channels (A/B knob; 0 = every eligible conv, the measured best:
+# profiles/r02_gn_fusion.md)
+FUSE_GN_MIN_C = int(__import__("os").environ.get("DCB_FUSE_GN_MIN_C", "0"))
 XF_UNSUPPORTED = object()     # gemm(xf=...) sentinel: this launch cannot apply the fused transform; nothing was launched
 
 
