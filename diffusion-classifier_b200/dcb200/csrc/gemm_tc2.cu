@@ -295,7 +295,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
     // ===================== epilogue: warps 3..6 drain sub-tile 0, warps 7..10 sub-tile 1, concurrently =====================
     const int q = warp & 3;             // TMEM lane quarter this warp may access
     const int grp = (warp - 3) >> 2;    // epilogue group == sub-tile == accumulator half
-    uint8_t* my_stg = stg8 + grp * TC_EPI_BYTES;
+    uint8_t* my_stg = stg8 + grp * TC_EPI_HALF_BYTES;
     EpiGeom gq{p.tiles_x, p.tiles_y, p.bw, p.bh, p.bn, p.OW, p.OH, p.NB, p.uniform};
     int as = 0;
     uint32_t aphase = 0;
@@ -312,8 +312,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
         continue;
       }
       if (p.staged) {
-        staged_epilogue(gq, e, my_stg, it & 1, 2 * tp + grp, tn, p.BN, taddr, smem_u32(&tfull_bar[as * 2 + grp]), aphase, true,
-                        smem_u32(&tempty_bar[as * 2 + grp]), true, 1 + grp);
+        // half-width staging tiles (64 columns at a time): the 33 KB this saves over two full tiles go to the operand rings
+        staged_epilogue_half(gq, e, my_stg, it & 1, 2 * tp + grp, tn, p.BN, taddr, smem_u32(&tfull_bar[as * 2 + grp]), aphase,
+                             smem_u32(&tempty_bar[as * 2 + grp]), 1 + grp);
       } else {
         // direct epilogue (same arithmetic and summation order as gemm_tc_kernel's): thread-per-row over the BN columns,
         // fused eps-MSE -> one partial per 128-row sub-tile
@@ -509,7 +510,7 @@ int launch_gemm_tc2(const GemmDev& g, cudaStream_t st, int bw, int bh, int bn, i
   // (6 K blocks) + 5 B slots, but tap-mode GEMMs (the K <= 768 projections) were A-ring bound with 2 slots -- with 3 + 3
   // the same kernel moves 20 % more (measured: 782 -> 941 TF/s at M=204800, K=N=768).
   const int kb_per_a = halo ? 3 : 1;
-  const int epi_bytes = staged ? 2 * TC_EPI_BYTES : 0;   // the direct epilogues need no staging tiles: deeper rings
+  const int epi_bytes = staged ? 2 * TC_EPI_HALF_BYTES : 0;   // the direct epilogues need no staging tiles: deeper rings
   const int ring_bytes = TC_SMEM_LIMIT - (1024 + 512 + epi_bytes);
   int best_a = 2, best_score = -1;
   for (int a = 2; a <= 4; ++a) {
