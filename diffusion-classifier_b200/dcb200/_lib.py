@@ -83,6 +83,10 @@ _PROTOS = {
     "dcb_nhwc_to_nchw": (c_int, [c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "dcb_unpatchify": (c_int, [c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "dcb_cast_f32": (c_int, [c_int, c_void_p, c_i64, c_void_p, c_void_p]),
+    "dcb_pack_conv": (c_int, [c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "dcb_pack_geglu": (c_int, [c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "dcb_pack_upsample": (c_int, [c_int, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "dcb_pack_rows": (c_int, [c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
 }
 
 EXPORTS = tuple(_PROTOS)

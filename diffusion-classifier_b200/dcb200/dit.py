@@ -148,12 +148,11 @@ class DiT(nn.Module):
         p, cin = cfg.patch_size, cfg.in_channels
         pk = SimpleNamespace()
         pk.kpad_in = (p * p * cin + 63) // 64 * 64
-        wpe = torch.zeros(D, pk.kpad_in, device=self.pos_embed.proj.weight.device)
-        wpe[:, :p * p * cin] = self.pos_embed.proj.weight.detach().permute(0, 2, 3, 1).reshape(D, -1)  # (py,px,c)
-        pk.pe_w, pk.pe_b = w(wpe), f32(self.pos_embed.proj.bias)
+        pk.pe_w = E.pack_conv(ctx, self.pos_embed.proj.weight, pk.kpad_in)     # K order (py, px, c), zero padded
+        pk.pe_b = f32(self.pos_embed.proj.bias)
         pk.pos = w(self.pos_embed.pos_embed[0])
         blks = list(self.transformer_blocks)
-        pk.te1_w = w(torch.cat([b.norm1.emb.timestep_embedder.linear_1.weight.detach() for b in blks], 0))
+        pk.te1_w = E.pack_rows(ctx, [b.norm1.emb.timestep_embedder.linear_1.weight for b in blks], 0)
         pk.te1_b = f32(torch.cat([b.norm1.emb.timestep_embedder.linear_1.bias.detach() for b in blks], 0))
         pk.blk = []
         for b in blks:
@@ -163,7 +162,7 @@ class DiT(nn.Module):
             q.table = w(b.norm1.emb.class_embedder.embedding_table.weight)
             q.mod_w, q.mod_b = w(b.norm1.linear.weight), f32(b.norm1.linear.bias)
             a = b.attn1
-            q.qkv_w = w(torch.cat([a.to_q.weight.detach(), a.to_k.weight.detach(), a.to_v.weight.detach()], 0))
+            q.qkv_w = E.pack_rows(ctx, [a.to_q.weight, a.to_k.weight, a.to_v.weight], 0)
             q.qkv_b = f32(torch.cat([a.to_q.bias.detach(), a.to_k.bias.detach(), a.to_v.bias.detach()], 0))
             q.o_w, q.o_b = w(a.to_out[0].weight), f32(a.to_out[0].bias)
             q.f1_w, q.f1_b = w(b.ff.net[0].proj.weight), f32(b.ff.net[0].proj.bias)

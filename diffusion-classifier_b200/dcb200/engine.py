@@ -400,6 +400,63 @@ def cast(ctx, src_f32, tdtype=None):
     return dst
 
 
+# ---- weight packing through the C ABI (dcb_pack_*): checkpoint layout (fp32) -> GEMM operand layouts, on the device ---------
+def _f32dev(ctx, t):
+    return t.detach().to(device=ctx.device, dtype=torch.float32).contiguous()
+
+
+def pack_conv(ctx, w, kpad=None, out=None):
+    """conv weight [Cout, Cin, kh, kw] -> [Cout, kpad] with K order (ky, kx, cin) (kpad >= kh*kw*Cin: zero padded)."""
+    Cout, Cin, kh, kw = w.shape
+    kpad = kpad or kh * kw * Cin
+    out = ctx.empty(Cout, kpad) if out is None else out
+    src = _f32dev(ctx, w)
+    L.check(L.lib().dcb_pack_conv(ctx.code, src.data_ptr(), Cout, Cin, kh, kw, kpad, out.data_ptr(), ctx.stream()), "pack_conv")
+    return out
+
+
+def pack_rows(ctx, mats, axis=0, out=None, col0=0):
+    """concatenate fp32 [rows, cols] matrices along rows (axis 0) or columns (axis 1) into one operand in the engine dtype;
+    ``out`` / ``col0``: write into an existing packed matrix starting at that column (axis 1 only)."""
+    mats = [_f32dev(ctx, m.reshape(m.shape[0], -1)) for m in mats]
+    if axis == 0:
+        rows, cols = sum(m.shape[0] for m in mats), mats[0].shape[1]
+        out = ctx.empty(rows, cols) if out is None else out
+        r0 = 0
+        for m in mats:
+            L.check(L.lib().dcb_pack_rows(ctx.code, m.data_ptr(), m.shape[1], m.shape[0], m.shape[1], out.data_ptr(),
+                                          out.shape[1], r0, col0, ctx.stream()), "pack_rows")
+            r0 += m.shape[0]
+    else:
+        rows = mats[0].shape[0]
+        out = ctx.empty(rows, sum(m.shape[1] for m in mats)) if out is None else out
+        for m in mats:
+            L.check(L.lib().dcb_pack_rows(ctx.code, m.data_ptr(), m.shape[1], rows, m.shape[1], out.data_ptr(),
+                                          out.shape[1], 0, col0, ctx.stream()), "pack_rows")
+            col0 += m.shape[1]
+    return out
+
+
+def pack_geglu(ctx, w, b):
+    """diffusers GEGLU proj [2*inner, C] (+ bias) -> (rows interleaved per 128 [value | gate], fp32 bias in the same order)."""
+    inner, C_ = w.shape[0] // 2, w.shape[1]
+    wo = ctx.empty(2 * inner, C_)
+    bo = torch.empty(2 * inner, device=ctx.device, dtype=torch.float32)
+    ws, bs = _f32dev(ctx, w), _f32dev(ctx, b)
+    L.check(L.lib().dcb_pack_geglu(ctx.code, ws.data_ptr(), bs.data_ptr(), inner, C_, wo.data_ptr(), bo.data_ptr(),
+                                   ctx.stream()), "pack_geglu")
+    return wo, bo
+
+
+def pack_upsample(ctx, w):
+    """[Cout, Cin, 3, 3] -> the four [Cout, (ty, tx, Cin)] phase weights of ``upsample_conv`` (== fold_upsample_weights)."""
+    Cout, Cin = w.shape[:2]
+    out = ctx.empty(4, Cout, 4 * Cin)
+    src = _f32dev(ctx, w)
+    L.check(L.lib().dcb_pack_upsample(ctx.code, src.data_ptr(), Cout, Cin, out.data_ptr(), ctx.stream()), "pack_upsample")
+    return [out[i] for i in range(4)]
+
+
 def haar_dwt(x, post_scale=1.0):
     B, C_, H, W = x.shape
     x = x.contiguous().float()

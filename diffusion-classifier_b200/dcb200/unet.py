@@ -275,22 +275,22 @@ class UNetCondition2D(nn.Module):
         def f32(t):
             return t.detach().to(ctx.device, torch.float32).contiguous()
 
-        def conv_w(c):  # [Cout,Cin,3,3] -> [Cout, (ky,kx,c)]
-            return c.weight.detach().permute(0, 2, 3, 1).reshape(c.weight.shape[0], -1)
+        def conv_w(c, kpad=None):  # [Cout,Cin,kh,kw] -> [Cout, (ky,kx,c)] (+ zero padding): dcb_pack_conv
+            return E.pack_conv(ctx, c.weight, kpad)
 
+        # every operand layout below is produced by the library's dcb_pack_* entry points (csrc/pack.cu), so a binder that
+        # is not Python can build the same packed weights from the checkpoint tensors
         pk = SimpleNamespace()
         cin = self.conv_in.weight.shape[1]
         pk.kpad_in = (9 * cin + 63) // 64 * 64
-        win = torch.zeros(self.conv_in.weight.shape[0], pk.kpad_in, device=self.conv_in.weight.device)
-        win[:, :9 * cin] = conv_w(self.conv_in)
-        pk.conv_in_w, pk.conv_in_b = w(win), f32(self.conv_in.bias)
+        pk.conv_in_w, pk.conv_in_b = conv_w(self.conv_in, pk.kpad_in), f32(self.conv_in.bias)
         te = self.time_embedding
         pk.te1_w, pk.te1_b, pk.te2_w, pk.te2_b = w(te.linear_1.weight), f32(te.linear_1.bias), w(te.linear_2.weight), \
             f32(te.linear_2.bias)
         pk.ehp_w, pk.ehp_b = w(self.encoder_hid_proj.weight), f32(self.encoder_hid_proj.bias)
         # every resnet's time_emb_proj as ONE [sum Cout, tdim] GEMM
         res = list(self._resnets())
-        pk.temb_w = w(torch.cat([r.time_emb_proj.weight.detach() for r in res], 0))
+        pk.temb_w = E.pack_rows(ctx, [r.time_emb_proj.weight for r in res], 0)
         pk.temb_b = f32(torch.cat([r.time_emb_proj.bias.detach() for r in res], 0))
         off = 0
         pk.res = {}
@@ -298,18 +298,19 @@ class UNetCondition2D(nn.Module):
             q = SimpleNamespace(temb_off=off, cin=r.cin, cout=r.cout, eps=r.eps)
             off += r.cout
             q.g1, q.b1n, q.g2, q.b2n = f32(r.norm1.weight), f32(r.norm1.bias), f32(r.norm2.weight), f32(r.norm2.bias)
-            q.w1, q.b1 = w(conv_w(r.conv1)), f32(r.conv1.bias)
+            q.w1, q.b1 = conv_w(r.conv1), f32(r.conv1.bias)
             if hasattr(r, "conv_shortcut"):  # fused: [conv2 | 1x1 shortcut] along K, biases summed
-                q.w2 = w(torch.cat([conv_w(r.conv2), r.conv_shortcut.weight.detach().reshape(r.cout, r.cin)], 1))
+                q.w2 = conv_w(r.conv2, 9 * r.cout + r.cin)
+                E.pack_rows(ctx, [r.conv_shortcut.weight], 1, out=q.w2, col0=9 * r.cout)
                 q.b2 = f32(r.conv2.bias.detach() + r.conv_shortcut.bias.detach())
                 q.shortcut = True
             else:
-                q.w2, q.b2, q.shortcut = w(conv_w(r.conv2)), f32(r.conv2.bias), False
+                q.w2, q.b2, q.shortcut = conv_w(r.conv2), f32(r.conv2.bias), False
             pk.res[id(r)] = q
         pk.temb_total = off
         # collapsed cross-attention: v = to_v(ctx) for all layers in one GEMM, then per-layer to_out
         trs = list(self._transformers())
-        pk.xv_w = w(torch.cat([t.transformer_blocks[0].attn2.to_v.weight.detach() for t in trs], 0))
+        pk.xv_w = E.pack_rows(ctx, [t.transformer_blocks[0].attn2.to_v.weight for t in trs], 0)
         off = 0
         pk.tr = {}
         for t in trs:
@@ -322,15 +323,11 @@ class UNetCondition2D(nn.Module):
             q.pout_w, q.pout_b = w(t.proj_out.weight.detach().reshape(Cc, Cc)), f32(t.proj_out.bias)
             q.ln1_g, q.ln1_b, q.ln3_g, q.ln3_b = f32(b.norm1.weight), f32(b.norm1.bias), f32(b.norm3.weight), \
                 f32(b.norm3.bias)
-            q.qkv_w = w(torch.cat([b.attn1.to_q.weight.detach(), b.attn1.to_k.weight.detach(),
-                                   b.attn1.to_v.weight.detach()], 0))
+            q.qkv_w = E.pack_rows(ctx, [b.attn1.to_q.weight, b.attn1.to_k.weight, b.attn1.to_v.weight], 0)
             q.o1_w, q.o1_b = w(b.attn1.to_out[0].weight), f32(b.attn1.to_out[0].bias)
             q.xo_w, q.xo_b = w(b.attn2.to_out[0].weight), f32(b.attn2.to_out[0].bias)
-            gw, gb = b.ff.net[0].proj.weight.detach(), b.ff.net[0].proj.bias.detach()
-            inner = gw.shape[0] // 2  # rows [0,inner) = value, [inner,2*inner) = gate (diffusers GEGLU chunk order)
-            q.gg_w = w(torch.cat([gw[:inner].reshape(inner // 128, 128, Cc), gw[inner:].reshape(inner // 128, 128, Cc)],
-                                 1).reshape(2 * inner, Cc))
-            q.gg_b = f32(torch.cat([gb[:inner].reshape(-1, 128), gb[inner:].reshape(-1, 128)], 1).reshape(-1))
+            # rows [0,inner) = value, [inner,2*inner) = gate (diffusers GEGLU chunk order) -> interleaved per 128
+            q.gg_w, q.gg_b = E.pack_geglu(ctx, b.ff.net[0].proj.weight, b.ff.net[0].proj.bias)
             q.ff2_w, q.ff2_b = w(b.ff.net[2].weight), f32(b.ff.net[2].bias)
             pk.tr[id(t)] = q
         pk.xv_total = off
@@ -339,11 +336,11 @@ class UNetCondition2D(nn.Module):
             for name in ("downsamplers", "upsamplers"):
                 if hasattr(blk, name):
                     s = getattr(blk, name)[0]
-                    pk.samp[id(s)] = SimpleNamespace(w=w(conv_w(s.conv)), b=f32(s.conv.bias))
+                    pk.samp[id(s)] = SimpleNamespace(w=conv_w(s.conv), b=f32(s.conv.bias))
                     if name == "upsamplers":   # nearest-2x + conv3x3 folded into four 2x2-tap phase convs
-                        pk.samp[id(s)].wph = [w(p) for p in E.fold_upsample_weights(s.conv.weight.detach().float())]
+                        pk.samp[id(s)].wph = E.pack_upsample(ctx, s.conv.weight)
         pk.out_g, pk.out_bn = f32(self.conv_norm_out.weight), f32(self.conv_norm_out.bias)
-        pk.out_w, pk.out_b = w(conv_w(self.conv_out)), f32(self.conv_out.bias)
+        pk.out_w, pk.out_b = conv_w(self.conv_out), f32(self.conv_out.bias)
         return pk
 
     # ---- the denoiser program -------------------------------------------------------------------------------

@@ -211,6 +211,23 @@ int dcb_unpatchify(int dtype, const void* tok, int B, int g, int p, int C, int l
 /* dst[i] = (dtype) src_f32[i] */
 int dcb_cast_f32(int dtype, const float* src, int64_t n, void* dst, dcb_stream stream);
 
+/* ---- weight packing (once per parameter version): checkpoint tensors (diffusers layout, fp32, DEVICE) -> the operand
+ * layouts dcb_gemm consumes, in `dtype`.  Sums are formed in fp32 and rounded once (as dcb_cast_f32). ---------------------- */
+/* conv weight [Cout][Cin][kh][kw] -> out [Cout][kpad]: column (ky*kw + kx)*Cin + ci, zero padded to kpad (3x3 / 1x1 convs,
+ * conv_in with K padded to 64, DiT patch embedding with K order (py, px, c)) */
+int dcb_pack_conv(int dtype, const float* w_oihw, int Cout, int Cin, int kh, int kw, int kpad, void* out, dcb_stream stream);
+/* GEGLU projection w [2*inner][C] (rows [0,inner) value, [inner,2*inner) gate: diffusers' chunk order), bias [2*inner] ->
+ * rows interleaved per 128 so that a 256-wide GEMM tile holds [128 value | 128 gate] of the same outputs (DCB_ACT_GEGLU) */
+int dcb_pack_geglu(int dtype, const float* w, const float* bias, int inner, int C, void* w_out, float* bias_out,
+                   dcb_stream stream);
+/* Upsample2D (nearest 2x) + conv3x3 [Cout][Cin][3][3] -> out [4][Cout][4*Cin]: phase 2a + b, K order (ty, tx, cin); the 3x3
+ * taps that land on the same low-resolution pixel are summed (dcb_gemm_desc.up_phase consumes phase 2a + b) */
+int dcb_pack_upsample(int dtype, const float* w_oihw, int Cout, int Cin, void* out, dcb_stream stream);
+/* dst[dst_row0 + r][dst_col0 + c] = (dtype) src[r][c], r < rows, c < cols: builds row- or column-concatenated operands (fused
+ * QKV [3C][C], all time-embedding projections [sum Cout][tdim], [conv2 | 1x1 shortcut] along K) */
+int dcb_pack_rows(int dtype, const float* src, int src_ld, int rows, int cols, void* dst, int dst_ld, int dst_row0,
+                  int dst_col0, dcb_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -447,4 +447,8 @@ def test_c_abi_argument_validation_returns_codes_not_crashes():
     assert lib.dcb_eps_mse(_lib.BF16, 1, 1, None, 1, 0, 16, 1, 1, None) == -1 and "div" in err()
     assert lib.dcb_upsample2x(_lib.BF16, 1, 1, 4, 4, 12, 1, None) == -1
     assert lib.dcb_expand_samples(_lib.BF16, 1, 2, 1, 3, 1, None) == -1
+    assert lib.dcb_pack_conv(_lib.BF16, 1, 8, 4, 3, 3, 20, 1, None) == -1 and "kpad" in err()
+    assert lib.dcb_pack_geglu(_lib.BF16, 1, None, 100, 8, 1, None, None) == -1 and "multiple of 128" in err()
+    assert lib.dcb_pack_upsample(7, 1, 8, 8, 1, None) == -1 and "dtype" in err()
+    assert lib.dcb_pack_rows(_lib.BF16, 1, 4, 2, 8, 1, 8, 0, 0, None) == -1
     assert lib.dcb_launch_count() == 0          # nothing was launched

@@ -323,3 +323,32 @@ def test_attention_tcgen05_fast_path_decided_per_head(dev):
     alone0 = E.attention(_ctx(dev, "bf16"), qb[:N].contiguous(), 1, N, heads, d)
     alone2 = E.attention(_ctx(dev, "bf16"), qb[2 * N:].contiguous(), 1, N, heads, d)
     assert torch.equal(out[:N], alone0) and torch.equal(out[2 * N:], alone2)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_pack_entry_points_match_the_torch_layout_code(dev, precision):
+    """dcb_pack_conv / dcb_pack_geglu / dcb_pack_upsample / dcb_pack_rows (the C-ABI packers a non-Python binder uses) against
+    the plain torch layout code they replaced: bit-identical (same fp32 sums in the same order, same rounding)."""
+    from dcb200 import engine as E
+    torch.manual_seed(0)
+    ctx = E.Ctx(device=dev, precision=precision)
+    dt = ctx.tdtype
+    w = torch.randn(48, 20, 3, 3, device=dev)
+    ref = torch.zeros(48, 192, device=dev)
+    ref[:, :180] = w.permute(0, 2, 3, 1).reshape(48, -1)
+    assert torch.equal(E.pack_conv(ctx, w, 192), E.cast(ctx, ref))
+    wp = torch.randn(32, 5, 4, 4, device=dev)                          # DiT patch embedding: K order (py, px, c)
+    assert torch.equal(E.pack_conv(ctx, wp), E.cast(ctx, wp.permute(0, 2, 3, 1).reshape(32, -1).contiguous()))
+    inner, C = 256, 24
+    gw, gb = torch.randn(2 * inner, C, device=dev), torch.randn(2 * inner, device=dev)
+    rw = torch.cat([gw[:inner].reshape(inner // 128, 128, C), gw[inner:].reshape(inner // 128, 128, C)], 1).reshape(2 * inner, C)
+    rb = torch.cat([gb[:inner].reshape(-1, 128), gb[inner:].reshape(-1, 128)], 1).reshape(-1)
+    pw, pb = E.pack_geglu(ctx, gw, gb)
+    assert torch.equal(pw, E.cast(ctx, rw.contiguous())) and torch.equal(pb, rb)
+    wu = torch.randn(16, 12, 3, 3, device=dev)
+    for got, want in zip(E.pack_upsample(ctx, wu), E.fold_upsample_weights(wu)):
+        assert got.dtype == dt and torch.equal(got, E.cast(ctx, want))
+    a, b = torch.randn(7, 10, device=dev), torch.randn(5, 10, device=dev)
+    assert torch.equal(E.pack_rows(ctx, [a, b], 0), E.cast(ctx, torch.cat([a, b], 0)))
+    c = torch.randn(7, 6, device=dev)
+    assert torch.equal(E.pack_rows(ctx, [a, c], 1), E.cast(ctx, torch.cat([a, c], 1).contiguous()))
