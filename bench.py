@@ -350,14 +350,14 @@ def run_ours(args):
             "achieved_basis": "one read + one write of every normalised tensor / summed CUDA-event durations",
             "launches_per_step": n_gn // passes, "kernel_share_of_step": (gn_ms / passes) / (ms / args.steps)},
     }
-    tr = os.path.join(ROOT, "profiles", "r01_traffic.json")   # per-launch DRAM bytes of the dominant kernel from the
+    tr = os.path.join(ROOT, "profiles", "r02_traffic.json")   # per-launch DRAM bytes of the dominant kernel from the
     if os.path.exists(tr):                                     # committed `ncu --set full` capture (same workload)
         try:
             tj = json.load(open(tr))
             per_eval = tj.get(args.workload + "_dram_bytes_per_eval")
             if per_eval:   # ncu DRAM bytes of all GEMM launches per eval -> per launch at this run's launch size
                 roofline["traffic"] = per_eval * (evals_per_step / world) / max(n_gemm // passes, 1)
-                roofline["traffic_source"] = "ncu dram__bytes_read+write of every tcgen05 GEMM launch of one pass (profiles/r01_traffic.json), scaled to this launch size"
+                roofline["traffic_source"] = "ncu dram__bytes_read+write of every tcgen05 GEMM launch of one pass (profiles/r02_traffic.json), scaled to this launch size"
         except (OSError, ValueError):
             pass
 
