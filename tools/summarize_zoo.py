@@ -6,10 +6,10 @@ import csv, json, os, re, subprocess, sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
-rep = sys.argv[1] if len(sys.argv) > 1 else os.path.join(G, "r02_zoo.ncu-rep")
+# the report itself (hundreds of MB with --import-source) stays on the GPU box: it is exported there with
+#   ncu -i gpurun_out/r02_zoo.ncu-rep --page raw --csv > gpurun_out/r02_zoo_raw.csv
 cases = [json.loads(l) for l in open(os.path.join(G, "zoo.json")) if l.startswith("{")]
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-rows = list(csv.reader(raw.splitlines()))
+rows = list(csv.reader(open(sys.argv[1] if len(sys.argv) > 1 else os.path.join(G, "r02_zoo_raw.csv"))))
 hdr, units, data = rows[0], rows[1], rows[2:]
 col = {h: i for i, h in enumerate(hdr)}
 peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
