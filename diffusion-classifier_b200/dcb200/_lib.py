@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libdcb200.so")
+LIB_PATH = os.environ.get("DCB_LIB") or os.path.join(HERE, "libdcb200.so")    # DCB_LIB: experiment builds (tools/ only)
 
 F32, BF16 = 0, 1
 ACT_NONE, ACT_SILU, ACT_GELU_TANH, ACT_GEGLU = 0, 1, 2, 3

@@ -79,6 +79,27 @@ __device__ __forceinline__ float ex2f(float x) {
   return y;
 }
 
+// 2^x for x in [-126, 0] on the FMA / ALU pipes (no MUFU op): round-to-nearest split x = n + f through the 1.5 * 2^23 magic
+// constant (n sits in the low mantissa bits of t), cubic minimax 2^f on [-0.5, 0.5] (max relative error 7.5e-5, far below
+// the bf16 rounding of P), exponent add: 7 more instructions than the MUFU form.  The single-pass kernel is bound by the MUFU
+// pipe on paper (16 ex2 / clk / SM: ncu XU pipe 65 %, issue slots 55 %), so moving a share of the exponentials here looked
+// like free throughput.  MEASURED (tools/attn_micro.py, same box, B = 16, incl. the norm pre-pass): never 652 TF/s, one in
+// eight 656, one in four 580, one in two 559 -- the softmax warps are as much issue / dependency bound as MUFU bound, and
+// every 7 extra instructions cost more than the MUFU slot they free.  Kept as a compile-time experiment
+// (-DDCB_ATTN_POLY_MASK=6), off in the product.
+#ifndef DCB_ATTN_POLY_MASK
+#define DCB_ATTN_POLY_MASK (-1)   // pairs (i, i + 1) with (i & MASK) == 0 evaluate element i + 1 on the FMA pipe; -1 = never (product)
+#endif
+__device__ __forceinline__ float ex2_poly(float x) {
+  const float magic = 12582912.f;
+  const float t = x + magic;
+  const float f = x - (t - magic);
+  float pl = fmaf(0.0551716685295105f, f, 0.2426111251115799f);
+  pl = fmaf(pl, f, 0.6932609677314758f);
+  pl = fmaf(pl, f, 0.9999280571937561f);
+  return __int_as_float(__float_as_int(pl) + (__float_as_int(t) << 23));
+}
+
 // the single-pass kernel is exact iff nothing underflows: max|q| max|k| c <= 50 bounds every (M_i - s_ij) c by 100 < 126
 // Decided per (batch, head) -- blockIdx.z, blockIdx.y -- from that head's own max|q|^2, max|k|^2, so which of the two kernels
 // scores a sample never depends on the other samples of the launch (results stay independent of the batch composition).
@@ -553,7 +574,8 @@ flash_attn_tc_fast_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
           float p0 = ex2f(fmaf(__uint_as_float(sv[i]), sc, -msc));
-          float p1 = ex2f(fmaf(__uint_as_float(sv[i + 1]), sc, -msc));
+          const float x1 = fmaf(__uint_as_float(sv[i + 1]), sc, -msc);       // in [-100.2, 0] (at_fast_ok)
+          float p1 = (DCB_ATTN_POLY_MASK >= 0 && (i & DCB_ATTN_POLY_MASK) == 0) ? ex2_poly(x1) : ex2f(x1);
           if (valid < 64) {
             if (c + i >= valid) p0 = 0.f;
             if (c + i + 1 >= valid) p1 = 0.f;
