@@ -666,6 +666,55 @@ __global__ void __launch_bounds__(256) attn_norms_kernel(const __nv_bfloat16* __
   }
 }
 
+// Row-contiguous version (heads <= 16): a warp reads WHOLE token rows of q (blockIdx.y = 0) or k (= 1) -- heads x 128
+// contiguous bytes, 16 bytes per lane and step -- instead of one 128-byte head slice out of every 4.6 KB row as above
+// (measured on the DiT-B/4 step: 1.5 ms per launch = 2.1 TB/s there).  Eight consecutive lanes hold one head of a token.
+__global__ void __launch_bounds__(256) attn_norms_rows_kernel(const __nv_bfloat16* __restrict__ q,
+                                                              const __nv_bfloat16* __restrict__ k, int ld, int N, int heads,
+                                                              float* __restrict__ out) {
+  __shared__ float s_max[8][16];
+  const int which = blockIdx.y, b = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const __nv_bfloat16* src = which ? k : q;
+  const int chunks = heads * 8;                 // 16-byte chunks per token row
+  float mx[4] = {0.f, 0.f, 0.f, 0.f};           // running maxima of the heads this lane group sees: chunk slot j -> head 4 j + lane / 8
+  const int t_end = min(N, (int)(blockIdx.x + 1) * 64);
+  for (int tkn = blockIdx.x * 64 + warp; tkn < t_end; tkn += 8) {
+    const __nv_bfloat16* row = src + ((int64_t)b * N + tkn) * ld;
+    uint4 raw[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (lane + 32 * j < chunks) raw[j] = *reinterpret_cast<const uint4*>(row + (lane + 32 * j) * 8);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float n2 = 0.f;
+      if (lane + 32 * j < chunks) {
+        float f[8];
+        unpack_bf16x8(raw[j], f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) n2 = fmaf(f[i], f[i], n2);
+      }
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) n2 += __shfl_xor_sync(0xffffffffu, n2, o);
+      mx[j] = fmaxf(mx[j], n2);
+    }
+  }
+  if ((lane & 7) == 0) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (4 * j + (lane >> 3) < heads) s_max[warp][4 * j + (lane >> 3)] = mx[j];
+  }
+  __syncthreads();
+  if (threadIdx.x < heads) {
+    float m = s_max[0][threadIdx.x];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) m = fmaxf(m, s_max[w][threadIdx.x]);
+    int* o2 = reinterpret_cast<int*>(out);
+    atomicMax(o2 + 2 + (b * heads + threadIdx.x) * 2 + which, __float_as_int(m));
+    atomicMax(o2 + which, __float_as_int(m));
+  }
+}
+
 static int encode_tok_map(CUtensorMap* map, const void* base, int ld, int N, int B, int width) {
   auto enc = tc_encode_fn();
   DCB_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
@@ -708,8 +757,12 @@ int launch_flash_tc(const void* q, const void* k, const void* v, int ld, int B, 
   dim3 grid((N + 255) / 256, heads, B);
   if (use_fast) {
     cudaMemsetAsync(norms_ws, 0, sizeof(float) * (2 + 2 * B * heads), st);
-    attn_norms_kernel<<<dim3((N + 255) / 256, heads, B), 256, 0, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k, ld, N,
-                                                                        norms_ws);
+    if (heads <= 16)
+      attn_norms_rows_kernel<<<dim3((N + 63) / 64, 2, B), 256, 0, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k, ld, N,
+                                                                         heads, norms_ws);
+    else
+      attn_norms_kernel<<<dim3((N + 255) / 256, heads, B), 256, 0, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k, ld, N,
+                                                                          norms_ws);
     DCB_CHECK_LAUNCH("attn_norms");
     flash_attn_tc_fast_kernel<<<grid, ATF_THREADS, smem, st>>>(mq, mk, mv, p, (__nv_bfloat16*)out);
     DCB_CHECK_LAUNCH("flash_attn_tc_fast");
