@@ -109,7 +109,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       const int x0 = tx * p.bw, y0 = ty * p.bh, nb0 = tb * p.bn;
       auto issue = [&](const TcSeg& sg, int nbs, int kb, int kb_glob) {
         const CUtensorMap* mp = sg.map == 0 ? &mapA0 : (sg.map == 1 ? &mapA1 : &mapA2);
-        mbar_wait(empty0 + stage * 8, phase ^ 1);
+        mbar_wait_long(empty0 + stage * 8, phase ^ 1);
         if (elect_one()) {
           const uint32_t fb = full0 + stage * 8;
           mbar_expect_tx(fb, (uint32_t)stage_bytes);
@@ -158,7 +158,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     const uint32_t lo_base = ((smem_base & 0x3FFFFu) >> 4) | (1u << 16), lo_step = (uint32_t)stage_bytes >> 4;
     uint32_t alo = lo_base, fb = full0, eb = empty0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      mbar_wait(smem_u32(&tempty_bar[as]), aphase ^ 1);
+      mbar_wait_long(smem_u32(&tempty_bar[as]), aphase ^ 1);
       const uint32_t d_tmem = tmem_base + (uint32_t)(as * 256);
       const uint32_t tfull_addr = smem_u32(&tfull_bar[as]);
       for (int kb = 0; kb < p.total_kb; ++kb) {
@@ -213,7 +213,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                         smem_u32(&tempty_bar[as]), true, bar_id);
         continue;
       }
-      mbar_wait(smem_u32(&tfull_bar[as]), aphase);
+      mbar_wait_long(smem_u32(&tfull_bar[as]), aphase);
       tc_fence_after();
       float mse_acc = 0.f;
       if (!geglu) {

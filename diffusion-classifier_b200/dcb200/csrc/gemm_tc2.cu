@@ -123,7 +123,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
       const int tn = tile % p.n_tiles, tp = tile / p.n_tiles;
       const SubTile s0 = decode_sub(p, 2 * tp), s1 = decode_sub(p, 2 * tp + 1);
       auto load_b = [&](int kb_glob) {
-        if (dbg & 64) mbar_spin(b_empty0 + bi * 8, bph ^ 1); else mbar_wait(b_empty0 + bi * 8, bph ^ 1);
+        if (dbg & 64) mbar_spin(b_empty0 + bi * 8, bph ^ 1); else mbar_wait_long(b_empty0 + bi * 8, bph ^ 1);
         if (elect_one()) {
           const uint32_t fb = b_full0 + bi * 8;
           if (no_tma) mbar_arrive(fb);
@@ -139,7 +139,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
         const int h0 = p.halo_div > 1 ? s0.nb0 / p.halo_div : s0.nb0;
         for (int kx = 0; kx < 3; ++kx)
           for (int kb = 0; kb < p.nkb_conv; ++kb) {
-            mbar_wait(a_empty0 + ai * 8, aph ^ 1);
+            mbar_wait_long(a_empty0 + ai * 8, aph ^ 1);
             if (elect_one()) {
               const uint32_t fa = a_full0 + ai * 8;
               if (no_tma) mbar_arrive(fa);
@@ -158,7 +158,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
         const int n_items = 3 * p.nkb_conv;
         for (int it = 0; it < n_items; ++it) {
             const int ky = p.kb_outer ? it % 3 : it / p.nkb_conv, kb = p.kb_outer ? it / 3 : it % p.nkb_conv;
-            if (dbg & 64) mbar_spin(a_empty0 + ai * 8, aph ^ 1); else mbar_wait(a_empty0 + ai * 8, aph ^ 1);
+            if (dbg & 64) mbar_spin(a_empty0 + ai * 8, aph ^ 1); else mbar_wait_long(a_empty0 + ai * 8, aph ^ 1);
             if (elect_one()) {
               const uint32_t fa = a_full0 + ai * 8;
               const uint32_t sa = a_ring0 + (uint32_t)(ai * p.a_slot_bytes);
@@ -177,7 +177,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
       auto issue_tap = [&](const TcSeg& sg, int kb, int kb_glob) {
         const CUtensorMap* mp = sg.map == 0 ? &mapA0 : (sg.map == 1 ? &mapA1 : &mapA2);
         const int n0s = sg.div > 1 ? s0.nb0 / sg.div : s0.nb0, n1s = sg.div > 1 ? s1.nb0 / sg.div : s1.nb0;
-        mbar_wait(a_empty0 + ai * 8, aph ^ 1);
+        mbar_wait_long(a_empty0 + ai * 8, aph ^ 1);
         if (elect_one()) {
           const uint32_t fa = a_full0 + ai * 8;
           const uint32_t sa = a_ring0 + (uint32_t)(ai * p.a_slot_bytes);
@@ -242,7 +242,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
     uint32_t a_off = 0, b_lo = b_lo_base;           // a_off: (slot index * slot bytes) >> 4
     uint32_t a_fb = a_full0, a_eb = a_empty0, b_fb = b_full0, b_eb = b_empty0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      { long long c0 = prof ? clock64() : 0; mbar_wait(smem_u32(&tempty_bar[as * 2 + sub]), aphase ^ 1); if (prof) w_te += clock64() - c0; }
+      { long long c0 = prof ? clock64() : 0; mbar_wait_long(smem_u32(&tempty_bar[as * 2 + sub]), aphase ^ 1); if (prof) w_te += clock64() - c0; }
       const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.acc_stage_cols + sub * p.acc_sub_cols);
       const uint32_t tfull_addr = smem_u32(&tfull_bar[as * 2 + sub]);
       uint32_t accumulate = 0;
@@ -303,7 +303,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
       const int tn = tile % p.n_tiles, tp = tile / p.n_tiles;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.acc_stage_cols + grp * p.acc_sub_cols);
       if (dbg & 2) {
-        mbar_wait(smem_u32(&tfull_bar[as * 2 + grp]), aphase);
+        mbar_wait_long(smem_u32(&tfull_bar[as * 2 + grp]), aphase);
         tc_fence_after();
         tc_fence_before();
         __syncwarp();
@@ -326,7 +326,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
         const bool row_ok = tm_lin < p.m_tiles && x < p.OW && y < p.OH && nb < p.NB;
         const int pix = y * p.OW + x;
         const int m = nb * e.rows_per_sample + pix;
-        mbar_wait(smem_u32(&tfull_bar[as * 2 + grp]), aphase);
+        mbar_wait_long(smem_u32(&tfull_bar[as * 2 + grp]), aphase);
         tc_fence_after();
         float mse_acc = 0.f;
         for (int c = 0; c < p.BN; c += 16) {

@@ -131,7 +131,7 @@ gemm_tc2x_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
         const int dv = second ? p.div1 : p.div0;
         const int smp = dv > 1 ? t.nb / dv : t.nb;
         auto load_box = [&](int j) {
-          mbar_wait(a_empty0 + ai * 8, aph ^ 1);
+          mbar_wait_long(a_empty0 + ai * 8, aph ^ 1);
           if (elect_one()) {
             const uint32_t fa = a_full0 + ai * 8;
             mbar_expect_tx(fa, 130u * 128u);
@@ -148,7 +148,7 @@ gemm_tc2x_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
         const int smp = sg.div > 1 ? t.nb / sg.div : t.nb;
         for (int kb = 0; kb < sg.nkb; ++kb) {
           for (int sub = 0; sub < 2; ++sub) {       // one [128 px x 64 ch] tile per output row, in two consecutive slots
-            mbar_wait(a_empty0 + ai * 8, aph ^ 1);
+            mbar_wait_long(a_empty0 + ai * 8, aph ^ 1);
             if (elect_one()) {
               const uint32_t fa = a_full0 + ai * 8;
               mbar_expect_tx(fa, (uint32_t)TC_A_BYTES);
@@ -170,7 +170,7 @@ gemm_tc2x_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
       const int conv_blocks = 9 * p.nkb_conv;
       for (int i = 0; i < conv_blocks + tap_items; ++i) {
         const int kb_glob = i < conv_blocks ? (i % 9) * p.nkb_conv + i / 9 : i;
-        mbar_wait(b_empty0 + bi * 8, bph ^ 1);
+        mbar_wait_long(b_empty0 + bi * 8, bph ^ 1);
         if (elect_one()) {
           const uint32_t fb = b_full0 + bi * 8;
           mbar_expect_tx(fb, (uint32_t)b_bytes);
@@ -225,7 +225,7 @@ gemm_tc2x_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
       if (++bi == p.b_slots) { bi = 0; bph ^= 1; b_lo = b_lo_base; b_fb = b_full0; b_eb = b_empty0; }
     };
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      mbar_wait(smem_u32(&tempty_bar[as * 2 + sub]), aphase ^ 1);
+      mbar_wait_long(smem_u32(&tempty_bar[as * 2 + sub]), aphase ^ 1);
       uint32_t accumulate = 0;
       for (int kb = 0; kb < p.nkb_conv; ++kb) {
         if (sub == 1) skip_box(0);
@@ -269,7 +269,7 @@ gemm_tc2x_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
       const int tm_lin = t.tm0 + grp * p.tiles_x;        // output row y0 + grp
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 256 + grp * 128);
       if (dbg & 2) {
-        mbar_wait(smem_u32(&tfull_bar[as * 2 + grp]), aphase);
+        mbar_wait_long(smem_u32(&tfull_bar[as * 2 + grp]), aphase);
         tc_fence_after();
         tc_fence_before();
         __syncwarp();
@@ -285,7 +285,7 @@ gemm_tc2x_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
         const bool row_ok = x < p.OW;
         const int pix = y * p.OW + x;
         const int m = t.nb * e.rows_per_sample + pix;
-        mbar_wait(smem_u32(&tfull_bar[as * 2 + grp]), aphase);
+        mbar_wait_long(smem_u32(&tfull_bar[as * 2 + grp]), aphase);
         tc_fence_after();
         float mse_acc = 0.f;
         for (int c = 0; c < p.BN; c += 16) {
@@ -338,7 +338,7 @@ gemm_tc2x_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
         }
         for (int j = 0; j < 4; ++j) {
           const int y = tp.y0 - 1 + j;
-          mbar_wait(a_full0 + ai * 8, aph);
+          mbar_wait_long(a_full0 + ai * 8, aph);
           if (y >= 0 && y < p.OH && !(dbg & 1)) {       // rows outside the image stay zero (TMA fill) = the conv padding
             const uint32_t base = a_ring0 + (uint32_t)(ai * TX_BOX);
 #pragma unroll
@@ -365,7 +365,7 @@ gemm_tc2x_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
         }
       }
       for (int k = 0; k < 2 * tap_items; ++k) {    // plain tap tiles (raw tensors): pass through
-        mbar_wait(a_full0 + ai * 8, aph);
+        mbar_wait_long(a_full0 + ai * 8, aph);
         __syncwarp();
         if (lane == 0) mbar_arrive(a_ready0 + ai * 8);
         if (++ai == p.nbox) { ai = 0; aph ^= 1; }
