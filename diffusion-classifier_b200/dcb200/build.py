@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libdcb200.so")
-SOURCES = ["api.cu", "gemm_tc.cu", "gemm_tc2.cu", "gemm_tc2x.cu", "gemm_simt.cu", "norm.cu", "elementwise.cu", "pack.cu", "attention.cu", "attention_tc.cu"]
+SOURCES = ["api.cu", "gemm_tc.cu", "gemm_tc2.cu", "gemm_tc2x.cu", "gemm_tc3.cu", "gemm_simt.cu", "norm.cu", "elementwise.cu", "pack.cu", "attention.cu", "attention_tc.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr", "-Xptxas", "-v"]

@@ -396,6 +396,7 @@ static int encode_a_map(CUtensorMap* map, const SegDev& s, int NBsrc, const TcGe
 int launch_gemm_tc2(const GemmDev& g, cudaStream_t st, int bw, int bh, int bn, int tiles_x, int tiles_y, int tiles_nb,
                     int BN, int uniform, int staged);
 int launch_gemm_tc2x(const GemmDev& g, cudaStream_t st, int tiles_x, int BN, int uniform, int staged, bool dry_run);
+int launch_gemm_tc3(const GemmDev& g, cudaStream_t st, int uniform);
 
 // dry_run: everything but the launch (dcb_gemm_xf_layout: would this descriptor run on the kernel that can apply a fused
 // GroupNorm transform?)
@@ -501,6 +502,11 @@ int launch_gemm_tc(const GemmDev& g, cudaStream_t st, bool dry_run) {
       rc = launch_gemm_tc2(g, st, t.bw, t.bh, t.bn, t.tiles_x, t.tiles_y, t.tiles_nb, 256, p.uniform, 0);
       if (rc != DCB_EUNSUPPORTED) return rc;
     }
+  }
+  // plain linear layers with N a multiple of 256 and enough rows: CTA pairs, 256 x 256 tiles (gemm_tc3.cu)
+  if (p.staged && g.xf_a == nullptr && !dry_run && !(knobs() & DCB_KNOB_NO_TC3)) {
+    rc = launch_gemm_tc3(g, st, p.uniform);
+    if (rc != DCB_EUNSUPPORTED) return rc;
   }
   // (also the fused eps-MSE of conv_out -- N = out_channels, nothing stored: with 9 separately loaded taps it is bound by
   //  L2->SMEM traffic, the x-halo boxes cut that 3x)

@@ -36,6 +36,24 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// arrive on the barrier at the same shared-memory offset in CTA `cta` of this cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(bar), "r"(cta)
+      : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_cta_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
 __device__ __forceinline__ uint64_t globaltimer_ns() {
   uint64_t t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -585,7 +603,7 @@ constexpr int TC_EPI_HALF_BYTES = 128 * 64 * 2 + 512 * 4 + 4 * 128 * 4;
 
 __device__ __forceinline__ void staged_epilogue_half(const EpiGeom& gq, const EpiDev& e, uint8_t* stg8, int parity, int tm_lin,
                                                      int tn, int BN, uint32_t taddr, uint32_t full_bar, uint32_t full_parity,
-                                                     uint32_t empty_bar, int bar_id) {
+                                                     uint32_t empty_bar, int bar_id, int release_cta = -1) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q = warp & 3;
   const int r = q * 32 + lane;           // accumulator row (TMEM lane) owned in the thread-per-row pass
@@ -713,7 +731,10 @@ __device__ __forceinline__ void staged_epilogue_half(const EpiGeom& gq, const Ep
     if (h0 + 64 >= ncols_out) {     // accumulator fully drained: hand the TMEM stage back to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(empty_bar);
+      if (lane == 0) {
+        if (release_cta < 0) mbar_arrive(empty_bar);
+        else mbar_arrive_cluster(empty_bar, (uint32_t)release_cta);    // CTA pair: the MMA warp lives in the leader CTA
+      }
     }
     epi_bar(bar_id);
     // ---- coalesced copy-out of this half + P[rr0] of the canonical statistics tree (see staged_epilogue) ----

@@ -557,3 +557,50 @@ def test_gn_fused_into_conv_operand_is_bit_identical(dev, NB, H, W, C0, C1, div1
         assert rel_err(fused[0], want) < 2e-3
     else:
         assert rel_err(fused[0], ref) < 6e-3
+
+
+@pytest.mark.parametrize("M,K,N,extra", [
+    (40000, 768, 768, "plain"),          # M not a multiple of 256 (last pair: peer CTA fully out of range rows masked)
+    (33000, 768, 2304, "bias"),          # DiT QKV
+    (20480, 768, 3072, "gelu"),          # DiT FF1 (GELU-tanh epilogue)
+    (20480, 3072, 768, "gate_res"),      # DiT FF2: adaLN gate + residual, K = 3072 (48 K blocks)
+    (51200, 512, 512, "rowvec_idx_c_off"),   # U-Net attention out-projection: gathered row vector, K range inside a wider tensor
+])
+def test_tc3_cta_pair_linear(dev, M, K, N, extra):
+    """gemm_tc3_kernel (tcgen05 cta_group::2: a pair of CTAs computes a 256 x 256 tile, each loading its own A rows and half
+    of W) vs the one-CTA kernel it replaces for these layers (DCB_KNOB_NO_TC3: bit for bit -- same K order, same staged
+    epilogue arithmetic) and vs torch fp32 math."""
+    from dcb200 import _lib as L
+    from dcb200 import engine as E
+    torch.manual_seed(0)
+    ctx = _ctx(dev)
+    Cw = K + 128 if extra == "rowvec_idx_c_off" else K
+    x = _bf(M, Cw, dev=dev)
+    w = _bf(N, K, dev=dev, scale=0.05)
+    kw = {}
+    xs = x[:, 64:64 + K] if extra == "rowvec_idx_c_off" else x
+    ref = xs.float() @ w.float().t()
+    rpg = 128 * 25
+    ngrp = (M + rpg - 1) // rpg
+    if extra != "plain":
+        b = torch.randn(N, device=dev)
+        kw["bias"] = b
+        ref = ref + b
+    if extra == "gelu":
+        kw["act"] = L.ACT_GELU_TANH
+        ref = F.gelu(ref, approximate="tanh")
+    if extra == "gate_res":
+        gate = torch.randn(ngrp, N, device=dev)
+        res = _bf(M, N, dev=dev)
+        kw.update(gate=gate, gate_ld=N, rows_per_group=rpg, residual=res, res_ld=N)
+        ref = ref * gate.repeat_interleave(rpg, 0)[:M] + res.float()
+    if extra == "rowvec_idx_c_off":
+        rv = torch.randn(7, N, device=dev)
+        idx = torch.randint(0, 7, (ngrp,), device=dev, dtype=torch.int32)
+        kw.update(rowvec=rv, rowvec_ld=N, rowvec_idx=idx, rows_per_group=rpg, K=K, c_off=64)
+        ref = ref + rv[idx.long()].repeat_interleave(rpg, 0)[:M]
+    out = E.linear(ctx, x, w, N, **kw)
+    with L.knob("NO_TC3"):
+        one = E.linear(ctx, x, w, N, **kw)
+    assert out.dtype == torch.bfloat16 and rel_err(out, ref) < 6e-3
+    assert torch.equal(out, one)
