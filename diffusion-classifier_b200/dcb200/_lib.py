@@ -95,7 +95,7 @@ _lib = None
 # DCB_KNOB_* of include/dcb200.h.  The environment variables of the same name (DCB_NO_TC2=1 ...) are read ONCE, when the
 # library is loaded; tests switch at run time with ``knob()``.
 KNOBS = {"NO_TC2": 1, "TC2_NO_HALO": 2, "TC2_NO_YHALO": 4, "NO_TC2_MSE": 8, "TC2_WIDE": 16, "TC_DIRECT_EPILOGUE": 32,
-         "ATTN_NO_TC": 64, "ATTN_NO_FAST": 128, "NO_TC3": 256}
+         "ATTN_NO_TC": 64, "ATTN_NO_FAST": 128, "NO_TC3": 256, "TC2X_NO_PAIR": 512}
 
 
 class DcbError(RuntimeError):

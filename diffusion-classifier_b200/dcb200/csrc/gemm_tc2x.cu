@@ -40,6 +40,8 @@ struct TxParams {
   int nkb_conv, nkb0;          // channel blocks of the (concatenated) conv input; blocks >= nkb0 come from source 1 (map 1)
   int div0, div1;              // sample divisors of the two raw sources
   int tiles_x, OH, OW, NB, BN, n_tiles, total_tiles, m_tiles;
+  int num_P;                   // row-pair tiles (m_tiles / 2); total_tiles counts the launch's work items: row-pair tiles x N tiles,
+                               // or (PAIR) CTA-pair items = ceil(num_P / 2) x N tiles, two row-pair tiles each
   int nbox, b_slots;
   uint32_t idesc;
   int uniform, staged, silu, xf_C;
@@ -53,6 +55,10 @@ struct TxPair {
 };
 __device__ __forceinline__ TxPair decode_pair(const TxParams& p, int P) {
   TxPair t;
+  if (P >= p.num_P) {          // the odd tail of a CTA pair: boxes land as zeros (sample out of range), every row is masked
+    t.x0 = 0; t.y0 = 0; t.nb = p.NB; t.tm0 = p.m_tiles;
+    return t;
+  }
   const int tx = P % p.tiles_x;
   P /= p.tiles_x;
   const int hp = p.OH >> 1;
@@ -63,13 +69,20 @@ __device__ __forceinline__ TxPair decode_pair(const TxParams& p, int P) {
   return t;
 }
 
+// PAIR: two CTAs on the SMs of one TPC (cluster of 2) run their row-pair tiles in lockstep and share every weight block:
+// each lands only HALF of it (N / 2 rows), the leader's two MMA warps issue tcgen05.mma.cta_group::2 with M = 256 -- output
+// row s of BOTH CTAs at once, all N columns of W, half from each CTA's shared memory -- and its commits are multicast to both
+// CTAs' barriers; transform / epilogue warps of the peer signal the leader's barriers (mapa + remote arrive).  Weight traffic
+// L2 -> SMEM and the weight ring halve (4 slots = 32 KB instead of 64 KB: two more row boxes).
+template <bool PAIR>
 __global__ void __launch_bounds__(TX_THREADS, 1)
 gemm_tc2x_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                  const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB,
                  const __grid_constant__ TxParams p, const __grid_constant__ EpiDev e) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int b_bytes = p.BN * TC_BK * 2;
+  const int b_rows = PAIR ? p.BN / 2 : p.BN;       // weight rows this CTA lands per block
+  const int b_bytes = b_rows * TC_BK * 2;
   uint8_t* a_ring = smem;
   uint8_t* b_ring = a_ring + (size_t)p.nbox * TX_BOX;
   uint64_t* bars = reinterpret_cast<uint64_t*>(b_ring + (size_t)p.b_slots * b_bytes);
@@ -85,25 +98,36 @@ gemm_tc2x_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
   uint8_t* stg8 = reinterpret_cast<uint8_t*>(bars) + 512;
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const uint32_t rank = PAIR ? cluster_cta_rank() : 0u;
+  // work items of this CTA (pair): item -> (row-pair tile P, N tile tn); both CTAs of a pair walk the same items
+  const int item0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, item_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  auto tile_P = [&](int item) { return PAIR ? 2 * (item / p.n_tiles) + (int)rank : item / p.n_tiles; };
+  if (PAIR) cluster_sync_all();
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&mapA0);
     prefetch_tmap(&mapB);
     for (int i = 0; i < p.nbox; ++i) {
       mbar_init(smem_u32(&a_full[i]), 1);
-      mbar_init(smem_u32(&a_ready[i]), TX_XF_WARPS);
+      mbar_init(smem_u32(&a_ready[i]), PAIR ? 2 * TX_XF_WARPS : TX_XF_WARPS);   // PAIR: the leader's counts both CTAs' warps
       mbar_init(smem_u32(&a_empty[i]), 2);
     }
-    for (int i = 0; i < p.b_slots; ++i) { mbar_init(smem_u32(&b_full[i]), 1); mbar_init(smem_u32(&b_empty[i]), 2); }
-    for (int i = 0; i < 4; ++i) { mbar_init(smem_u32(&tfull_bar[i]), 1); mbar_init(smem_u32(&tempty_bar[i]), 4); }
+    for (int i = 0; i < p.b_slots; ++i) { mbar_init(smem_u32(&b_full[i]), PAIR ? 2 : 1); mbar_init(smem_u32(&b_empty[i]), 2); }
+    for (int i = 0; i < 4; ++i) { mbar_init(smem_u32(&tfull_bar[i]), 1); mbar_init(smem_u32(&tempty_bar[i]), PAIR ? 8 : 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 #ifdef DCB_PROBES
@@ -122,8 +146,8 @@ gemm_tc2x_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
     // ===================== TMA producer =====================
     int ai = 0;
     uint32_t aph = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const TxPair t = decode_pair(p, tile / p.n_tiles);
+    for (int tile = item0; tile < p.total_tiles; tile += item_step) {
+      const TxPair t = decode_pair(p, tile_P(tile));
       for (int kb = 0; kb < p.nkb_conv; ++kb) {
         const bool second = kb >= p.nkb0;
         const CUtensorMap* mp = second ? &mapA1 : &mapA0;
@@ -165,7 +189,7 @@ gemm_tc2x_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
     int bi = 0;
     uint32_t bph = 0;
     prefetch_tmap(&mapB);
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    for (int tile = item0; tile < p.total_tiles; tile += item_step) {
       const int tn = tile % p.n_tiles;
       const int conv_blocks = 9 * p.nkb_conv;
       for (int i = 0; i < conv_blocks + tap_items; ++i) {
@@ -173,15 +197,23 @@ gemm_tc2x_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
         mbar_wait_long(b_empty0 + bi * 8, bph ^ 1);
         if (elect_one()) {
           const uint32_t fb = b_full0 + bi * 8;
-          mbar_expect_tx(fb, (uint32_t)b_bytes);
-          tma_load_2d(b_ring0 + (uint32_t)(bi * b_bytes), &mapB, fb, kb_glob * TC_BK, tn * p.BN);
+          if (PAIR) {      // this CTA's half of the block; both halves are counted on the leader's barrier
+            if (rank == 0) mbar_expect_tx(fb, 2u * (uint32_t)b_bytes);
+            else mbar_arrive_cluster(fb, 0);
+            tma_load_2d_2sm(b_ring0 + (uint32_t)(bi * b_bytes), &mapB, fb, kb_glob * TC_BK, tn * p.BN + (int)rank * b_rows);
+          } else {
+            mbar_expect_tx(fb, (uint32_t)b_bytes);
+            tma_load_2d(b_ring0 + (uint32_t)(bi * b_bytes), &mapB, fb, kb_glob * TC_BK, tn * p.BN);
+          }
         }
         __syncwarp();
         if (++bi == p.b_slots) { bi = 0; bph ^= 1; }
       }
     }
   } else if (warp <= 2) {
+   if (!PAIR || rank == 0) {
     // ===================== MMA issuers: warp 1 -> output row y0, warp 2 -> output row y0 + 1 =====================
+    // (PAIR: of the leader CTA only, each MMA covering that output row of both CTAs)
     const int sub = warp - 1;
     int ai = 0, bi = 0, as = 0;
     uint32_t aph = 0, bph = 0, aphase = 0;
@@ -205,7 +237,10 @@ gemm_tc2x_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
       uint32_t par;
       const int idx = slot(j, par);
       mbar_wait(a_ready0 + idx * 8, par);
-      if (elect_one()) mbar_arrive(a_empty0 + idx * 8);
+      if (elect_one()) {
+        mbar_arrive(a_empty0 + idx * 8);
+        if (PAIR) mbar_arrive_cluster(a_empty0 + idx * 8, 1);
+      }
       __syncwarp();
     };
     auto mma_block = [&](uint32_t alo, uint32_t accumulate, uint32_t a_release, bool last) {
@@ -213,19 +248,29 @@ gemm_tc2x_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
       tc_fence_after();
       if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < TC_BK / 16; ++k)
-          umma_f16_lohi2(tmem_base + (uint32_t)(as * 256 + sub * 128), alo + 2 * k, desc_hi, b_lo + 2 * k, desc_hi, p.idesc,
-                         k == 0 ? accumulate : 1u);
-        umma_commit(b_eb);
-        if (a_release) umma_commit(a_release);
-        if (last) umma_commit(smem_u32(&tfull_bar[as * 2 + sub]));
+        for (int k = 0; k < TC_BK / 16; ++k) {
+          if (PAIR) umma_f16_2sm(tmem_base + (uint32_t)(as * 256 + sub * 128), alo + 2 * k, b_lo + 2 * k, desc_hi, p.idesc,
+                                 k == 0 ? accumulate : 1u);
+          else umma_f16_lohi2(tmem_base + (uint32_t)(as * 256 + sub * 128), alo + 2 * k, desc_hi, b_lo + 2 * k, desc_hi, p.idesc,
+                              k == 0 ? accumulate : 1u);
+        }
+        if (PAIR) {
+          umma_commit_2sm(b_eb);
+          if (a_release) umma_commit_2sm(a_release);
+          if (last) umma_commit_2sm(smem_u32(&tfull_bar[as * 2 + sub]));
+        } else {
+          umma_commit(b_eb);
+          if (a_release) umma_commit(a_release);
+          if (last) umma_commit(smem_u32(&tfull_bar[as * 2 + sub]));
+        }
       }
       __syncwarp();
       b_lo += b_step; b_fb += 8; b_eb += 8;
       if (++bi == p.b_slots) { bi = 0; bph ^= 1; b_lo = b_lo_base; b_fb = b_full0; b_eb = b_empty0; }
     };
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    for (int tile = item0; tile < p.total_tiles; tile += item_step) {
       mbar_wait_long(smem_u32(&tempty_bar[as * 2 + sub]), aphase ^ 1);
+      tc_fence_after();
       uint32_t accumulate = 0;
       for (int kb = 0; kb < p.nkb_conv; ++kb) {
         if (sub == 1) skip_box(0);
@@ -256,6 +301,7 @@ gemm_tc2x_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
       }
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
+   }
   } else if (warp <= 10) {
     // ===================== epilogue: warps 3..6 drain output row y0, warps 7..10 row y0 + 1 =====================
     const int q = warp & 3;             // TMEM lane quarter this warp may access
@@ -263,9 +309,10 @@ gemm_tc2x_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
     EpiGeom gq{p.tiles_x, p.OH, 128, 1, 1, p.OW, p.OH, p.NB, p.uniform};
     int as = 0;
     uint32_t aphase = 0;
-    for (int tile = blockIdx.x, it = 0; tile < p.total_tiles; tile += gridDim.x, ++it) {
+    const int release_cta = (PAIR && rank != 0) ? 0 : -1;      // the accumulator is handed back on the leader's barrier
+    for (int tile = item0, it = 0; tile < p.total_tiles; tile += item_step, ++it) {
       const int tn = tile % p.n_tiles;
-      const TxPair t = decode_pair(p, tile / p.n_tiles);
+      const TxPair t = decode_pair(p, tile_P(tile));
       const int tm_lin = t.tm0 + grp * p.tiles_x;        // output row y0 + grp
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 256 + grp * 128);
       if (dbg & 2) {
@@ -273,16 +320,19 @@ gemm_tc2x_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
         tc_fence_after();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[as * 2 + grp]));
+        if (lane == 0) {
+          if (release_cta < 0) mbar_arrive(smem_u32(&tempty_bar[as * 2 + grp]));
+          else mbar_arrive_cluster(smem_u32(&tempty_bar[as * 2 + grp]), 0);
+        }
       } else if (p.staged) {
         // each group drains its accumulator through its own HALF-width staging tile (64 columns at a time)
         staged_epilogue_half(gq, e, stg8 + grp * TC_EPI_HALF_BYTES, it & 1, tm_lin, tn, p.BN, taddr,
-                             smem_u32(&tfull_bar[as * 2 + grp]), aphase, smem_u32(&tempty_bar[as * 2 + grp]), 1 + grp);
+                             smem_u32(&tfull_bar[as * 2 + grp]), aphase, smem_u32(&tempty_bar[as * 2 + grp]), 1 + grp, release_cta);
       } else {
         // direct epilogue (same arithmetic and summation order as gemm_tc_kernel's): fused eps-MSE, one partial per row tile
         const int rr = q * 32 + lane;
         const int x = t.x0 + rr, y = t.y0 + grp;
-        const bool row_ok = x < p.OW;
+        const bool row_ok = x < p.OW && t.nb < p.NB;
         const int pix = y * p.OW + x;
         const int m = t.nb * e.rows_per_sample + pix;
         mbar_wait_long(smem_u32(&tfull_bar[as * 2 + grp]), aphase);
@@ -300,13 +350,16 @@ gemm_tc2x_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[as * 2 + grp]));
+        if (lane == 0) {
+          if (release_cta < 0) mbar_arrive(smem_u32(&tempty_bar[as * 2 + grp]));
+          else mbar_arrive_cluster(smem_u32(&tempty_bar[as * 2 + grp]), 0);
+        }
         if (e.mse_part) {
           float* my_mse = mse_smem + grp * 4;
           mse_acc = warp_sum(mse_acc);
           if (lane == 0) my_mse[q] = mse_acc;
           epi_bar(1 + grp);
-          if (q == 0 && lane == 0)
+          if (q == 0 && lane == 0 && t.nb < p.NB)
             e.mse_part[(int64_t)tm_lin * p.n_tiles + tn] = (my_mse[0] + my_mse[1]) + (my_mse[2] + my_mse[3]);
           epi_bar(1 + grp);
         }
@@ -319,15 +372,18 @@ gemm_tc2x_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
     const int l = t & 7, r0 = t >> 3;             // logical 16-byte chunk, first box row
     int ai = 0;
     uint32_t aph = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const TxPair tp = decode_pair(p, tile / p.n_tiles);
+    const bool remote = PAIR && rank != 0;                       // the MMA warps that wait for the boxes live in the leader CTA
+    for (int tile = item0; tile < p.total_tiles; tile += item_step) {
+      const TxPair tp = decode_pair(p, tile_P(tile));
+      const bool tile_ok = tp.nb < p.NB;
       for (int kb = 0; kb < p.nkb_conv; ++kb) {
         // y = a x + b; with SiLU the canonical form is h = (a/2) x + (b/2), out = h tanh(h) + h  (= y sigmoid(y)): see
         // gn_apply_kernel, which computes exactly this
         float ca[8], cb[8];
         {
-          const float4* pa = reinterpret_cast<const float4*>(p.xf_a + (int64_t)tp.nb * p.xf_C + kb * TC_BK + l * 8);
-          const float4* pb = reinterpret_cast<const float4*>(p.xf_b + (int64_t)tp.nb * p.xf_C + kb * TC_BK + l * 8);
+          const int nbc = tile_ok ? tp.nb : 0;
+          const float4* pa = reinterpret_cast<const float4*>(p.xf_a + (int64_t)nbc * p.xf_C + kb * TC_BK + l * 8);
+          const float4* pb = reinterpret_cast<const float4*>(p.xf_b + (int64_t)nbc * p.xf_C + kb * TC_BK + l * 8);
           const float4 a0 = __ldg(pa), a1 = __ldg(pa + 1), b0 = __ldg(pb), b1 = __ldg(pb + 1);
           ca[0] = a0.x; ca[1] = a0.y; ca[2] = a0.z; ca[3] = a0.w; ca[4] = a1.x; ca[5] = a1.y; ca[6] = a1.z; ca[7] = a1.w;
           cb[0] = b0.x; cb[1] = b0.y; cb[2] = b0.z; cb[3] = b0.w; cb[4] = b1.x; cb[5] = b1.y; cb[6] = b1.z; cb[7] = b1.w;
@@ -339,7 +395,7 @@ gemm_tc2x_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
         for (int j = 0; j < 4; ++j) {
           const int y = tp.y0 - 1 + j;
           mbar_wait_long(a_full0 + ai * 8, aph);
-          if (y >= 0 && y < p.OH && !(dbg & 1)) {       // rows outside the image stay zero (TMA fill) = the conv padding
+          if (tile_ok && y >= 0 && y < p.OH && !(dbg & 1)) {       // rows outside the image stay zero (TMA fill) = the conv padding
             const uint32_t base = a_ring0 + (uint32_t)(ai * TX_BOX);
 #pragma unroll
             for (int rr = 0; rr < 5; ++rr) {
@@ -360,24 +416,31 @@ gemm_tc2x_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA's reads
           }
           __syncwarp();
-          if (lane == 0) mbar_arrive(a_ready0 + ai * 8);
+          if (lane == 0) {
+            if (remote) mbar_arrive_cluster(a_ready0 + ai * 8, 0);
+            else mbar_arrive(a_ready0 + ai * 8);
+          }
           if (++ai == p.nbox) { ai = 0; aph ^= 1; }
         }
       }
       for (int k = 0; k < 2 * tap_items; ++k) {    // plain tap tiles (raw tensors): pass through
         mbar_wait_long(a_full0 + ai * 8, aph);
         __syncwarp();
-        if (lane == 0) mbar_arrive(a_ready0 + ai * 8);
+        if (lane == 0) {
+          if (remote) mbar_arrive_cluster(a_ready0 + ai * 8, 0);
+          else mbar_arrive(a_ready0 + ai * 8);
+        }
         if (++ai == p.nbox) { ai = 0; aph ^= 1; }
       }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
 }
 
@@ -416,7 +479,10 @@ int launch_gemm_tc2x(const GemmDev& g, cudaStream_t st, int tiles_x, int BN, int
   p.tiles_x = tiles_x; p.OH = g.OH; p.OW = g.OW; p.NB = g.NB; p.BN = BN;
   p.m_tiles = tiles_x * g.OH * g.NB;
   p.n_tiles = (e.N + BN - 1) / BN;
-  p.total_tiles = (p.m_tiles / 2) * p.n_tiles;
+  p.num_P = p.m_tiles / 2;
+  // CTA pairs (cta_group::2) whenever the tile width allows it: UMMA M = 256 needs N % 16 == 0, each CTA lands N / 2 weight rows
+  const bool pair = BN % 16 == 0 && BN >= 16 && !(knobs() & DCB_KNOB_TC2X_NO_PAIR);
+  p.total_tiles = (pair ? (p.num_P + 1) / 2 : p.num_P) * p.n_tiles;
   p.uniform = uniform; p.staged = staged; p.silu = g.xf_silu;
   p.xf_C = p.nkb_conv * TC_BK;
   p.xf_a = g.xf_a; p.xf_b = g.xf_b;
@@ -456,7 +522,7 @@ int launch_gemm_tc2x(const GemmDev& g, cudaStream_t st, int tiles_x, int BN, int
     auto enc = tc_encode_fn();
     cuuint64_t dims[2] = {(cuuint64_t)g.K, (cuuint64_t)e.N};
     cuuint64_t strides[1] = {(cuuint64_t)g.K * 2};
-    cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)BN};
+    cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)(pair ? BN / 2 : BN)};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(&mapB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(g.W), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -465,14 +531,14 @@ int launch_gemm_tc2x(const GemmDev& g, cudaStream_t st, int tiles_x, int BN, int
   }
 
   // rings: two half-width staging tiles (staged epilogue) or none; 6 row boxes (1.5 channel blocks in flight), the rest weights
-  const int b_bytes = BN * TC_BK * 2;
+  const int b_bytes = (pair ? BN / 2 : BN) * TC_BK * 2;      // per CTA
 #ifdef DCB_PROBES
   p.dbg = getenv("DCB_TX_DBG") ? atoi(getenv("DCB_TX_DBG")) : 0;
 #endif
   const int fixed = 1024 + 512 + (staged ? 2 * TC_EPI_HALF_BYTES : 0);
   // (measured, tools/xf_micro.py: 7 boxes + 4 weight slots beat 6 + 5 on the residual / shortcut convs by 10 % and 8 + 8 on
   //  conv_out by 25 %; a ring that is a multiple of the 4 boxes per channel block does worst)
-  int nbox = 7;
+  int nbox = pair ? 8 : 7;        // PAIR: the halved weight ring pays for another row box
 #ifdef DCB_PROBES
   if (getenv("DCB_TX_NBOX")) nbox = atoi(getenv("DCB_TX_NBOX"));
 #endif
@@ -480,16 +546,37 @@ int launch_gemm_tc2x(const GemmDev& g, cudaStream_t st, int tiles_x, int BN, int
   if (b_slots > TX_MAX_SLOTS) b_slots = TX_MAX_SLOTS;
   if (b_slots < 4) return DCB_EUNSUPPORTED;
   p.nbox = nbox; p.b_slots = b_slots;
-  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((pair ? 256 : TC_BM) >> 4) << 24);
   if (dry_run) return DCB_OK;
 
   const size_t smem = (size_t)fixed + (size_t)nbox * TX_BOX + (size_t)b_slots * b_bytes;
   static std::once_flag attr_once;
   std::call_once(attr_once, [] {
-    cudaFuncSetAttribute(gemm_tc2x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT);
+    cudaFuncSetAttribute(gemm_tc2x_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT);
+    cudaFuncSetAttribute(gemm_tc2x_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT);
   });
-  const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-  gemm_tc2x_kernel<<<grid, TX_THREADS, smem, st>>>(maps[0], maps[1], maps[2], mapB, p, e);
+  if (pair) {
+    const int pairs = num_sms() / 2;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * (p.total_tiles < pairs ? p.total_tiles : pairs));
+    cfg.blockDim = dim3(TX_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tc2x_kernel<true>, maps[0], maps[1], maps[2], mapB, p, e);
+    if (le != cudaSuccess) {
+      set_error("gemm_tc2x<pair> launch failed: %s", cudaGetErrorString(le));
+      return (int)le;
+    }
+  } else {
+    const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+    gemm_tc2x_kernel<false><<<grid, TX_THREADS, smem, st>>>(maps[0], maps[1], maps[2], mapB, p, e);
+  }
   DCB_CHECK_LAUNCH("gemm_tc2x");
   return DCB_OK;
 }

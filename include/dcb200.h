@@ -47,7 +47,8 @@ enum {
   DCB_KNOB_TC_DIRECT_EPILOGUE = 32, /* thread-per-row epilogue instead of the staged (coalesced) one */
   DCB_KNOB_ATTN_NO_TC = 64,         /* head-dim-64 attention on the mma.sync kernel */
   DCB_KNOB_ATTN_NO_FAST = 128,      /* tcgen05 attention always with the running maximum (no single-pass kernel) */
-  DCB_KNOB_NO_TC3 = 256             /* no CTA-pair (cta_group::2) GEMM for the N % 256 == 0 linear layers */
+  DCB_KNOB_NO_TC3 = 256,            /* no CTA-pair (cta_group::2) GEMM for the N % 256 == 0 linear layers */
+  DCB_KNOB_TC2X_NO_PAIR = 512       /* fused-GroupNorm conv on single CTAs (no cta_group::2 weight sharing) */
 };
 void dcb_set_knobs(uint32_t mask);
 uint32_t dcb_get_knobs(void);
