@@ -30,7 +30,8 @@
 namespace dcb {
 
 constexpr int TX_THREADS = 640;
-constexpr int TX_MAX_SLOTS = 8;
+constexpr int TX_MAX_SLOTS = 12;
+constexpr int TX_BAR_BYTES = 1024;
 constexpr int TX_BOX = 17 * 1024;      // 130 rows x 128 B = 16640 B, padded to the 1024-B swizzle repeat
 constexpr int TX_XF_WARPS = 8;
 
@@ -94,8 +95,8 @@ gemm_tc2x_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
   uint64_t* tfull_bar = bars + 5 * TX_MAX_SLOTS;    // [2 TMEM stages][2 output rows]
   uint64_t* tempty_bar = tfull_bar + 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 4);
-  float* mse_smem = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 400);  // [2 groups][4 warps]
-  uint8_t* stg8 = reinterpret_cast<uint8_t*>(bars) + 512;
+  float* mse_smem = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 640);  // [2 groups][4 warps]
+  uint8_t* stg8 = reinterpret_cast<uint8_t*>(bars) + TX_BAR_BYTES;
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const uint32_t rank = PAIR ? cluster_cta_rank() : 0u;
@@ -405,8 +406,14 @@ gemm_tc2x_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
                 const uint32_t addr = base + (uint32_t)(r * 128) + (uint32_t)((l ^ (r & 7)) << 4);
                 uint4 v;
                 asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+                // bf16 -> fp32 is a shift (low half) or a mask (high half): one ALU op per element
+                const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
                 float f[8];
-                unpack_bf16x8(v, f);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  f[2 * i] = __uint_as_float(wv[i] << 16);
+                  f[2 * i + 1] = __uint_as_float(wv[i] & 0xffff0000u);
+                }
 #pragma unroll
                 for (int i = 0; i < 8; ++i) f[i] = gn_act_bf16(fmaf(f[i], ca[i], cb[i]), p.silu);
                 v = pack_bf16x8(f);
@@ -535,10 +542,10 @@ int launch_gemm_tc2x(const GemmDev& g, cudaStream_t st, int tiles_x, int BN, int
 #ifdef DCB_PROBES
   p.dbg = getenv("DCB_TX_DBG") ? atoi(getenv("DCB_TX_DBG")) : 0;
 #endif
-  const int fixed = 1024 + 512 + (staged ? 2 * TC_EPI_HALF_BYTES : 0);
+  const int fixed = 1024 + TX_BAR_BYTES + (staged ? 2 * TC_EPI_HALF_BYTES : 0);
   // (measured, tools/xf_micro.py: 7 boxes + 4 weight slots beat 6 + 5 on the residual / shortcut convs by 10 % and 8 + 8 on
   //  conv_out by 25 %; a ring that is a multiple of the 4 boxes per channel block does worst)
-  int nbox = pair ? 8 : 7;        // PAIR: the halved weight ring pays for another row box
+  int nbox = 7;                   // (PAIR: the halved weight blocks double the weight ring to 8 slots; 9 boxes + 4 slots measured equal)
 #ifdef DCB_PROBES
   if (getenv("DCB_TX_NBOX")) nbox = atoi(getenv("DCB_TX_NBOX"));
 #endif

@@ -70,6 +70,9 @@ FUSE_GN = __import__("os").environ.get("DCB_FUSE_GN", "1") != "0"   # A/B switch
 # ... only for convs over at least this many input channels (A/B knob; 0 = every eligible conv, the measured best:
 # profiles/r02_gn_fusion.md)
 FUSE_GN_MIN_C = int(__import__("os").environ.get("DCB_FUSE_GN_MIN_C", "0"))
+# conv_out (N = out_channels, fused eps-MSE epilogue) has almost no tensor work to hide the transform behind: the fused launch
+# is MUFU bound and measured 0.93-1.0 ms against 0.73-0.83 ms for gn_apply + conv (200 samples of 128^2): not fused
+FUSE_GN_MSE = __import__("os").environ.get("DCB_FUSE_GN_MSE", "0") != "0"
 XF_UNSUPPORTED = object()     # gemm(xf=...) sentinel: this launch cannot apply the fused transform; nothing was launched
 
 
@@ -281,7 +284,7 @@ def gn_conv3x3(ctx, x0, C0, x1, C1, NB, H, W, gamma, beta, eps, silu, Wt, N, *, 
     HW = H * W
     if FUSE_GN and ctx.code == L.BF16 and ctx.engine != L.ENGINE_SIMT and st0 is not None and (x1 is None or st1 is not None) \
             and USE_TILE_STATS and HW % 128 == 0 and W % 128 == 0 and C0 % 64 == 0 and C1 % 64 == 0 \
-            and C0 + C1 >= FUSE_GN_MIN_C:
+            and C0 + C1 >= FUSE_GN_MIN_C and (FUSE_GN_MSE or kw.get("mse") is None):
         ca = torch.empty(NB, C0 + C1, device=ctx.device, dtype=torch.float32)
         cb = torch.empty(NB, C0 + C1, device=ctx.device, dtype=torch.float32)
 

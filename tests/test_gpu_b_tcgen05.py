@@ -528,13 +528,13 @@ def test_gn_fused_into_conv_operand_is_bit_identical(dev, NB, H, W, C0, C1, div1
                          extra_segs=extra_segs, **kw)
         return (err,) if extra == "mse" else r, L.launch_count() - n0
 
-    min_c = E.FUSE_GN_MIN_C
-    E.FUSE_GN_MIN_C = 0           # whatever the product's policy knob says, the kernel is tested on every layer shape
+    min_c, E.FUSE_GN_MSE = E.FUSE_GN_MIN_C, True
+    E.FUSE_GN_MIN_C = 0           # whatever the product's policy knobs say, the kernel is tested on every layer shape
     try:
         fused, n_f = run(True)
         plain, n_p = run(False)
     finally:
-        E.FUSE_GN, E.FUSE_GN_MIN_C = True, min_c
+        E.FUSE_GN, E.FUSE_GN_MIN_C, E.FUSE_GN_MSE = True, min_c, False
     # fused: coefficient kernel + conv (+ mse finalize); plain: statistics finalize + gn_apply + conv (+ mse finalize)
     assert n_f == n_p - 1, (n_f, n_p)
     for a, c in zip(fused, plain):

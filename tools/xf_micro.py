@@ -8,7 +8,7 @@ import torch
 from dcb200 import engine as E
 dev = torch.device("cuda:0")
 ctx = E.Ctx(device=dev, precision="bf16")
-E.FUSE_GN_MIN_C = 0     # time the fused kernel on every layer shape, whatever the product policy
+E.FUSE_GN_MIN_C, E.FUSE_GN_MSE = 0, True     # time the fused kernel on every layer shape, whatever the product policy
 
 
 def bench(fn, n=int(os.environ.get("MICRO_ITERS", "100"))):
