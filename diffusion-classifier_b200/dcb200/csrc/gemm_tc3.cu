@@ -22,16 +22,19 @@
 
 namespace dcb {
 
-constexpr int T3_THREADS = 320;
+constexpr int T3_THREADS = 64 + 512;    // TMA warp, MMA warp, up to four epilogue groups of four warps
 constexpr int T3_MAX_STAGES = 8;
 constexpr int T3_STAGE_BYTES = 2 * TC_A_BYTES;     // A [128 x 64] + W half [128 x 64]
 
 struct T3Params {
   int M, nkb, m_pairs, n_tiles, total_tiles, stages, uniform, c_off;
+  int ngroups;      // epilogue groups per CTA: 2 (128 columns each) or 4 (64 columns each: layers whose epilogue -- an
+                    // activation over 128 x 256 outputs per CTA -- is longer than a K <= 1024 main loop)
   uint32_t idesc;
 };
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T3_THREADS, 1)
+template <int NGROUPS>     // 2: 320 threads (the epilogue keeps its registers); 4: 576 threads
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 128 * NGROUPS, 1)
 gemm_tc3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                 const __grid_constant__ T3Params p, const __grid_constant__ EpiDev e) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -54,7 +57,7 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     prefetch_tmap(&mapA);
     prefetch_tmap(&mapB);
     for (int i = 0; i < p.stages; ++i) { mbar_init(smem_u32(&full_bar[i]), 2); mbar_init(smem_u32(&empty_bar[i]), 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&tfull_bar[i]), 1); mbar_init(smem_u32(&tempty_bar[i]), 16); }
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&tfull_bar[i]), 1); mbar_init(smem_u32(&tempty_bar[i]), 8 * p.ngroups); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {   // one warp of EACH CTA, same shared-memory slot: allocates the same columns in both tensor memories
@@ -120,18 +123,19 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
     }
-  } else {
-    // ===================== epilogue (both CTAs): group g drains columns [128 g, +128) of this CTA's 128 rows =====================
+  } else if (((warp - 2) >> 2) < p.ngroups) {
+    // ===================== epilogue (both CTAs): group g drains columns [w g, + w) of this CTA's 128 rows, w = 256 / ngroups ==========
     const int q = warp & 3;
     const int grp = (warp - 2) >> 2;
+    const int gw = 256 / p.ngroups;
     const int tiles_x = (p.M + 127) / 128;
     EpiGeom gq{tiles_x, 1, 128, 1, 1, p.M, 1, 1, p.uniform};
     int as = 0;
     uint32_t aphase = 0;
     for (int tile = pair, it = 0; tile < p.total_tiles; tile += n_pairs, ++it) {
       const int tn = tile % p.n_tiles, tm = tile / p.n_tiles;
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 256 + grp * 128);
-      staged_epilogue_half(gq, e, stg8 + grp * TC_EPI_HALF_BYTES, it & 1, tm * 2 + (int)rank, tn * 2 + grp, 128, taddr,
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 256 + grp * gw);
+      staged_epilogue_half(gq, e, stg8 + grp * TC_EPI_HALF_BYTES, it & 1, tm * 2 + (int)rank, tn * p.ngroups + grp, gw, taddr,
                            smem_u32(&tfull_bar[as]), aphase, smem_u32(&tempty_bar[as]), 1 + grp, rank == 0 ? -1 : 0);
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
@@ -186,19 +190,22 @@ int launch_gemm_tc3(const GemmDev& g, cudaStream_t st, int uniform) {
   int rc;
   if ((rc = encode_2d(&mapA, s.src, M, s.C, s.C, 128))) return rc;
   if ((rc = encode_2d(&mapB, g.W, e.N, g.K, g.K, 128))) return rc;
-  int stages = (TC_SMEM_LIMIT - 1024 - 512 - 2 * TC_EPI_HALF_BYTES) / T3_STAGE_BYTES;
+  p.ngroups = (e.act != DCB_ACT_NONE && g.K <= 1024) ? 4 : 2;
+  int stages = (TC_SMEM_LIMIT - 1024 - 512 - p.ngroups * TC_EPI_HALF_BYTES) / T3_STAGE_BYTES;
   if (stages > T3_MAX_STAGES) stages = T3_MAX_STAGES;
   if (stages > p.nkb) stages = p.nkb < 2 ? 2 : p.nkb;
   p.stages = stages;
   // instruction descriptor: D = f32, A = B = bf16, both K-major, N = 256, M = 256 (the pair)
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | ((256u >> 4) << 24);
-  const size_t smem = (size_t)stages * T3_STAGE_BYTES + 1024 + 512 + 2 * TC_EPI_HALF_BYTES;
+  const size_t smem = (size_t)stages * T3_STAGE_BYTES + 1024 + 512 + p.ngroups * TC_EPI_HALF_BYTES;
   static std::once_flag attr_once;
   std::call_once(attr_once, [] {
-    cudaFuncSetAttribute(gemm_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT);
+    cudaFuncSetAttribute(gemm_tc3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT);
+    cudaFuncSetAttribute(gemm_tc3_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT);
   });
   const int grid = 2 * (p.total_tiles < pairs ? p.total_tiles : pairs);
-  gemm_tc3_kernel<<<grid, T3_THREADS, smem, st>>>(mapA, mapB, p, e);
+  if (p.ngroups == 4) gemm_tc3_kernel<4><<<grid, 64 + 128 * 4, smem, st>>>(mapA, mapB, p, e);
+  else gemm_tc3_kernel<2><<<grid, 64 + 128 * 2, smem, st>>>(mapA, mapB, p, e);
   DCB_CHECK_LAUNCH("gemm_tc3");
   return DCB_OK;
 }
