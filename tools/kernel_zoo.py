@@ -87,7 +87,7 @@ xsk = bf((NB // 2) * 128 * 128, 128)
 g5, b5 = torch.randn(256, device=dev), torch.randn(256, device=dev)
 w256 = bf(128, 9 * 256) * 0.05
 st_sk = stats(xsk)
-case("gemm_tc2x: GroupNorm+SiLU fused into conv3x3 cat(128,128)->128 @128^2 x200 (dominant conv) + coefficient kernel", "flops",
+case("gemm_tc2x (CTA pairs): GroupNorm+SiLU fused into conv3x3 cat(128,128)->128 @128^2 x200 (dominant conv) + coefficient kernel", "flops",
      2.0 * NB * 16384 * 128 * 2304,
      lambda: E.gn_conv3x3(ctx, xg, 128, xsk, 128, NB, 128, 128, g5, b5, 1e-5, True, w256, 128, div1=2, st0=st, st1=st_sk,
                           gn_stats=True))
@@ -102,8 +102,12 @@ case("gemm_tc GEGLU: [51200 x 512] -> 4096 (2048 outputs)", "flops", 2.0 * NB * 
      lambda: E.linear(ctx, xt, wg, 4096, bias=bg, act=L.ACT_GEGLU))
 xd = bf(32 * 4096, 768)
 wq = bf(2304, 768) * 0.03
-case("gemm_tc2 tap mode: DiT QKV [131072 x 768] -> 2304", "flops", 2.0 * 32 * 4096 * 2304 * 768,
+case("gemm_tc3 (CTA pairs, cta_group::2): DiT QKV [131072 x 768] -> 2304", "flops", 2.0 * 32 * 4096 * 2304 * 768,
      lambda: E.linear(ctx, xd, wq, 2304))
+wf1 = bf(3072, 768) * 0.03
+bf1 = torch.randn(3072, device=dev)
+case("gemm_tc3 (CTA pairs, four epilogue groups): DiT FF1 + GELU [131072 x 768] -> 3072", "flops", 2.0 * 32 * 4096 * 3072 * 768,
+     lambda: E.linear(ctx, xd, wf1, 3072, bias=bf1, act=L.ACT_GELU_TANH))
 xo = bf(NB * 128 * 128, 128)
 w3 = bf(3, 9 * 128) * 0.05
 tgt = torch.randn((NB // 2) * 128 * 128, 3, device=dev)
