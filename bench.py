@@ -332,7 +332,9 @@ def run_ours(args):
         "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
         "peak_source": f"{peak_src} bf16_tflops_sustained",
         "achieved_basis": "executed FLOPs (2 M N K of every tcgen05 GEMM launch) / summed CUDA-event durations of those "
-                          "launches, eager launches on the bench workload",
+                          "launches, eager launches on the bench workload; since round 2 the full-resolution conv launches also "
+                          "apply the GroupNorm + SiLU of their operand (gemm_tc2x), so their time contains what used to be the "
+                          "separate gn_apply pass",
         "effective_tflops_on_reference_graph": algorithmic,
         "effective_speedup_vs_reference_flops": (ref_flops * passes) / gemm_flops if gemm_flops else None,
         "launches_per_step": n_gemm // passes, "avg_launch_ms": gemm_ms / max(n_gemm, 1),

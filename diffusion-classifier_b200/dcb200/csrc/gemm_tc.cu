@@ -345,13 +345,17 @@ static int choose_geometry(const GemmDev& g, TcGeom* t) {
   return DCB_OK;
 }
 
-// bf16 outputs with <= 128 output columns per tile (BN <= 128, or GEGLU's 256 -> 128); 16-byte aligned rows
-static bool staged_for(const GemmDev& g, const TcGeom& t) {
+// what any staged (coalesced, bf16) epilogue needs of the output / residual, whatever the tile width
+static bool staged_layout_ok(const GemmDev& g) {
   const EpiDev& e = g.epi;
   if (knobs() & DCB_KNOB_TC_DIRECT_EPILOGUE) return false;
   return e.out != nullptr && e.out_dtype == DCB_BF16 && e.mse_part == nullptr && e.n_out % 8 == 0 && e.out_ld % 8 == 0 &&
-         ((uintptr_t)e.out % 16) == 0 && (t.BN <= 128 || e.act == DCB_ACT_GEGLU) &&
+         ((uintptr_t)e.out % 16) == 0 &&
          (e.residual == nullptr || (e.res_dtype == DCB_BF16 && e.res_ld % 8 == 0 && ((uintptr_t)e.residual % 16) == 0));
+}
+// bf16 outputs with <= 128 output columns per tile (BN <= 128, or GEGLU's 256 -> 128); 16-byte aligned rows
+static bool staged_for(const GemmDev& g, const TcGeom& t) {
+  return staged_layout_ok(g) && (t.BN <= 128 || g.epi.act == DCB_ACT_GEGLU);
 }
 
 bool tc_staged(const GemmDev& g) {
@@ -504,7 +508,7 @@ int launch_gemm_tc(const GemmDev& g, cudaStream_t st, bool dry_run) {
     }
   }
   // plain linear layers with N a multiple of 256 and enough rows: CTA pairs, 256 x 256 tiles (gemm_tc3.cu)
-  if (p.staged && g.xf_a == nullptr && !dry_run && !(knobs() & DCB_KNOB_NO_TC3)) {
+  if (staged_layout_ok(g) && g.xf_a == nullptr && !dry_run && !(knobs() & DCB_KNOB_NO_TC3)) {
     rc = launch_gemm_tc3(g, st, p.uniform);
     if (rc != DCB_EUNSUPPORTED) return rc;
   }
