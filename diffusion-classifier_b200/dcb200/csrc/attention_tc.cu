@@ -26,6 +26,7 @@
 #include <cudaTypedefs.h>
 
 #include <mutex>
+#include <type_traits>
 
 #include "tc_common.cuh"
 
@@ -79,7 +80,7 @@ __device__ __forceinline__ float ex2f(float x) {
   return y;
 }
 
-// 2^x for x in [-126, 0] on the FMA / ALU pipes (no MUFU op): round-to-nearest split x = n + f through the 1.5 * 2^23 magic
+// 2^x for |x| <= 126 on the FMA / ALU pipes (no MUFU op): round-to-nearest split x = n + f through the 1.5 * 2^23 magic
 // constant (n sits in the low mantissa bits of t), cubic minimax 2^f on [-0.5, 0.5] (max relative error 7.5e-5, far below
 // the bf16 rounding of P), exponent add: 7 more instructions than the MUFU form.  The single-pass kernel is bound by the MUFU
 // pipe on paper (16 ex2 / clk / SM: ncu XU pipe 65 %, issue slots 55 %), so moving a share of the exponentials here looked
@@ -538,64 +539,60 @@ flash_attn_tc_fast_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid
     const uint32_t s_addr = lane_addr + (uint32_t)(t * 128 + hf * 64);
     const uint32_t p_addr = lane_addr + (uint32_t)(256 + t * 64 + hf * 32);
     const uint32_t o_addr = lane_addr + (uint32_t)(384 + t * 64 + hf * 32);
-    // |q_r|^2 from the swizzled Q tile (16-byte chunk c of row r sits at chunk c ^ (r & 7))
-    mbar_wait(smem_u32(q_full), 0);
-    float qn2 = 0.f;
-    {
-      const uint8_t* qrow = q_s + t * AT_TILE_BYTES + r * 128;
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        float f[8];
-        unpack_bf16x8(*reinterpret_cast<const uint4*>(qrow + ((c ^ (r & 7)) << 4)), f);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) qn2 = fmaf(f[i], f[i], qn2);
-      }
-    }
-    const float kn2 = p.norms[2 + (b * gridDim.y + h) * 2 + 1];
+    // No shift at all: at_fast_ok bounds every |s_ij| c by 50 (Cauchy-Schwarz on this head's max |q|, max |k|), so
+    // P' = 2^(s c) lies in [2^-50, 2^50] -- inside the range of bf16 / fp32 with room for the 4096-term sums -- and
+    // softmax = P' / sum P' needs no reference value: one instruction less per score than exp2(s c - M_i c).  When the
+    // caller has folded c into the query projection (sc == 1: dcb200's DiT does, at pack time) the score IS the exponent.
     const float sc = p.sc;
-    const float msc = sqrtf(qn2 * kn2) * 1.002f * sc;   // M_i c (log2 units), a hair above the Cauchy-Schwarz bound
+    const bool prescaled = fabsf(sc - 1.0f) < 1e-6f;
     float l = 0.f;
-    for (int j = 0; j < p.nblk; ++j) {
-      mbar_wait(s_full0 + t * 8, (uint32_t)(j & 1));
-      tc_fence_after();
-      const int valid = p.N - j * 128 - hf * 64;   // keys of this half block that exist (>= 64: all)
-      uint32_t pk[32];
-      float rs = 0.f;
-#pragma unroll
-      for (int c = 0; c < 64; c += 32) {
-        uint32_t sv[32];
-        tmem_ld32_nowait(s_addr + (uint32_t)c, sv);
-        tmem_ld_wait();
-        if (c == 32) {   // this thread's half row of S is in registers
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(s_free0 + t * 8);
-        }
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float p0 = ex2f(fmaf(__uint_as_float(sv[i]), sc, -msc));
-          const float x1 = fmaf(__uint_as_float(sv[i + 1]), sc, -msc);       // in [-100.2, 0] (at_fast_ok)
-          float p1 = (DCB_ATTN_POLY_MASK >= 0 && (i & DCB_ATTN_POLY_MASK) == 0) ? ex2_poly(x1) : ex2f(x1);
-          if (valid < 64) {
-            if (c + i >= valid) p0 = 0.f;
-            if (c + i + 1 >= valid) p1 = 0.f;
-          }
-          rs += p0 + p1;
-          pk[(c + i) >> 1] = pack_bf16x2(p0, p1);
-        }
-      }
-      l += rs;
-      if (j > 0) {   // P_t is free once the previous block's P V has been consumed
-        mbar_wait(o_full0 + t * 8, (uint32_t)((j - 1) & 1));
+    auto key_blocks = [&](auto pre_tag) {      // two instantiations: the multiply is gone from the loop, not selected in it
+      constexpr bool PRE = decltype(pre_tag)::value;
+      for (int j = 0; j < p.nblk; ++j) {
+        mbar_wait(s_full0 + t * 8, (uint32_t)(j & 1));
         tc_fence_after();
+        const int valid = p.N - j * 128 - hf * 64;   // keys of this half block that exist (>= 64: all)
+        uint32_t pk[32];
+        float rs = 0.f;
+#pragma unroll
+        for (int c = 0; c < 64; c += 32) {
+          uint32_t sv[32];
+          tmem_ld32_nowait(s_addr + (uint32_t)c, sv);
+          tmem_ld_wait();
+          if (c == 32) {   // this thread's half row of S is in registers
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(s_free0 + t * 8);
+          }
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float x0 = PRE ? __uint_as_float(sv[i]) : __uint_as_float(sv[i]) * sc;
+            const float x1 = PRE ? __uint_as_float(sv[i + 1]) : __uint_as_float(sv[i + 1]) * sc;    // |x| <= 50 (at_fast_ok)
+            float p0 = ex2f(x0);
+            float p1 = (DCB_ATTN_POLY_MASK >= 0 && (i & DCB_ATTN_POLY_MASK) == 0) ? ex2_poly(x1) : ex2f(x1);
+            if (valid < 64) {
+              if (c + i >= valid) p0 = 0.f;
+              if (c + i + 1 >= valid) p1 = 0.f;
+            }
+            rs += p0 + p1;
+            pk[(c + i) >> 1] = pack_bf16x2(p0, p1);
+          }
+        }
+        l += rs;
+        if (j > 0) {   // P_t is free once the previous block's P V has been consumed
+          mbar_wait(o_full0 + t * 8, (uint32_t)((j - 1) & 1));
+          tc_fence_after();
+        }
+        tmem_st16(p_addr, pk);
+        tmem_st16(p_addr + 16u, pk + 16);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full0 + t * 8);
       }
-      tmem_st16(p_addr, pk);
-      tmem_st16(p_addr + 16u, pk + 16);
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(p_full0 + t * 8);
-    }
+    };
+    if (prescaled) key_blocks(std::true_type{});
+    else key_blocks(std::false_type{});
     // the other half's share of the row sum, then O / l
     lsum[(t * 2 + hf) * 128 + r] = l;
     asm volatile("bar.sync %0, 256;" ::"r"(1 + t) : "memory");

@@ -17,6 +17,9 @@ from . import engine as E
 from .unet import _P, _Attn, _TimeEmb
 
 
+LOG2E = 1.4426950408889634
+
+
 def _sincos_1d(dim, pos):
     omega = np.arange(dim // 2, dtype=np.float64) / (dim / 2.0)
     omega = 1.0 / 10000 ** omega
@@ -124,6 +127,11 @@ class DiT(nn.Module):
     def _version(self):
         return tuple(p._version for p in self.parameters()) + tuple(p.data_ptr() for p in self.parameters())
 
+    @staticmethod
+    def _fold_qscale(ctx):
+        # bf16 product path only: the fp32-verify engine keeps the reference's order of operations (1e-4 mode)
+        return ctx.precision == "bf16"
+
     def packed(self, ctx):
         key = (ctx.precision, str(ctx.device))
         ver = self._version()
@@ -162,8 +170,12 @@ class DiT(nn.Module):
             q.table = w(b.norm1.emb.class_embedder.embedding_table.weight)
             q.mod_w, q.mod_b = w(b.norm1.linear.weight), f32(b.norm1.linear.bias)
             a = b.attn1
-            q.qkv_w = E.pack_rows(ctx, [a.to_q.weight, a.to_k.weight, a.to_v.weight], 0)
-            q.qkv_b = f32(torch.cat([a.to_q.bias.detach(), a.to_k.bias.detach(), a.to_v.bias.detach()], 0))
+            # the softmax exponent scale c = d^-0.5 log2(e) is folded into the query projection (weights and bias, in fp32,
+            # before the one rounding to the engine dtype): QK^T then IS the base-2 exponent and the single-pass attention
+            # kernel spends one instruction less per score (attention_tc.cu); attention() is told scale = 1 / log2(e)
+            cq = (cfg.attention_head_dim ** -0.5) * LOG2E if self._fold_qscale(ctx) else 1.0
+            q.qkv_w = E.pack_rows(ctx, [a.to_q.weight.detach() * cq, a.to_k.weight, a.to_v.weight], 0)
+            q.qkv_b = f32(torch.cat([a.to_q.bias.detach() * cq, a.to_k.bias.detach(), a.to_v.bias.detach()], 0))
             q.o_w, q.o_b = w(a.to_out[0].weight), f32(a.to_out[0].bias)
             q.f1_w, q.f1_b = w(b.ff.net[0].proj.weight), f32(b.ff.net[0].proj.bias)
             q.f2_w, q.f2_b = w(b.ff.net[2].weight), f32(b.ff.net[2].bias)
@@ -192,7 +204,7 @@ class DiT(nn.Module):
             mod = E.linear(ctx, sc, q.mod_w, 6 * D, bias=q.mod_b, out_dtype=torch.float32)
             n = E.layernorm(ctx, h, None, None, 1e-6, scale=mod[:, D:], shift=mod, mod_ld=6 * D, rows_per_group=N)
             qkv = E.linear(ctx, n, q.qkv_w, 3 * D, bias=q.qkv_b)
-            att = E.attention(ctx, qkv, S, N, heads, hd)
+            att = E.attention(ctx, qkv, S, N, heads, hd, scale=(1.0 / LOG2E) if self._fold_qscale(ctx) else None)
             h = E.linear(ctx, att, q.o_w, D, bias=q.o_b, gate=mod[:, 2 * D:], gate_ld=6 * D, rows_per_group=N,
                          residual=h, res_ld=D)
             n = E.layernorm(ctx, h, None, None, cfg.norm_eps, scale=mod[:, 4 * D:], shift=mod[:, 3 * D:], mod_ld=6 * D,

@@ -318,8 +318,9 @@ def layernorm(ctx, x, gamma=None, beta=None, eps=1e-5, scale=None, shift=None, m
     return out
 
 
-def attention(ctx, qkv, B, Ntok, heads, d, q_off=0, k_off=None, v_off=None, simt=False):
-    """qkv: [B*Ntok, ld] with q/k/v column blocks of width heads*d starting at q_off/k_off/v_off."""
+def attention(ctx, qkv, B, Ntok, heads, d, q_off=0, k_off=None, v_off=None, simt=False, scale=None):
+    """qkv: [B*Ntok, ld] with q/k/v column blocks of width heads*d starting at q_off/k_off/v_off.
+    scale: softmax scale (default d^-0.5); a caller that folded d^-0.5 log2(e) into its query projection passes 1 / log2(e)."""
     Cw = heads * d
     ld = qkv.shape[1]
     k_off = Cw if k_off is None else k_off
@@ -330,7 +331,8 @@ def attention(ctx, qkv, B, Ntok, heads, d, q_off=0, k_off=None, v_off=None, simt
     code = ctx.code | (0x100 if (simt and ctx.code == L.BF16) else 0)
     ws = torch.empty(2 + B * heads * 2, device=ctx.device, dtype=torch.float32) if code == L.BF16 and d == 64 else None
     L.check(L.lib().dcb_attention_ws(code, base + q_off * es, base + k_off * es, base + v_off * es, ld, B, Ntok, heads, d,
-                                     float(d) ** -0.5, out.data_ptr(), Cw, _p(ws), ctx.stream()), "attention")
+                                     float(d) ** -0.5 if scale is None else float(scale), out.data_ptr(), Cw, _p(ws),
+                                     ctx.stream()), "attention")
     return out
 
 
