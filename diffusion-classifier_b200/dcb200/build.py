@@ -19,7 +19,7 @@ SOURCES = ["api.cu", "gemm_tc.cu", "gemm_tc2.cu", "gemm_tc2x.cu", "gemm_tc3.cu",
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr", "-Xptxas", "-v"]
-FLAGS += os.environ.get("DCB_EXTRA_NVCC_FLAGS", "").split()       # experiments only (e.g. -DDCB_ATTN_POLY_MASK=6)
+FLAGS += os.environ.get("DCB_EXTRA_NVCC_FLAGS", "").split()       # experiments only (e.g. -DDCB_ATTN_POLY=4)
 if os.environ.get("DCB_BUILD_SUFFIX"):                               # ... built next to the product library, never replacing it
     OBJ = os.path.join(HERE, "build" + os.environ["DCB_BUILD_SUFFIX"])
     LIB = os.path.join(HERE, "build", "libdcb200" + os.environ["DCB_BUILD_SUFFIX"] + ".so")

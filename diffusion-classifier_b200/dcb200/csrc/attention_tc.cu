@@ -80,25 +80,63 @@ __device__ __forceinline__ float ex2f(float x) {
   return y;
 }
 
-// 2^x for |x| <= 126 on the FMA / ALU pipes (no MUFU op): round-to-nearest split x = n + f through the 1.5 * 2^23 magic
-// constant (n sits in the low mantissa bits of t), cubic minimax 2^f on [-0.5, 0.5] (max relative error 7.5e-5, far below
-// the bf16 rounding of P), exponent add: 7 more instructions than the MUFU form.  The single-pass kernel is bound by the MUFU
-// pipe on paper (16 ex2 / clk / SM: ncu XU pipe 65 %, issue slots 55 %), so moving a share of the exponentials here looked
-// like free throughput.  MEASURED (tools/attn_micro.py, same box, B = 16, incl. the norm pre-pass): never 652 TF/s, one in
-// eight 656, one in four 580, one in two 559 -- the softmax warps are as much issue / dependency bound as MUFU bound, and
-// every 7 extra instructions cost more than the MUFU slot they free.  Kept as a compile-time experiment
-// (-DDCB_ATTN_POLY_MASK=6), off in the product.
-#ifndef DCB_ATTN_POLY_MASK
-#define DCB_ATTN_POLY_MASK (-1)   // pairs (i, i + 1) with (i & MASK) == 0 evaluate element i + 1 on the FMA pipe; -1 = never (product)
+// packed fp32 pairs (sm_100 add / fma .f32x2: two lanes of arithmetic per issue slot)
+__device__ __forceinline__ uint64_t f2_pack(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ void add_f32x2(float& a0, float& a1, float b0, float b1) {   // {a0, a1} += {b0, b1}
+  f2_unpack(f2_add(f2_pack(a0, a1), f2_pack(b0, b1)), a0, a1);
+}
+
+// 2^x for |x| <= 126 on the FMA / ALU pipes (no MUFU op), two scores at a time: round-to-nearest split x = n + f through
+// the 1.5 * 2^23 magic constant (n sits in the low mantissa bits of t), cubic minimax 2^f on [-0.5, 0.5] (max relative
+// error 7.5e-5, far below the bf16 rounding of P), exponent add.  Packed: 6 f32x2 slots + 2 integer ops per PAIR of scores
+// (4 per score), against 1 MUFU slot that occupies the 4-lane XU pipe for 8 clocks.
+// History: the scalar form (8 slots per score) was a loss when the loop still carried a subtract, a multiply and the
+// ragged-N compare + select on every score (issue slots 55 %: never 652 TF/s, one in eight 656, one in four 580).  With
+// the loop down to ex2 + 1/2 add.f32x2 + 1/2 cvt per score the XU pipe is the only thing left to relieve.
+// DCB_ATTN_POLY: 0 = never; 8 / 4 / 2 = one score in eight / four / two goes to the FMA pipe.
+// MEASURED (tools/attn_micro.py, one box, B = 16 x 12 heads x 4096 x 64, incl. the norm pre-pass, query pre-scaled):
+// never 772 TF/s, one in eight 821, one in four 912, one in two 961 -> the product uses one in two.
+#ifndef DCB_ATTN_POLY
+#define DCB_ATTN_POLY 2
 #endif
-__device__ __forceinline__ float ex2_poly(float x) {
-  const float magic = 12582912.f;
-  const float t = x + magic;
-  const float f = x - (t - magic);
-  float pl = fmaf(0.0551716685295105f, f, 0.2426111251115799f);
-  pl = fmaf(pl, f, 0.6932609677314758f);
-  pl = fmaf(pl, f, 0.9999280571937561f);
-  return __int_as_float(__float_as_int(pl) + (__float_as_int(t) << 23));
+__device__ __forceinline__ void ex2_poly2(float x0, float x1, float& p0, float& p1) {
+  const uint64_t magic = f2_pack(12582912.f, 12582912.f), nmagic = f2_pack(-12582912.f, -12582912.f);
+  const uint64_t neg1 = f2_pack(-1.f, -1.f);
+  const uint64_t c3 = f2_pack(0.0551716685295105f, 0.0551716685295105f), c2 = f2_pack(0.2426111251115799f, 0.2426111251115799f);
+  const uint64_t c1 = f2_pack(0.6932609677314758f, 0.6932609677314758f), c0 = f2_pack(0.9999280571937561f, 0.9999280571937561f);
+  const uint64_t x = f2_pack(x0, x1);
+  const uint64_t t = f2_add(x, magic);
+  const uint64_t f = f2_fma(f2_add(t, nmagic), neg1, x);      // x - n
+  uint64_t pl = f2_fma(c3, f, c2);
+  pl = f2_fma(pl, f, c1);
+  pl = f2_fma(pl, f, c0);
+  float t0, t1, q0, q1;
+  f2_unpack(t, t0, t1);
+  f2_unpack(pl, q0, q1);
+  p0 = __int_as_float(__float_as_int(q0) + (__float_as_int(t0) << 23));
+  p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
 }
 
 // the single-pass kernel is exact iff nothing underflows: max|q| max|k| c <= 50 bounds every (M_i - s_ij) c by 100 < 126
@@ -545,54 +583,76 @@ flash_attn_tc_fast_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid
     // caller has folded c into the query projection (sc == 1: dcb200's DiT does, at pack time) the score IS the exponent.
     const float sc = p.sc;
     const bool prescaled = fabsf(sc - 1.0f) < 1e-6f;
-    float l = 0.f;
-    auto key_blocks = [&](auto pre_tag) {      // two instantiations: the multiply is gone from the loop, not selected in it
+    const uint64_t sc2 = f2_pack(sc, sc);
+    float l0 = 0.f, l1 = 0.f;                  // even / odd columns: one packed add per pair of scores
+    // PRE: the multiply is gone from the loop, not selected in it.  MASKED: only the last key block of a ragged N
+    // compares column indices; everywhere else a score costs ex2 + half an add.f32x2 + half a cvt.bf16x2
+    auto key_block = [&](int j, auto pre_tag, auto mask_tag) {
       constexpr bool PRE = decltype(pre_tag)::value;
-      for (int j = 0; j < p.nblk; ++j) {
-        mbar_wait(s_full0 + t * 8, (uint32_t)(j & 1));
-        tc_fence_after();
-        const int valid = p.N - j * 128 - hf * 64;   // keys of this half block that exist (>= 64: all)
-        uint32_t pk[32];
-        float rs = 0.f;
+      constexpr bool MASKED = decltype(mask_tag)::value;
+      mbar_wait(s_full0 + t * 8, (uint32_t)(j & 1));
+      tc_fence_after();
+      const int valid = p.N - j * 128 - hf * 64;   // keys of this half block that exist (>= 64: all)
+      uint32_t pk[32];
 #pragma unroll
-        for (int c = 0; c < 64; c += 32) {
-          uint32_t sv[32];
-          tmem_ld32_nowait(s_addr + (uint32_t)c, sv);
-          tmem_ld_wait();
-          if (c == 32) {   // this thread's half row of S is in registers
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(s_free0 + t * 8);
-          }
+      for (int c = 0; c < 64; c += 32) {
+        uint32_t sv[32];
+        tmem_ld32_nowait(s_addr + (uint32_t)c, sv);
+        tmem_ld_wait();
+        if (c == 32) {   // this thread's half row of S is in registers
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(s_free0 + t * 8);
+        }
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const float x0 = PRE ? __uint_as_float(sv[i]) : __uint_as_float(sv[i]) * sc;
-            const float x1 = PRE ? __uint_as_float(sv[i + 1]) : __uint_as_float(sv[i + 1]) * sc;    // |x| <= 50 (at_fast_ok)
-            float p0 = ex2f(x0);
-            float p1 = (DCB_ATTN_POLY_MASK >= 0 && (i & DCB_ATTN_POLY_MASK) == 0) ? ex2_poly(x1) : ex2f(x1);
-            if (valid < 64) {
-              if (c + i >= valid) p0 = 0.f;
-              if (c + i + 1 >= valid) p1 = 0.f;
-            }
-            rs += p0 + p1;
-            pk[(c + i) >> 1] = pack_bf16x2(p0, p1);
+        for (int i = 0; i < 32; i += 4) {
+          float x[4], e[4];
+#pragma unroll
+          for (int u = 0; u < 4; u += 2) {   // |x| <= 50 (at_fast_ok)
+            x[u] = __uint_as_float(sv[i + u]);
+            x[u + 1] = __uint_as_float(sv[i + u + 1]);
+            if (!PRE) f2_unpack(f2_mul(f2_pack(x[u], x[u + 1]), sc2), x[u], x[u + 1]);
           }
+          e[0] = ex2f(x[0]);
+          e[1] = ex2f(x[1]);
+          const bool on_fma = DCB_ATTN_POLY == 2 || (DCB_ATTN_POLY == 4 && (i & 4) == 0) || (DCB_ATTN_POLY == 8 && (i & 12) == 0);
+          if (on_fma) {
+            ex2_poly2(x[2], x[3], e[2], e[3]);
+          } else {
+            e[2] = ex2f(x[2]);
+            e[3] = ex2f(x[3]);
+          }
+          if (MASKED) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (c + i + u >= valid) e[u] = 0.f;
+          }
+          add_f32x2(l0, l1, e[0], e[1]);
+          add_f32x2(l0, l1, e[2], e[3]);
+          pk[(c + i) >> 1] = pack_bf16x2(e[0], e[1]);
+          pk[((c + i) >> 1) + 1] = pack_bf16x2(e[2], e[3]);
         }
-        l += rs;
-        if (j > 0) {   // P_t is free once the previous block's P V has been consumed
-          mbar_wait(o_full0 + t * 8, (uint32_t)((j - 1) & 1));
-          tc_fence_after();
-        }
-        tmem_st16(p_addr, pk);
-        tmem_st16(p_addr + 16u, pk + 16);
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(p_full0 + t * 8);
       }
+      if (j > 0) {   // P_t is free once the previous block's P V has been consumed
+        mbar_wait(o_full0 + t * 8, (uint32_t)((j - 1) & 1));
+        tc_fence_after();
+      }
+      tmem_st16(p_addr, pk);
+      tmem_st16(p_addr + 16u, pk + 16);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full0 + t * 8);
+    };
+    auto key_blocks = [&](auto pre_tag) {
+      const bool ragged = (p.N & 127) != 0;
+      const int nfull = ragged ? p.nblk - 1 : p.nblk;
+      for (int j = 0; j < nfull; ++j) key_block(j, pre_tag, std::false_type{});
+      if (ragged) key_block(p.nblk - 1, pre_tag, std::true_type{});
     };
     if (prescaled) key_blocks(std::true_type{});
     else key_blocks(std::false_type{});
+    float l = l0 + l1;
     // the other half's share of the row sum, then O / l
     lsum[(t * 2 + hf) * 128 + r] = l;
     asm volatile("bar.sync %0, 256;" ::"r"(1 + t) : "memory");
