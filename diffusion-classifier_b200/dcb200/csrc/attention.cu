@@ -270,8 +270,8 @@ static int launch_simt(const void* q, const void* k, const void* v, int ld, int 
   return DCB_OK;
 }
 
-int launch_flash_tc(const void* q, const void* k, const void* v, int ld, int B, int N, int heads, float scale, void* out,
-                    int out_ld, float* norms_ws, cudaStream_t st);
+int launch_flash_tc(const void* q, const void* k, const void* v, int ld, int B, int N, int heads, int d, float scale,
+                    void* out, int out_ld, float* norms_ws, cudaStream_t st);
 
 }  // namespace dcb
 
@@ -293,11 +293,11 @@ extern "C" int dcb_attention_ws(int dtype, const void* q, const void* k, const v
   if (dtype == DCB_BF16) {
     DCB_REQUIRE(ld % 8 == 0 && ((uintptr_t)q & 15) == 0 && ((uintptr_t)k & 15) == 0 && ((uintptr_t)v & 15) == 0,
                 "attention: bf16 path needs 16-byte aligned rows");
-    // head dim 64 with at least one full key block: tcgen05 / TMEM kernel (attention_tc.cu); the mma.sync kernel keeps
-    // the small-N / other-head-dim cases (d = 32, 96, 128 are a few per cent of the U-Net configs' FLOPs)
+    // at least one full key block: tcgen05 / TMEM kernel (attention_tc.cu, every head dim); the mma.sync kernel keeps
+    // the sequences shorter than one 128-key block (the 8^2 levels)
     const bool tc_on = !(knobs() & DCB_KNOB_ATTN_NO_TC);
-    if (d == 64 && Ntok >= 128 && tc_on && out_ld % 8 == 0 && ((uintptr_t)out & 15) == 0)
-      return launch_flash_tc(q, k, v, ld, B, Ntok, heads, scale, out, out_ld, ws, st);
+    if (Ntok >= 128 && tc_on && out_ld % 8 == 0 && ((uintptr_t)out & 15) == 0)
+      return launch_flash_tc(q, k, v, ld, B, Ntok, heads, d, scale, out, out_ld, ws, st);
     DCB_ATTN_DISPATCH(launch_flash, )
   } else if (dtype == DCB_F32) {
     DCB_ATTN_DISPATCH(launch_simt, float, )

@@ -1,5 +1,6 @@
-// attention_tc.cu -- tcgen05 / TMEM flash attention (forward, no mask) for head dim 64 (two kernels: the running-maximum
-// kernel documented here and the single-pass kernel further down, which the launcher prefers for N >= 1024): softmax(Q K^T * scale) V per
+// attention_tc.cu -- tcgen05 / TMEM flash attention (forward, no mask): the running-maximum kernel documented here
+// (head dims 32 / 64 / 96 / 128, described for 64; see AtGeo for the others) and the single-pass kernel further down
+// (head dim 64, which the launcher prefers for N >= 1024): softmax(Q K^T * scale) V per
 // (batch, head), replacing F.scaled_dot_product_attention behind diffusers' AttnProcessor2_0
 // for the DiT blocks (12 heads x 64, N = 4096 tokens) and the U-Net Transformer2D blocks with C/8 = 64.
 //
@@ -154,22 +155,45 @@ struct AtParams {
   const float* norms;   // [2 + B*heads*2] fp32: global max|q|^2, max|k|^2, then the same per (batch, head); NULL = none
 };
 
+// Head dims other than 64 (template D = 32 / 96 / 128, the U-Net levels whose channels / heads is not 64): the same program
+// with NB = ceil(D / 64) boxes of [128 tokens x 64 ch] per Q / K / V tile (a box always carries 64 channels -- for D = 32
+// and 96 the upper half of the last box is the next head's data or TMA zero fill and is never multiplied in Q K^T: the
+// product runs D / 16 k-steps), P V computed NB * 64 channels wide (the surplus columns are finite and never stored), the
+// K / V rings two deep for NB = 2, and -- D > 64 only, where 2 x (128 S + 64 P + NB * 64 O) columns do not fit TMEM --
+// P_t written over the first 64 columns of S_t: pass 2 reads 32 score columns and then stores 16 packed columns that lie at
+// or below what it has read, and the MMA warp issues P_t V_j BEFORE Q_t K_{j+1}^T so the tensor pipe (in order) has consumed
+// P_t when S_t is overwritten.
+template <int D>
+struct AtGeo {
+  static constexpr int NB = (D + 63) / 64;                 // 64-channel boxes per tile
+  static constexpr int STAGES = NB == 1 ? AT_KV_STAGES : 2;
+  static constexpr int TILE = NB * AT_TILE_BYTES;
+  static constexpr int PVN = NB * 64;                      // channels the P V product computes
+  static constexpr bool ALIAS = D > 64;
+  static constexpr int P_COL0 = ALIAS ? 0 : 256, P_STRIDE = ALIAS ? 128 : 64;
+  static constexpr int O_COL0 = ALIAS ? 256 : 384, O_STRIDE = PVN;
+  static constexpr size_t SMEM = 1024 + (size_t)(2 + 2 * STAGES) * TILE + 256 + 2048;
+};
+
+template <int D>
 __global__ void __launch_bounds__(AT_THREADS, 1)
 flash_attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                      const __grid_constant__ CUtensorMap mapV, const __grid_constant__ AtParams p,
                      __nv_bfloat16* __restrict__ out) {
+  using G = AtGeo<D>;
+  constexpr int NB = G::NB, STAGES = G::STAGES, TILE = G::TILE;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* q_s = smem;                                    // 2 tiles
-  uint8_t* k_s = q_s + 2 * AT_TILE_BYTES;                 // ring
-  uint8_t* v_s = k_s + AT_KV_STAGES * AT_TILE_BYTES;      // ring
-  uint64_t* bars = reinterpret_cast<uint64_t*>(v_s + AT_KV_STAGES * AT_TILE_BYTES);
+  uint8_t* k_s = q_s + 2 * TILE;                          // ring
+  uint8_t* v_s = k_s + STAGES * TILE;                     // ring
+  uint64_t* bars = reinterpret_cast<uint64_t*>(v_s + STAGES * TILE);
   uint64_t* q_full = bars;                       // [1]
   uint64_t* k_full = bars + 1;                   // [stages]
-  uint64_t* k_empty = k_full + AT_KV_STAGES;
-  uint64_t* v_full = k_empty + AT_KV_STAGES;
-  uint64_t* v_empty = v_full + AT_KV_STAGES;
-  uint64_t* s_full = v_empty + AT_KV_STAGES;     // [2]  MMA -> softmax: S_t(j) complete
+  uint64_t* k_empty = k_full + STAGES;
+  uint64_t* v_full = k_empty + STAGES;
+  uint64_t* v_empty = v_full + STAGES;
+  uint64_t* s_full = v_empty + STAGES;           // [2]  MMA -> softmax: S_t(j) complete
   uint64_t* p_full = s_full + 2;                 // [2]  softmax -> MMA: P_t(j) written, S_t and O_t free again
   uint64_t* o_full = p_full + 2;                 // [2]  MMA -> softmax: O_t(j) = P_t(j) V_j complete
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
@@ -186,7 +210,7 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
     prefetch_tmap(&mapK);
     prefetch_tmap(&mapV);
     mbar_init(smem_u32(q_full), 1);
-    for (int i = 0; i < AT_KV_STAGES; ++i) {
+    for (int i = 0; i < STAGES; ++i) {
       mbar_init(smem_u32(&k_full[i]), 1);
       mbar_init(smem_u32(&k_empty[i]), 1);
       mbar_init(smem_u32(&v_full[i]), 1);
@@ -216,9 +240,12 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
     // ===================== TMA producer =====================
     if (elect_one()) {
       const uint32_t fq = smem_u32(q_full);
-      mbar_expect_tx(fq, 2u * AT_TILE_BYTES);
-      tma_load_3d(smem_u32(q_s), &mapQ, fq, h * 64, q0, b);
-      tma_load_3d(smem_u32(q_s + AT_TILE_BYTES), &mapQ, fq, h * 64, q0 + 128, b);
+      mbar_expect_tx(fq, 2u * TILE);
+#pragma unroll
+      for (int x = 0; x < NB; ++x) {
+        tma_load_3d(smem_u32(q_s + x * AT_TILE_BYTES), &mapQ, fq, h * D + x * 64, q0, b);
+        tma_load_3d(smem_u32(q_s + TILE + x * AT_TILE_BYTES), &mapQ, fq, h * D + x * 64, q0 + 128, b);
+      }
     }
     __syncwarp();
     int st = 0;
@@ -226,45 +253,54 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
     for (int j = 0; j < p.nblk; ++j) {
       mbar_wait(k_empty0 + st * 8, ph ^ 1);
       if (elect_one()) {
-        mbar_expect_tx(k_full0 + st * 8, (uint32_t)AT_TILE_BYTES);
-        tma_load_3d(smem_u32(k_s + st * AT_TILE_BYTES), &mapK, k_full0 + st * 8, h * 64, j * 128, b);
+        mbar_expect_tx(k_full0 + st * 8, (uint32_t)TILE);
+#pragma unroll
+        for (int x = 0; x < NB; ++x)
+          tma_load_3d(smem_u32(k_s + st * TILE + x * AT_TILE_BYTES), &mapK, k_full0 + st * 8, h * D + x * 64, j * 128, b);
       }
       __syncwarp();
       mbar_wait(v_empty0 + st * 8, ph ^ 1);
       if (elect_one()) {
-        mbar_expect_tx(v_full0 + st * 8, (uint32_t)AT_TILE_BYTES);
-        tma_load_3d(smem_u32(v_s + st * AT_TILE_BYTES), &mapV, v_full0 + st * 8, h * 64, j * 128, b);
+        mbar_expect_tx(v_full0 + st * 8, (uint32_t)TILE);
+#pragma unroll
+        for (int x = 0; x < NB; ++x)
+          tma_load_3d(smem_u32(v_s + st * TILE + x * AT_TILE_BYTES), &mapV, v_full0 + st * 8, h * D + x * 64, j * 128, b);
       }
       __syncwarp();
-      if (++st == AT_KV_STAGES) { st = 0; ph ^= 1; }
+      if (++st == STAGES) { st = 0; ph ^= 1; }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    // instruction descriptors: D fp32, A/B bf16; QK^T: N=128, both K-major; PV: N=64, B (=V) MN-major
+    // instruction descriptors: D fp32, A/B bf16; QK^T: N=128, both K-major; PV: N = NB * 64, B (=V) MN-major
     const uint32_t idesc_qk = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
-    const uint32_t idesc_pv = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t idesc_pv =
+        (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | (((uint32_t)G::PVN >> 3) << 17) | ((128u >> 4) << 24);
     const uint32_t hi_k = (uint32_t)(make_kmajor_sw128_desc(0) >> 32);  // SBO 1024, version 1, SWIZZLE_128B
     const uint32_t hi_v = hi_k;                                         // MN-major: SBO = 1024 B between 8-token groups
     const uint32_t q_lo = ((smem_u32(q_s) & 0x3FFFFu) >> 4) | (1u << 16);
     const uint32_t k_lo0 = ((smem_u32(k_s) & 0x3FFFFu) >> 4) | (1u << 16);
-    const uint32_t v_lo0 = ((smem_u32(v_s) & 0x3FFFFu) >> 4) | (1u << 16);
+    // V: leading byte offset = distance between the 64-channel atoms along N (the next box); unused for NB = 1
+    const uint32_t v_lo0 = ((smem_u32(v_s) & 0x3FFFFu) >> 4) | ((NB == 1 ? 1u : (uint32_t)(AT_TILE_BYTES >> 4)) << 16);
     auto issue_qk = [&](int t, int st) {
-      const uint32_t a = q_lo + (uint32_t)t * (AT_TILE_BYTES >> 4), bq = k_lo0 + (uint32_t)st * (AT_TILE_BYTES >> 4);
+      const uint32_t a = q_lo + (uint32_t)t * (TILE >> 4), bq = k_lo0 + (uint32_t)st * (TILE >> 4);
       if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_f16_lohi(tmem_base + (uint32_t)(t * 128), a + 2 * k, bq + 2 * k, hi_k, idesc_qk, k ? 1u : 0u);
+        for (int k = 0; k < D / 16; ++k) {   // 16 channels per step: 32 B inside the 128-byte row of box k / 4
+          const uint32_t off = (uint32_t)((k >> 2) * (AT_TILE_BYTES >> 4) + 2 * (k & 3));
+          umma_f16_lohi(tmem_base + (uint32_t)(t * 128), a + off, bq + off, hi_k, idesc_qk, k ? 1u : 0u);
+        }
         umma_commit(s_full0 + t * 8);
       }
       __syncwarp();
     };
     auto issue_pv = [&](int t, int st) {
-      const uint32_t bv = v_lo0 + (uint32_t)st * (AT_TILE_BYTES >> 4);
+      const uint32_t bv = v_lo0 + (uint32_t)st * (TILE >> 4);
       if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < 8; ++k)   // 16 keys per step: 8 TMEM columns of packed bf16 pairs, 2 x 1024 B of V rows
-          umma_f16_ts(tmem_base + (uint32_t)(384 + t * 64), tmem_base + (uint32_t)(256 + t * 64 + k * 8),
-                      bv + (uint32_t)k * (2048 >> 4), hi_v, idesc_pv, k ? 1u : 0u);
+          umma_f16_ts(tmem_base + (uint32_t)(G::O_COL0 + t * G::O_STRIDE),
+                      tmem_base + (uint32_t)(G::P_COL0 + t * G::P_STRIDE + k * 8), bv + (uint32_t)k * (2048 >> 4), hi_v,
+                      idesc_pv, k ? 1u : 0u);
         umma_commit(o_full0 + t * 8);
       }
       __syncwarp();
@@ -276,19 +312,25 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
     issue_qk(1, 0);
     if (elect_one()) umma_commit(k_empty0);
     __syncwarp();
-    int st = 0, stn = 1 % AT_KV_STAGES;
-    uint32_t ph = 0, phn = (AT_KV_STAGES == 1) ? 1u : 0u;
+    int st = 0, stn = 1 % STAGES;
+    uint32_t ph = 0, phn = (STAGES == 1) ? 1u : 0u;
     for (int j = 0; j < p.nblk; ++j) {
       const bool more = j + 1 < p.nblk;
       for (int t = 0; t < 2; ++t) {
         mbar_wait(p_full0 + t * 8, (uint32_t)(j & 1));
         tc_fence_after();
+        if (G::ALIAS) {   // P_t lives in S_t: the product that reads it goes first
+          if (t == 0) { mbar_wait(v_full0 + st * 8, ph); tc_fence_after(); }
+          issue_pv(t, st);
+        }
         if (more) {
           if (t == 0) { mbar_wait(k_full0 + stn * 8, phn); tc_fence_after(); }
           issue_qk(t, stn);
         }
-        if (t == 0) { mbar_wait(v_full0 + st * 8, ph); tc_fence_after(); }
-        issue_pv(t, st);
+        if (!G::ALIAS) {
+          if (t == 0) { mbar_wait(v_full0 + st * 8, ph); tc_fence_after(); }
+          issue_pv(t, st);
+        }
       }
       if (elect_one()) {
         if (more) umma_commit(k_empty0 + stn * 8);
@@ -296,7 +338,7 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
       }
       __syncwarp();
       st = stn; ph = phn;
-      if (++stn == AT_KV_STAGES) { stn = 0; phn ^= 1; }
+      if (++stn == STAGES) { stn = 0; phn ^= 1; }
     }
   } else {
     // ===================== softmax groups =====================
@@ -305,11 +347,11 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
     const int r = qd * 32 + lane;           // query row inside the tile == TMEM lane
     const uint32_t lane_addr = tmem_base + ((uint32_t)(qd * 32) << 16);
     const uint32_t s_addr = lane_addr + (uint32_t)(t * 128);
-    const uint32_t p_addr = lane_addr + (uint32_t)(256 + t * 64);
-    const uint32_t o_addr = lane_addr + (uint32_t)(384 + t * 64);
-    float o[64];
+    const uint32_t p_addr = lane_addr + (uint32_t)(G::P_COL0 + t * G::P_STRIDE);
+    const uint32_t o_addr = lane_addr + (uint32_t)(G::O_COL0 + t * G::O_STRIDE);
+    float o[D];
 #pragma unroll
-    for (int i = 0; i < 64; ++i) o[i] = 0.f;
+    for (int i = 0; i < D; ++i) o[i] = 0.f;
     float m = -1e30f, l = 0.f, alpha_prev = 1.f;
     const float sc = p.sc;
     for (int j = 0; j < p.nblk; ++j) {
@@ -341,7 +383,7 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
         mbar_wait(o_full0 + t * 8, (uint32_t)((j - 1) & 1));
         tc_fence_after();
 #pragma unroll
-        for (int c = 0; c < 64; c += 32) {
+        for (int c = 0; c < D; c += 32) {
           uint32_t ov[32];
           tmem_ld32_nowait(o_addr + (uint32_t)c, ov);
           tmem_ld_wait();
@@ -382,9 +424,9 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
     tc_fence_after();
     const float inv = 1.f / l;
     const int qrow = q0 + t * 128 + r;
-    __nv_bfloat16* orow = out + ((int64_t)b * p.N + qrow) * p.out_ld + h * 64;
+    __nv_bfloat16* orow = out + ((int64_t)b * p.N + qrow) * p.out_ld + h * D;
 #pragma unroll
-    for (int c = 0; c < 64; c += 32) {
+    for (int c = 0; c < D; c += 32) {
       uint32_t ov[32];
       tmem_ld32_nowait(o_addr + (uint32_t)c, ov);
       tmem_ld_wait();
@@ -786,30 +828,31 @@ static int encode_tok_map(CUtensorMap* map, const void* base, int ld, int N, int
   return DCB_OK;
 }
 
-// head dim 64, bf16, N >= 128; q/k/v: [B, N, heads, 64] views with row stride ld.
-// norms_ws: [2 + B*heads*2] fp32 workspace or NULL.  With it (and enough key blocks for the norm pre-pass to pay) the
-// single-pass kernel is enqueued ahead of the running-maximum kernel and the device decides which of the two runs.
-int launch_flash_tc(const void* q, const void* k, const void* v, int ld, int B, int N, int heads, float scale, void* out,
-                    int out_ld, float* norms_ws, cudaStream_t st) {
+// head dim D, bf16, N >= 128; q/k/v: [B, N, heads, D] views with row stride ld.
+// norms_ws: [2 + B*heads*2] fp32 workspace or NULL.  With it (D = 64 and enough key blocks for the norm pre-pass to pay)
+// the single-pass kernel is enqueued ahead of the running-maximum kernel and the device decides which of the two runs.
+template <int D>
+static int launch_flash_tc_d(const void* q, const void* k, const void* v, int ld, int B, int N, int heads, float scale,
+                             void* out, int out_ld, float* norms_ws, cudaStream_t st) {
   DCB_REQUIRE(out_ld % 8 == 0 && ((uintptr_t)out & 15) == 0, "attention: out rows must be 16-byte aligned");
   CUtensorMap mq, mk, mv;
   int rc;
-  if ((rc = encode_tok_map(&mq, q, ld, N, B, heads * 64))) return rc;
-  if ((rc = encode_tok_map(&mk, k, ld, N, B, heads * 64))) return rc;
-  if ((rc = encode_tok_map(&mv, v, ld, N, B, heads * 64))) return rc;
+  if ((rc = encode_tok_map(&mq, q, ld, N, B, heads * D))) return rc;
+  if ((rc = encode_tok_map(&mk, k, ld, N, B, heads * D))) return rc;
+  if ((rc = encode_tok_map(&mv, v, ld, N, B, heads * D))) return rc;
   AtParams p;
   p.N = N;
   p.nblk = (N + 127) / 128;
   p.sc = scale * 1.4426950408889634f;
   p.out_ld = out_ld;
   const bool fast_on = !(knobs() & DCB_KNOB_ATTN_NO_FAST);
-  const bool use_fast = norms_ws != nullptr && fast_on && N >= 1024;   // short sequences: two extra launches do not pay
+  const bool use_fast = D == 64 && norms_ws != nullptr && fast_on && N >= 1024;   // short sequences: two extra launches do not pay
   p.norms = use_fast ? norms_ws : nullptr;
-  const size_t smem = 1024 + (2 + 2 * AT_KV_STAGES) * AT_TILE_BYTES + 256 + 2048;
+  const size_t smem = AtGeo<D>::SMEM;
   static std::once_flag once;
   std::call_once(once, [] {
-    cudaFuncSetAttribute(flash_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT);
-    cudaFuncSetAttribute(flash_attn_tc_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT);
+    cudaFuncSetAttribute(flash_attn_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT);
+    if (D == 64) cudaFuncSetAttribute(flash_attn_tc_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT);
   });
   dim3 grid((N + 255) / 256, heads, B);
   if (use_fast) {
@@ -824,9 +867,21 @@ int launch_flash_tc(const void* q, const void* k, const void* v, int ld, int B, 
     flash_attn_tc_fast_kernel<<<grid, ATF_THREADS, smem, st>>>(mq, mk, mv, p, (__nv_bfloat16*)out);
     DCB_CHECK_LAUNCH("flash_attn_tc_fast");
   }
-  flash_attn_tc_kernel<<<grid, AT_THREADS, smem, st>>>(mq, mk, mv, p, (__nv_bfloat16*)out);
+  flash_attn_tc_kernel<D><<<grid, AT_THREADS, smem, st>>>(mq, mk, mv, p, (__nv_bfloat16*)out);
   DCB_CHECK_LAUNCH("flash_attn_tc");
   return DCB_OK;
+}
+
+int launch_flash_tc(const void* q, const void* k, const void* v, int ld, int B, int N, int heads, int d, float scale,
+                    void* out, int out_ld, float* norms_ws, cudaStream_t st) {
+  switch (d) {
+    case 32: return launch_flash_tc_d<32>(q, k, v, ld, B, N, heads, scale, out, out_ld, norms_ws, st);
+    case 64: return launch_flash_tc_d<64>(q, k, v, ld, B, N, heads, scale, out, out_ld, norms_ws, st);
+    case 96: return launch_flash_tc_d<96>(q, k, v, ld, B, N, heads, scale, out, out_ld, norms_ws, st);
+    case 128: return launch_flash_tc_d<128>(q, k, v, ld, B, N, heads, scale, out, out_ld, norms_ws, st);
+  }
+  set_error("attention: head dim %d not in {32,64,96,128}", d);
+  return DCB_EINVAL;
 }
 
 }  // namespace dcb

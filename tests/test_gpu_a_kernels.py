@@ -276,6 +276,30 @@ def test_attention_tcgen05_head64(dev, B, heads, N, qscale):
     assert rel_err(out, simt) < 1e-2
 
 
+@pytest.mark.parametrize("d", [32, 96, 128])
+@pytest.mark.parametrize("B,heads,N,qscale", [(2, 3, 128, 3.0), (2, 5, 300, 3.0), (1, 4, 1024, 3.0), (1, 2, 4096, 1.0),
+                                               (3, 1, 1000, 6.0), (1, 2, 512, 0.0)])
+def test_attention_tcgen05_other_head_dims(dev, d, B, heads, N, qscale):
+    """the running-maximum tcgen05 kernel at head dims 32 / 96 / 128 (two 64-channel boxes per tile for d > 64, P written
+    over S in TMEM, P V before the next Q K^T) against torch SDPA in fp32 on the same bf16 inputs and against the
+    mma.sync kernel (DCB_KNOB_ATTN_NO_TC) it replaces for N >= 128; ragged N, sharp softmax, all-zero queries."""
+    from dcb200 import engine as E, _lib as L
+    torch.manual_seed(N + d)
+    qkv = torch.randn(B * N, 3 * heads * d, device=dev)
+    qkv[:, : heads * d] *= qscale
+    qb = qkv.to(torch.bfloat16)
+    q, k, v = (t.float().reshape(B, N, heads, d).transpose(1, 2) for t in qb.chunk(3, -1))
+    ref = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B * N, heads * d)
+    out = E.attention(_ctx(dev, "bf16"), qb, B, N, heads, d).float()
+    assert torch.isfinite(out).all()
+    assert rel_err(out, ref) < 1e-2
+    with L.knob("ATTN_NO_TC"):
+        old = E.attention(_ctx(dev, "bf16"), qb, B, N, heads, d).float()
+    assert rel_err(out, old) < 1e-2
+    again = E.attention(_ctx(dev, "bf16"), qb, B, N, heads, d).float()
+    assert torch.equal(out, again)
+
+
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 @pytest.mark.parametrize("C0,C1,HW,NB,div1", [(256, 0, 64, 7, 1), (256, 256, 16, 300, 1), (512, 0, 16, 33, 1),
                                               (384, 128, 64, 12, 3), (1024, 0, 16, 5, 1)])

@@ -7,7 +7,7 @@ import torch
 from dcb200 import engine as E
 dev = torch.device("cuda:0")
 ctx = E.Ctx(device=dev, precision="bf16")
-B, heads, N, d = int(os.environ.get("AB", 16)), 12, int(os.environ.get("AN", 4096)), 64
+B, heads, N, d = int(os.environ.get("AB", 16)), int(os.environ.get("AH", 12)), int(os.environ.get("AN", 4096)), int(os.environ.get("AD", 64))
 qkv = torch.randn(B * N, 3 * heads * d, device=dev).to(torch.bfloat16)
 fl = 4.0 * B * heads * N * N * d
 qkv = qkv * 0.35   # q, k of the size DiT's LayerNorm'd projections produce: the single-pass kernel's bound holds
