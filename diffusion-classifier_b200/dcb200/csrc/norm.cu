@@ -392,6 +392,111 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const T* __restrict__ x,
   }
 }
 
+
+// bf16 rows: the row stays PACKED in registers (16-byte vectors, unpacked again in each of the three passes -- a shift per
+// element) so that a warp can hold R rows in flight at 4 registers per vector instead of 8: the one-row fp32 form needs 79
+// registers (3 blocks / SM, 36 KB of loads in flight per SM, and only while a warp is in its load phase: 2.9 TB/s = 45 %
+// of the copy peak on the DiT adaLN shape).  Arithmetic and its order per row are those of layernorm_kernel: bit-identical.
+// MEASURED (tools/ln_micro.py, GB/s of read + write, one box): fp32-register form 3 291 (DiT adaLN 262 144 x 768) / 3 155
+// (U-Net affine 204 800 x 512) / 3 381 (51 200 x 1024); packed R = 1: 3 988 / 4 550 / 4 458; R = 2: 4 156 / 4 118 / 3 455;
+// R = 4: 3 431 / 4 215 / 3 313 -> one row per warp, two for the three-vector rows (C in (512, 768]: the DiT width).
+#ifdef DCB_LN_R
+#define DCB_LN_ROWS(MAXV) DCB_LN_R
+#else
+#define DCB_LN_ROWS(MAXV) ((MAXV) == 3 ? 2 : 1)
+#endif
+template <int MAXV, int R>
+__global__ void __launch_bounds__(256) layernorm_bf16_kernel(const __nv_bfloat16* __restrict__ x, int64_t rows, int C,
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                            float eps, const float* __restrict__ scale,
+                                                            const float* __restrict__ shift, int mod_ld, int rows_per_group,
+                                                            __nv_bfloat16* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * R;
+  if (row0 >= rows) return;
+  const int V = C >> 3;
+  const float inv_c = 1.f / (float)C;
+  uint4 raw[R][MAXV];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+#pragma unroll
+    for (int j = 0; j < MAXV; ++j) {
+      const int v = lane + j * 32;
+      raw[r][j] = make_uint4(0u, 0u, 0u, 0u);
+      if (v < V && row0 + r < rows) raw[r][j] = *reinterpret_cast<const uint4*>(x + (row0 + r) * C + v * 8);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int64_t row = row0 + r;
+    if (row >= rows) break;
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < MAXV; ++j) {
+      if (lane + j * 32 < V) {
+        float f[8];
+        unpack_bf16x8(raw[r][j], f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += f[i];
+      }
+    }
+    const float mean = warp_sum(s) * inv_c;
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < MAXV; ++j) {
+      if (lane + j * 32 < V) {
+        float f[8];
+        unpack_bf16x8(raw[r][j], f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { float d = f[i] - mean; q = fmaf(d, d, q); }
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(q) * inv_c + eps);
+    const int64_t grp = rows_per_group > 0 ? row / rows_per_group : 0;
+    const float* sp = scale ? scale + grp * mod_ld : nullptr;
+    const float* hp = scale ? shift + grp * mod_ld : nullptr;
+    __nv_bfloat16* orow = out + row * C;
+#pragma unroll
+    for (int j = 0; j < MAXV; ++j) {
+      const int v = lane + j * 32;
+      if (v < V) {
+        const int c = v * 8;
+        float f[8];
+        unpack_bf16x8(raw[r][j], f);
+#pragma unroll
+        for (int i = 0; i < 8; i += 4) {
+          float y[4] = {(f[i] - mean) * rstd, (f[i + 1] - mean) * rstd, (f[i + 2] - mean) * rstd, (f[i + 3] - mean) * rstd};
+          if (gamma) {
+            const float4 g4 = *reinterpret_cast<const float4*>(gamma + c + i);
+            y[0] *= g4.x; y[1] *= g4.y; y[2] *= g4.z; y[3] *= g4.w;
+          }
+          if (beta) {
+            const float4 b4 = *reinterpret_cast<const float4*>(beta + c + i);
+            y[0] += b4.x; y[1] += b4.y; y[2] += b4.z; y[3] += b4.w;
+          }
+          if (sp) {
+            const float4 s4 = *reinterpret_cast<const float4*>(sp + c + i);
+            const float4 h4 = *reinterpret_cast<const float4*>(hp + c + i);
+            y[0] = fmaf(y[0], 1.f + s4.x, h4.x); y[1] = fmaf(y[1], 1.f + s4.y, h4.y);
+            y[2] = fmaf(y[2], 1.f + s4.z, h4.z); y[3] = fmaf(y[3], 1.f + s4.w, h4.w);
+          }
+          f[i] = y[0]; f[i + 1] = y[1]; f[i + 2] = y[2]; f[i + 3] = y[3];
+        }
+        *reinterpret_cast<uint4*>(orow + c) = pack_bf16x8(f);
+      }
+    }
+  }
+}
+
+template <int MAXV>
+static void launch_ln_bf16(const void* x, int64_t rows, int C, const float* gamma, const float* beta, float eps,
+                           const float* scale, const float* shift, int mod_ld, int rows_per_group, void* out, cudaStream_t st) {
+  constexpr int R = DCB_LN_ROWS(MAXV), WPB = 8;
+  const int64_t warps = (rows + R - 1) / R;
+  layernorm_bf16_kernel<MAXV, R><<<(unsigned)((warps + WPB - 1) / WPB), WPB * 32, 0, st>>>(
+      (const __nv_bfloat16*)x, rows, C, gamma, beta, eps, scale, shift, mod_ld, rows_per_group, (__nv_bfloat16*)out);
+}
+
 }  // namespace dcb
 
 using namespace dcb;
@@ -499,10 +604,20 @@ extern "C" int dcb_layernorm(int dtype, const void* x, int64_t rows, int C, cons
   const int wpb = 8;
   const int64_t warps = (rows + LN_ROWS - 1) / LN_ROWS;
   const unsigned grid = (unsigned)((warps + wpb - 1) / wpb);
-  if (dtype == DCB_BF16)
+#ifdef DCB_LN_OLD   // A/B only: the one-row fp32-register form on bf16 data
+  if (dtype == DCB_BF16) {
     layernorm_kernel<__nv_bfloat16><<<grid, wpb * 32, 0, st>>>((const __nv_bfloat16*)x, rows, C, gamma, beta, eps, scale,
                                                                shift, mod_ld, rows_per_group, (__nv_bfloat16*)out);
-  else
+  } else
+#endif
+  if (dtype == DCB_BF16) {
+    switch ((C / 8 + 31) / 32) {
+      case 1: launch_ln_bf16<1>(x, rows, C, gamma, beta, eps, scale, shift, mod_ld, rows_per_group, out, st); break;
+      case 2: launch_ln_bf16<2>(x, rows, C, gamma, beta, eps, scale, shift, mod_ld, rows_per_group, out, st); break;
+      case 3: launch_ln_bf16<3>(x, rows, C, gamma, beta, eps, scale, shift, mod_ld, rows_per_group, out, st); break;
+      default: launch_ln_bf16<4>(x, rows, C, gamma, beta, eps, scale, shift, mod_ld, rows_per_group, out, st); break;
+    }
+  } else
     layernorm_kernel<float><<<grid, wpb * 32, 0, st>>>((const float*)x, rows, C, gamma, beta, eps, scale, shift, mod_ld,
                                                        rows_per_group, (float*)out);
   DCB_CHECK_LAUNCH("layernorm");
