@@ -328,7 +328,8 @@ def run_ours(args):
     hbm_peak = peaks["hbm_gbs"]
     gn_gbs = gn_bytes / (gn_ms / 1e3) / 1e9 if gn_ms > 0 else 0.0
     roofline = {
-        "bound": "tensor", "kernel": "gemm_tc_kernel + gemm_tc2_kernel (tcgen05 implicit GEMM)", "achieved": achieved,
+        "bound": "tensor", "kernel": "tcgen05 GEMM kernels (gemm_tc, gemm_tc2, gemm_tc2x, gemm_tc3: implicit-GEMM convs and "
+                                     "linears)", "achieved": achieved,
         "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
         "peak_source": f"{peak_src} bf16_tflops_sustained",
         "achieved_basis": "executed FLOPs (2 M N K of every tcgen05 GEMM launch) / summed CUDA-event durations of those "
@@ -352,6 +353,16 @@ def run_ours(args):
             "achieved_basis": "one read + one write of every normalised tensor / summed CUDA-event durations",
             "launches_per_step": n_gn // passes, "kernel_share_of_step": (gn_ms / passes) / (ms / args.steps)},
     }
+    at_ms, at_flops, n_at = prof.attn_totals()
+    if at_ms > gn_ms and n_at:   # DiT: attention, not GroupNorm, is the second kernel of the step
+        at_tf = at_flops / (at_ms / 1e3) / 1e12
+        roofline["secondary"] = {
+            "kernel": "flash_attn_tc_fast_kernel / flash_attn_tc_kernel (tcgen05 attention, incl. the norm pre-pass)",
+            "bound": "tensor", "achieved": at_tf, "peak": peak, "unit": "TFLOP/s", "frac": at_tf / peak,
+            "peak_source": f"{peak_src} bf16_tflops_sustained",
+            "achieved_basis": "4 B h N^2 d / summed CUDA-event durations of the attention calls; the softmax (one exponential "
+                              "per score on the XU / FMA pipes) bounds this kernel below the tensor peak at head dim 64",
+            "launches_per_step": n_at // passes, "kernel_share_of_step": (at_ms / passes) / (ms / args.steps)}
     tr = os.path.join(ROOT, "profiles", "r02_traffic.json")   # per-launch DRAM bytes of the dominant kernel from the
     if os.path.exists(tr):                                     # committed `ncu --set full` capture (same workload)
         try:

@@ -40,6 +40,12 @@ class GemmProfile:
     def __init__(self):
         self.rows = []     # (start_event, end_event, flops, tag)
         self.gn_rows = []  # (start_event, end_event, algorithmic bytes) of every streaming GroupNorm-apply launch
+        self.attn_rows = []  # (start_event, end_event, 4 B h N^2 d) of every tcgen05 attention call (N >= 128)
+
+    def attn_totals(self):
+        torch.cuda.synchronize()
+        return (sum(a.elapsed_time(b) for a, b, _ in self.attn_rows), sum(f for _, _, f in self.attn_rows),
+                len(self.attn_rows))
 
     def gn_totals(self):
         torch.cuda.synchronize()
@@ -330,9 +336,16 @@ def attention(ctx, qkv, B, Ntok, heads, d, q_off=0, k_off=None, v_off=None, simt
     out = torch.empty(B * Ntok, Cw, device=ctx.device, dtype=qkv.dtype)
     code = ctx.code | (0x100 if (simt and ctx.code == L.BF16) else 0)
     ws = torch.empty(2 + B * heads * 2, device=ctx.device, dtype=torch.float32) if code == L.BF16 and d == 64 else None
+    prof = PROFILE if (PROFILE is not None and code == L.BF16 and Ntok >= 128) else None
+    if prof is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     L.check(L.lib().dcb_attention_ws(code, base + q_off * es, base + k_off * es, base + v_off * es, ld, B, Ntok, heads, d,
                                      float(d) ** -0.5 if scale is None else float(scale), out.data_ptr(), Cw, _p(ws),
                                      ctx.stream()), "attention")
+    if prof is not None:
+        e1.record()
+        prof.attn_rows.append((e0, e1, 4.0 * B * heads * Ntok * Ntok * d))
     return out
 
 
