@@ -18,6 +18,7 @@ from __future__ import annotations
 
 import math
 import os
+import time
 
 import torch
 import torch.nn as nn
@@ -187,6 +188,7 @@ class DiffusionClassifier(nn.Module):
         self.last_errors = None  # [BS, classes, T] fp32 table of the most recent classify() call
         self._eps_calls = 0
         self._graphs = _GraphCache()
+        self._mem_probe = None     # (time, bytes the device could still give us) of the last cudaMemGetInfo
 
     # ---- schedule (diffusion_classifier.py:119-161), evaluated exactly as the reference does ------------------
     def logsnr_schedule_cosine(self, t, logsnr_min=-15, logsnr_max=15):
@@ -222,12 +224,17 @@ class DiffusionClassifier(nn.Module):
         want = max(1, min(2048, (1 << 24) // (H * W)))
         if "DCB_MAX_BATCH" in os.environ:
             return int(os.environ["DCB_MAX_BATCH"])
-        try:
-            free, _ = torch.cuda.mem_get_info()
-            free += torch.cuda.memory_reserved() - torch.cuda.memory_allocated()
+        now = time.monotonic()     # cudaMemGetInfo costs ~1 ms of host time ahead of the first launch: ask once a second
+        if self._mem_probe is None or now - self._mem_probe[0] > 1.0:
+            try:
+                free, _ = torch.cuda.mem_get_info()
+                free += torch.cuda.memory_reserved() - torch.cuda.memory_allocated()
+            except RuntimeError:
+                free = None
+            self._mem_probe = (now, free)
+        free = self._mem_probe[1]
+        if free is not None:
             want = max(1, min(want, int(0.5 * free / (2560.0 * H * W))))
-        except RuntimeError:
-            pass
         return want
 
     # ---- the hot path ---------------------------------------------------------------------------------------------

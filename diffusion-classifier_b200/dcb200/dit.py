@@ -125,7 +125,7 @@ class DiT(nn.Module):
         self.precision = "bf16"
 
     def _version(self):
-        return tuple(p._version for p in self.parameters()) + tuple(p.data_ptr() for p in self.parameters())
+        return E.params_version(self)
 
     @staticmethod
     def _fold_qscale(ctx):

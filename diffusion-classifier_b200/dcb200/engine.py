@@ -82,6 +82,24 @@ FUSE_GN_MSE = __import__("os").environ.get("DCB_FUSE_GN_MSE", "0") != "0"
 XF_UNSUPPORTED = object()     # gemm(xf=...) sentinel: this launch cannot apply the fused transform; nothing was launched
 
 
+def params_version(module):
+    """(version counter, address) of every parameter of ``module``, walked iteratively over ``_modules`` / ``_parameters``
+    (0.2 ms for the 491 tensors of unet-128 instead of the 2 ms two ``module.parameters()`` generators take: this runs at
+    the top of every classify() call, ahead of the first launch).  Catches in-place updates (optimizer, load_state_dict,
+    EMA copies), ``.to()`` moves and replaced parameters / sub-modules alike."""
+    out, stack = [], [module]
+    while stack:
+        m = stack.pop()
+        for t in m._parameters.values():
+            if t is not None:
+                out.append(t._version)
+                out.append(t.data_ptr())
+        for c in m._modules.values():
+            if c is not None:
+                stack.append(c)
+    return tuple(out)
+
+
 def _p(t):
     return None if t is None else t.data_ptr()
 

@@ -253,7 +253,7 @@ class UNetCondition2D(nn.Module):
                 yield from blk.attentions
 
     def _version(self):
-        return tuple(p._version for p in self.parameters()) + tuple(p.data_ptr() for p in self.parameters())
+        return E.params_version(self)
 
     def packed(self, ctx: E.Ctx):
         key = (ctx.precision, str(ctx.device))
