@@ -34,7 +34,7 @@ class GemmDesc(C.Structure):
                 ("act_post", c_i32), ("res_ld", c_i32), ("res_mod", c_i32), ("res_dtype", c_i32),
                 ("out_ld", c_i32), ("out_dtype", c_i32), ("mse_div", c_i32), ("mse_ld", c_i32), ("up_phase", c_i32),
                 ("xf_silu", c_i32), ("xf_a", c_void_p), ("xf_b", c_void_p), ("xf_src1", c_void_p), ("xf_c1", c_i32),
-                ("xf_div1", c_i32)]
+                ("xf_div1", c_i32), ("attn_norms", c_void_p), ("attn_heads", c_i32), ("attn_tok", c_i32)]
 
 
 _PROTOS = {
@@ -94,6 +94,7 @@ _lib = None
 
 # DCB_KNOB_* of include/dcb200.h.  The environment variables of the same name (DCB_NO_TC2=1 ...) are read ONCE, when the
 # library is loaded; tests switch at run time with ``knob()``.
+ATTN_NORMS_READY = 0x200   # dcb_attention_ws dtype flag (include/dcb200.h)
 KNOBS = {"NO_TC2": 1, "TC2_NO_HALO": 2, "TC2_NO_YHALO": 4, "NO_TC2_MSE": 8, "TC2_WIDE": 16, "TC_DIRECT_EPILOGUE": 32,
          "ATTN_NO_TC": 64, "ATTN_NO_FAST": 128, "NO_TC3": 256, "TC2X_NO_PAIR": 512}
 

@@ -83,8 +83,19 @@ static int to_dev(const dcb_gemm_desc* d, GemmDev* g) {
   DCB_REQUIRE((e.rowvec == nullptr && e.gate == nullptr) || e.rows_per_group > 0, "gemm: rows_per_group needed");
   DCB_REQUIRE(e.mse_part == nullptr || e.mse_target != nullptr, "gemm: mse_part without mse_target");
   DCB_REQUIRE(d->act != DCB_ACT_GEGLU || d->N % 256 == 0, "gemm: GEGLU needs N %% 256 == 0");
+  e.attn_norms = d->attn_norms; e.attn_heads = d->attn_heads; e.attn_tok = d->attn_tok;
+  if (d->attn_norms != nullptr) {
+    DCB_REQUIRE(d->dtype == DCB_BF16 && d->out_dtype == DCB_BF16 && e.out != nullptr && d->act == DCB_ACT_NONE &&
+                    d->act_post == DCB_ACT_NONE && d->up_phase == 0,
+                "gemm: attn_norms needs a plain bf16 projection");
+    DCB_REQUIRE(d->attn_heads >= 1 && d->N >= 2 * d->attn_heads * 64 && d->attn_tok >= 128 && d->attn_tok % 128 == 0 &&
+                    e.M % d->attn_tok == 0 && d->out_ld % 8 == 0 && ((uintptr_t)d->out & 15) == 0,
+                "gemm: attn_norms needs N >= 2 * heads * 64, attn_tok %% 128 == 0, rows %% attn_tok == 0, 16-byte rows");
+  }
   return DCB_OK;
 }
+
+thread_local bool g_attn_norms_written = false;
 
 static int pick_engine(const dcb_gemm_desc* d) {
   if (d->engine == DCB_ENGINE_SIMT || d->engine == DCB_ENGINE_TCGEN05) return d->engine;
@@ -95,7 +106,7 @@ static int pick_engine(const dcb_gemm_desc* d) {
 
 using namespace dcb;
 
-extern "C" int dcb_version(void) { return 110; }
+extern "C" int dcb_version(void) { return 111; }
 extern "C" const char* dcb_last_error(void) { return g_err; }
 extern "C" int64_t dcb_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 extern "C" void dcb_note_graph_replay(int64_t n_kernels) { g_launches.fetch_add(n_kernels, std::memory_order_relaxed); }
@@ -110,8 +121,17 @@ extern "C" int dcb_gemm(const dcb_gemm_desc* d, dcb_stream stream) {
   int rc = to_dev(d, &g);
   if (rc) return rc;
   const int eng = pick_engine(d);
-  if (eng == DCB_ENGINE_TCGEN05) return launch_gemm_tc(g, (cudaStream_t)stream);
-  return launch_gemm_simt(g, (cudaStream_t)stream);
+  cudaStream_t st = (cudaStream_t)stream;
+  const EpiDev& e = g.epi;
+  if (e.attn_norms != nullptr) {
+    cudaMemsetAsync(e.attn_norms, 0, sizeof(float) * (2 + 2 * (size_t)(e.M / e.attn_tok) * e.attn_heads), st);
+    g_attn_norms_written = false;
+  }
+  rc = eng == DCB_ENGINE_TCGEN05 ? launch_gemm_tc(g, st) : launch_gemm_simt(g, st);
+  if (rc == DCB_OK && e.attn_norms != nullptr && !g_attn_norms_written)   // this launch's kernel has no norm epilogue
+    rc = launch_attn_norms(e.out, (const __nv_bfloat16*)e.out + e.attn_heads * 64, e.out_ld, e.attn_tok, e.M / e.attn_tok,
+                           e.attn_heads, e.attn_norms, st);
+  return rc;
 }
 
 extern "C" int dcb_gemm_gn_layout(const dcb_gemm_desc* d, int32_t* supported) {

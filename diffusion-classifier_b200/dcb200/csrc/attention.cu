@@ -271,7 +271,7 @@ static int launch_simt(const void* q, const void* k, const void* v, int ld, int 
 }
 
 int launch_flash_tc(const void* q, const void* k, const void* v, int ld, int B, int N, int heads, int d, float scale,
-                    void* out, int out_ld, float* norms_ws, cudaStream_t st);
+                    void* out, int out_ld, float* norms_ws, bool norms_ready, cudaStream_t st);
 
 }  // namespace dcb
 
@@ -281,6 +281,9 @@ using namespace dcb;
 extern "C" int dcb_attention_ws(int dtype, const void* q, const void* k, const void* v, int ld, int B, int Ntok, int heads,
                                 int d, float scale, void* out, int out_ld, float* ws, dcb_stream stream) {
   cudaStream_t st = (cudaStream_t)stream;
+  const bool norms_ready = (dtype & DCB_ATTN_NORMS_READY) != 0;
+  dtype &= ~DCB_ATTN_NORMS_READY;
+  DCB_REQUIRE(!norms_ready || (ws != nullptr && dtype == DCB_BF16 && d == 64), "attention: NORMS_READY needs bf16, d = 64, a workspace");
   DCB_REQUIRE(B >= 1 && B <= 65535 && heads >= 1 && Ntok >= 1, "attention: bad sizes");
   DCB_REQUIRE(d == 32 || d == 64 || d == 96 || d == 128, "attention: head dim %d not in {32,64,96,128}", d);
 #define DCB_ATTN_DISPATCH(FN, ...)                                         \
@@ -297,7 +300,7 @@ extern "C" int dcb_attention_ws(int dtype, const void* q, const void* k, const v
     // the sequences shorter than one 128-key block (the 8^2 levels)
     const bool tc_on = !(knobs() & DCB_KNOB_ATTN_NO_TC);
     if (Ntok >= 128 && tc_on && out_ld % 8 == 0 && ((uintptr_t)out & 15) == 0)
-      return launch_flash_tc(q, k, v, ld, B, Ntok, heads, d, scale, out, out_ld, ws, st);
+      return launch_flash_tc(q, k, v, ld, B, Ntok, heads, d, scale, out, out_ld, ws, norms_ready, st);
     DCB_ATTN_DISPATCH(launch_flash, )
   } else if (dtype == DCB_F32) {
     DCB_ATTN_DISPATCH(launch_simt, float, )

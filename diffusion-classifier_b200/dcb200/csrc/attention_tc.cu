@@ -143,12 +143,13 @@ __device__ __forceinline__ void ex2_poly2(float x0, float x1, float& p0, float& 
 // the single-pass kernel is exact iff nothing underflows: max|q| max|k| c <= 50 bounds every (M_i - s_ij) c by 100 < 126
 // Decided per (batch, head) -- blockIdx.z, blockIdx.y -- from that head's own max|q|^2, max|k|^2, so which of the two kernels
 // scores a sample never depends on the other samples of the launch (results stay independent of the batch composition).
-__device__ __forceinline__ bool at_fast_ok(const float* norms, float sc) {
-  const float* n = norms + 2 + ((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * 2;
+__device__ __forceinline__ bool at_fast_ok(const float* norms, float sc, int b, int h) {
+  const float* n = norms + 2 + ((int64_t)b * gridDim.y + h) * 2;
   return sqrtf(n[0] * n[1]) * sc <= 50.f;
 }
 
 struct AtParams {
+  int B;              // samples (the running-maximum kernel strides over them when it is only the fallback)
   int N, nblk;        // tokens per (batch, head); ceil(N / 128)
   float sc;           // softmax scale * log2(e)
   int out_ld;
@@ -198,17 +199,41 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
   uint64_t* o_full = p_full + 2;                 // [2]  MMA -> softmax: O_t(j) = P_t(j) V_j complete
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
 
-  // when the single-pass kernel can take this (batch, head), this one has nothing to do for it
-  if (p.norms != nullptr && at_fast_ok(p.norms, p.sc)) return;
+  // A CTA serves samples blockIdx.z, blockIdx.z + gridDim.z, ...  Without a norm workspace gridDim.z == B (one sample).
+  // With one this kernel is only the FALLBACK of the single-pass kernel -- for every (batch, head) that one can take, this
+  // one has nothing to do -- and is launched with a few CTAs per (query tile, head) that stride over the samples: when
+  // nothing falls back (the normal case) the launch costs 8 instead of B CTA start-ups per (tile, head) (1.1 % of the
+  // DiT-B/4 step at B = 250), and when everything does, there are still >= 148 CTAs.
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
-  const int h = blockIdx.y, b = blockIdx.z;
+  const int h = blockIdx.y;
   const int q0 = blockIdx.x * 256;
-
+  {
+    bool any = p.norms == nullptr;
+    for (int bb = blockIdx.z; bb < p.B && !any; bb += gridDim.z) any = !at_fast_ok(p.norms, p.sc, bb, h);
+    if (!any) return;
+  }
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&mapQ);
     prefetch_tmap(&mapK);
     prefetch_tmap(&mapV);
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  const uint32_t k_full0 = smem_u32(k_full), k_empty0 = smem_u32(k_empty), v_full0 = smem_u32(v_full),
+                 v_empty0 = smem_u32(v_empty);
+  const uint32_t s_full0 = smem_u32(s_full), p_full0 = smem_u32(p_full), o_full0 = smem_u32(o_full);
+  bool first = true;
+  uint32_t tmem_base = 0;
+  for (int b = blockIdx.z; b < p.B; b += gridDim.z) {
+  if (p.norms != nullptr && at_fast_ok(p.norms, p.sc, b, h)) continue;     // CTA-uniform
+  if (warp == 0 && lane == 0) {
+    constexpr int NBARS = 1 + 4 * STAGES + 6;
+    if (!first)
+      for (int i = 0; i < NBARS; ++i) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(bars + i)) : "memory");
     mbar_init(smem_u32(q_full), 1);
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(smem_u32(&k_full[i]), 1);
@@ -223,18 +248,11 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
+  first = false;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t k_full0 = smem_u32(k_full), k_empty0 = smem_u32(k_empty), v_full0 = smem_u32(v_full),
-                 v_empty0 = smem_u32(v_empty);
-  const uint32_t s_full0 = smem_u32(s_full), p_full0 = smem_u32(p_full), o_full0 = smem_u32(o_full);
+  tmem_base = *tmem_slot;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -441,7 +459,8 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
   }
 
   tc_fence_before();
-  __syncthreads();
+  __syncthreads();      // every role is done with this sample: the barriers may be re-initialised
+  }  // samples of this CTA
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
@@ -466,7 +485,7 @@ __global__ void __launch_bounds__(ATF_THREADS, 1)
 flash_attn_tc_fast_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                           const __grid_constant__ CUtensorMap mapV, const __grid_constant__ AtParams p,
                           __nv_bfloat16* __restrict__ out) {
-  if (!at_fast_ok(p.norms, p.sc)) return;
+  if (!at_fast_ok(p.norms, p.sc, blockIdx.z, blockIdx.y)) return;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* q_s = smem;                                    // 2 tiles
@@ -831,9 +850,20 @@ static int encode_tok_map(CUtensorMap* map, const void* base, int ld, int N, int
 // head dim D, bf16, N >= 128; q/k/v: [B, N, heads, D] views with row stride ld.
 // norms_ws: [2 + B*heads*2] fp32 workspace or NULL.  With it (D = 64 and enough key blocks for the norm pre-pass to pay)
 // the single-pass kernel is enqueued ahead of the running-maximum kernel and the device decides which of the two runs.
+int launch_attn_norms(const void* q, const void* k, int ld, int N, int B, int heads, float* norms, cudaStream_t st) {
+  if (heads <= 16)
+    attn_norms_rows_kernel<<<dim3((N + 63) / 64, 2, B), 256, 0, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k, ld, N,
+                                                                       heads, norms);
+  else
+    attn_norms_kernel<<<dim3((N + 255) / 256, heads, B), 256, 0, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k, ld, N,
+                                                                        norms);
+  DCB_CHECK_LAUNCH("attn_norms");
+  return DCB_OK;
+}
+
 template <int D>
 static int launch_flash_tc_d(const void* q, const void* k, const void* v, int ld, int B, int N, int heads, float scale,
-                             void* out, int out_ld, float* norms_ws, cudaStream_t st) {
+                             void* out, int out_ld, float* norms_ws, bool norms_ready, cudaStream_t st) {
   DCB_REQUIRE(out_ld % 8 == 0 && ((uintptr_t)out & 15) == 0, "attention: out rows must be 16-byte aligned");
   CUtensorMap mq, mk, mv;
   int rc;
@@ -841,6 +871,7 @@ static int launch_flash_tc_d(const void* q, const void* k, const void* v, int ld
   if ((rc = encode_tok_map(&mk, k, ld, N, B, heads * D))) return rc;
   if ((rc = encode_tok_map(&mv, v, ld, N, B, heads * D))) return rc;
   AtParams p;
+  p.B = B;
   p.N = N;
   p.nblk = (N + 127) / 128;
   p.sc = scale * 1.4426950408889634f;
@@ -856,29 +887,27 @@ static int launch_flash_tc_d(const void* q, const void* k, const void* v, int ld
   });
   dim3 grid((N + 255) / 256, heads, B);
   if (use_fast) {
-    cudaMemsetAsync(norms_ws, 0, sizeof(float) * (2 + 2 * B * heads), st);
-    if (heads <= 16)
-      attn_norms_rows_kernel<<<dim3((N + 63) / 64, 2, B), 256, 0, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k, ld, N,
-                                                                         heads, norms_ws);
-    else
-      attn_norms_kernel<<<dim3((N + 255) / 256, heads, B), 256, 0, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k, ld, N,
-                                                                          norms_ws);
-    DCB_CHECK_LAUNCH("attn_norms");
+    if (!norms_ready) {   // otherwise the projection that wrote q and k left them (dcb_gemm_desc.attn_norms)
+      cudaMemsetAsync(norms_ws, 0, sizeof(float) * (2 + 2 * B * heads), st);
+      int rcn = launch_attn_norms(q, k, ld, N, B, heads, norms_ws, st);
+      if (rcn) return rcn;
+    }
     flash_attn_tc_fast_kernel<<<grid, ATF_THREADS, smem, st>>>(mq, mk, mv, p, (__nv_bfloat16*)out);
     DCB_CHECK_LAUNCH("flash_attn_tc_fast");
   }
-  flash_attn_tc_kernel<D><<<grid, AT_THREADS, smem, st>>>(mq, mk, mv, p, (__nv_bfloat16*)out);
+  const dim3 grid_rm((N + 255) / 256, heads, use_fast ? (B < 8 ? B : 8) : B);   // as the fallback: strided over samples
+  flash_attn_tc_kernel<D><<<grid_rm, AT_THREADS, smem, st>>>(mq, mk, mv, p, (__nv_bfloat16*)out);
   DCB_CHECK_LAUNCH("flash_attn_tc");
   return DCB_OK;
 }
 
 int launch_flash_tc(const void* q, const void* k, const void* v, int ld, int B, int N, int heads, int d, float scale,
-                    void* out, int out_ld, float* norms_ws, cudaStream_t st) {
+                    void* out, int out_ld, float* norms_ws, bool norms_ready, cudaStream_t st) {
   switch (d) {
-    case 32: return launch_flash_tc_d<32>(q, k, v, ld, B, N, heads, scale, out, out_ld, norms_ws, st);
-    case 64: return launch_flash_tc_d<64>(q, k, v, ld, B, N, heads, scale, out, out_ld, norms_ws, st);
-    case 96: return launch_flash_tc_d<96>(q, k, v, ld, B, N, heads, scale, out, out_ld, norms_ws, st);
-    case 128: return launch_flash_tc_d<128>(q, k, v, ld, B, N, heads, scale, out, out_ld, norms_ws, st);
+    case 32: return launch_flash_tc_d<32>(q, k, v, ld, B, N, heads, scale, out, out_ld, norms_ws, norms_ready, st);
+    case 64: return launch_flash_tc_d<64>(q, k, v, ld, B, N, heads, scale, out, out_ld, norms_ws, norms_ready, st);
+    case 96: return launch_flash_tc_d<96>(q, k, v, ld, B, N, heads, scale, out, out_ld, norms_ws, norms_ready, st);
+    case 128: return launch_flash_tc_d<128>(q, k, v, ld, B, N, heads, scale, out, out_ld, norms_ws, norms_ready, st);
   }
   set_error("attention: head dim %d not in {32,64,96,128}", d);
   return DCB_EINVAL;

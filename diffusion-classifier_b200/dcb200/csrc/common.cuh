@@ -182,6 +182,8 @@ struct EpiDev {
   int mse_div, mse_ld;
   int up_phase;         // 0 or 1 + 2a + b (sub-pixel phase of a folded 2x upsample; see dcb200.h)
   int OH, OW;           // output grid of THIS launch (the low-resolution grid when up_phase != 0)
+  float* attn_norms;    // dcb_gemm_desc.attn_norms: per (sample, head) max |q|^2, max |k|^2 of the written rows, or null
+  int attn_heads, attn_tok;
 };
 
 struct GemmDev {
@@ -223,6 +225,9 @@ __device__ __forceinline__ float epi_scalar(const EpiDev& e, int m, int n, float
 // host entry points of the engines (gemm_simt.cu / gemm_tc.cu)
 int launch_gemm_simt(const GemmDev& g, cudaStream_t st);
 int launch_gemm_tc(const GemmDev& g, cudaStream_t st, bool dry_run = false);
+// set by a launch whose epilogue filled EpiDev::attn_norms itself (dcb_gemm runs the row pass otherwise)
+extern thread_local bool g_attn_norms_written;
+int launch_attn_norms(const void* q, const void* k, int ld, int N, int B, int heads, float* norms, cudaStream_t st);
 int tc_geometry(const GemmDev& g, int* m_tiles, int* n_tiles, int* BN);
 bool tc_staged(const GemmDev& g);
 

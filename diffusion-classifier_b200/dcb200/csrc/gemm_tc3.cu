@@ -207,6 +207,7 @@ int launch_gemm_tc3(const GemmDev& g, cudaStream_t st, int uniform) {
   if (p.ngroups == 4) gemm_tc3_kernel<4><<<grid, 64 + 128 * 4, smem, st>>>(mapA, mapB, p, e);
   else gemm_tc3_kernel<2><<<grid, 64 + 128 * 2, smem, st>>>(mapA, mapB, p, e);
   DCB_CHECK_LAUNCH("gemm_tc3");
+  if (g.epi.attn_norms != nullptr) g_attn_norms_written = true;   // staged_epilogue_half filled them
   return DCB_OK;
 }
 

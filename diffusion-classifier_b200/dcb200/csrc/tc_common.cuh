@@ -690,6 +690,7 @@ __device__ __forceinline__ void staged_epilogue_half(const EpiGeom& gq, const Ep
       asm volatile("cp.async.wait_group 0;" ::: "memory");
       epi_bar(bar_id);
     }
+    float ss = 0.f;     // |row|^2 over this 64-column half: one attention head of q or k (EpiDev::attn_norms)
     auto process = [&](int c, const uint32_t (&ra)[16]) {     // c: column inside this half
       float v[16], bz[16];
       lds16f(smem_u32(s_bias + h0 + c), bz);
@@ -733,6 +734,10 @@ __device__ __forceinline__ void staged_epilogue_half(const EpiGeom& gq, const Ep
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = apply_act_fast(e.act_post, v[i]);
       }
+      if (e.attn_norms != nullptr) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) ss = fmaf(v[i], v[i], ss);
+      }
       *s0 = pack_bf16x8(v);
       *s1 = pack_bf16x8(v + 8);
     };
@@ -758,6 +763,21 @@ __device__ __forceinline__ void staged_epilogue_half(const EpiGeom& gq, const Ep
       if (lane == 0) {
         if (release_cta < 0) mbar_arrive(empty_bar);
         else mbar_arrive_cluster(empty_bar, (uint32_t)release_cta);    // CTA pair: the MMA warp lives in the leader CTA
+      }
+    }
+    if (e.attn_norms != nullptr && ocol0 + h0 < 2 * e.attn_heads * 64) {
+      // the 64 columns of this half are one head of q (columns below heads * 64) or k: max over the warp's 32 rows of
+      // |row|^2, then one atomic per warp.  attn_tok % 128 == 0: the tile's rows belong to one sample.  Non-negative
+      // floats order like their bit patterns, so an integer max does the reduction (attention_tc.cu reads it back).
+      float mx = row_ok ? ss : 0.f;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      const int m_any = __shfl_sync(0xffffffffu, m, 0);
+      if (lane == 0) {
+        const int col = ocol0 + h0, which = col >= e.attn_heads * 64 ? 1 : 0;
+        const int head = (col >> 6) - which * e.attn_heads;
+        atomicMax(reinterpret_cast<int*>(e.attn_norms) + 2 + ((m_any / e.attn_tok) * e.attn_heads + head) * 2 + which,
+                  __float_as_int(mx));
       }
     }
     epi_bar(bar_id);

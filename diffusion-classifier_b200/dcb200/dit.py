@@ -18,6 +18,7 @@ from .unet import _P, _Attn, _TimeEmb
 
 
 LOG2E = 1.4426950408889634
+FOLD_NORMS = __import__("os").environ.get("DCB_FOLD_NORMS", "1") != "0"   # A/B switch: attention norm pre-pass in the QKV epilogue
 
 
 def _sincos_1d(dim, pos):
@@ -203,8 +204,12 @@ class DiT(nn.Module):
                 sc0 = sc
             mod = E.linear(ctx, sc, q.mod_w, 6 * D, bias=q.mod_b, out_dtype=torch.float32)
             n = E.layernorm(ctx, h, None, None, 1e-6, scale=mod[:, D:], shift=mod, mod_ld=6 * D, rows_per_group=N)
-            qkv = E.linear(ctx, n, q.qkv_w, 3 * D, bias=q.qkv_b)
-            att = E.attention(ctx, qkv, S, N, heads, hd, scale=(1.0 / LOG2E) if self._fold_qscale(ctx) else None)
+            # the projection's epilogue leaves the per-head max |q|^2, max |k|^2 the single-pass attention kernel needs
+            nws = E.attn_norms_ws(ctx, S, heads) if (FOLD_NORMS and ctx.precision == "bf16" and hd == 64 and N % 128 == 0
+                                                     and N >= 1024) else None
+            qkv = E.linear(ctx, n, q.qkv_w, 3 * D, bias=q.qkv_b, attn_norms=None if nws is None else (nws, heads, N))
+            att = E.attention(ctx, qkv, S, N, heads, hd, scale=(1.0 / LOG2E) if self._fold_qscale(ctx) else None,
+                              norms_ready=nws)
             h = E.linear(ctx, att, q.o_w, D, bias=q.o_b, gate=mod[:, 2 * D:], gate_ld=6 * D, rows_per_group=N,
                          residual=h, res_ld=D)
             n = E.layernorm(ctx, h, None, None, cfg.norm_eps, scale=mod[:, 4 * D:], shift=mod[:, 3 * D:], mod_ld=6 * D,

@@ -116,7 +116,7 @@ def conv3x3_segs(src, C_, H, W, stride=1, nb_div=1):
 def gemm(ctx: Ctx, segs, W, N, NB, OH, OW, *, bias=None, rowvec=None, rowvec_ld=0, rowvec_idx=None, rows_per_group=0,
          gate=None, gate_ld=0, residual=None, res_ld=0, res_mod=0, res_idx=None, act=L.ACT_NONE, act_post=L.ACT_NONE,
          out=None, out_dtype=None, out_ld=None, mse=None, want_out=True, k_alg=None, gn_stats=False, up_phase=0,
-         gn_part=None, xf=None):
+         gn_part=None, xf=None, attn_norms=None):
     """D = sum_seg A_seg . W^T with the fused epilogue; returns the [M, n_out] output (or None if want_out=False).
 
     mse = dict(target=, scale=, div=, ld=, err=[S] fp32 out) enables the fused eps-MSE epilogue (tcgen05 only).
@@ -128,6 +128,8 @@ def gemm(ctx: Ctx, segs, W, N, NB, OH, OW, *, bias=None, rowvec=None, rowvec_ld=
     xf = dict(a=, b=, src1=, c1=, div1=, silu=, prepare=): segments 0..8 name the RAW input of a GroupNorm(+SiLU) and the
     kernel normalises the operand on the fly (dcb_gemm_desc.xf_a).  Returns ``XF_UNSUPPORTED`` -- before anything is
     launched -- when this launch cannot do that; otherwise calls ``xf['prepare']()`` (fills the coefficient tables) first.
+    attn_norms = (ws, heads, tokens): this projection writes q and k of an attention layer (head dim 64); the launch also
+    leaves max |q_i|^2, max |k_j|^2 per (sample, head) in ``ws`` (dcb_gemm_desc.attn_norms) for ``attention(norms_ready=ws)``.
     """
     lib = L.lib()
     d = L.GemmDesc()
@@ -149,6 +151,8 @@ def gemm(ctx: Ctx, segs, W, N, NB, OH, OW, *, bias=None, rowvec=None, rowvec_ld=
     d.res_dtype = L.F32 if (residual is not None and residual.dtype == torch.float32) else L.BF16
     d.act, d.act_post = act, act_post
     d.up_phase = up_phase
+    if attn_norms is not None:
+        d.attn_norms, d.attn_heads, d.attn_tok = attn_norms[0].data_ptr(), attn_norms[1], attn_norms[2]
     assert up_phase == 0 or out is not None
     if xf is not None:
         d.xf_a, d.xf_b, d.xf_silu = xf["a"].data_ptr(), xf["b"].data_ptr(), int(xf["silu"])
@@ -342,9 +346,16 @@ def layernorm(ctx, x, gamma=None, beta=None, eps=1e-5, scale=None, shift=None, m
     return out
 
 
-def attention(ctx, qkv, B, Ntok, heads, d, q_off=0, k_off=None, v_off=None, simt=False, scale=None):
+def attn_norms_ws(ctx, B, heads):
+    """workspace of the attention pre-pass: [2 + 2 B heads] fp32 (max |q|^2, max |k|^2 per (sample, head))"""
+    return torch.empty(2 + B * heads * 2, device=ctx.device, dtype=torch.float32)
+
+
+def attention(ctx, qkv, B, Ntok, heads, d, q_off=0, k_off=None, v_off=None, simt=False, scale=None, norms_ready=None):
     """qkv: [B*Ntok, ld] with q/k/v column blocks of width heads*d starting at q_off/k_off/v_off.
-    scale: softmax scale (default d^-0.5); a caller that folded d^-0.5 log2(e) into its query projection passes 1 / log2(e)."""
+    scale: softmax scale (default d^-0.5); a caller that folded d^-0.5 log2(e) into its query projection passes 1 / log2(e).
+    norms_ready: the ``attn_norms_ws`` buffer the projection that wrote ``qkv`` filled (``gemm(attn_norms=)``): the
+    launch skips its own pass over q and k."""
     Cw = heads * d
     ld = qkv.shape[1]
     k_off = Cw if k_off is None else k_off
@@ -353,8 +364,10 @@ def attention(ctx, qkv, B, Ntok, heads, d, q_off=0, k_off=None, v_off=None, simt
     base = qkv.data_ptr()
     out = torch.empty(B * Ntok, Cw, device=ctx.device, dtype=qkv.dtype)
     code = ctx.code | (0x100 if (simt and ctx.code == L.BF16) else 0)
-    ws = torch.empty(2 + B * heads * 2, device=ctx.device, dtype=torch.float32) if code == L.BF16 and d == 64 else None
-    prof = PROFILE if (PROFILE is not None and code == L.BF16 and Ntok >= 128) else None
+    ws = attn_norms_ws(ctx, B, heads) if code == L.BF16 and d == 64 else None
+    if norms_ready is not None and code == L.BF16 and d == 64:
+        ws, code = norms_ready, code | L.ATTN_NORMS_READY
+    prof = PROFILE if (PROFILE is not None and (code & 0xFF) == L.BF16 and not simt and Ntok >= 128) else None
     if prof is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()

@@ -136,6 +136,15 @@ typedef struct dcb_gemm_desc {
   const float* xf_b;
   const void* xf_src1;
   int32_t xf_c1, xf_div1;
+  /* attention pre-pass folded into the projection that PRODUCES q and k (a bf16 linear over [rows, >= 2*attn_heads*64]
+   * output columns, q heads first, then k heads, head dim 64): when attn_norms != NULL the call also leaves
+   * max_i |q_i|^2 and max_j |k_j|^2 per (sample, head) in attn_norms[2 + (sample * attn_heads + head) * 2 + {0, 1}]
+   * (fp32 [2 + 2 * samples * attn_heads]; sample = row / attn_tok; the buffer is zeroed by this call), computed from the
+   * epilogue's own registers where the launch runs on the CTA-pair kernel and by a pass over the written rows otherwise.
+   * Hand the buffer to dcb_attention_ws with DCB_ATTN_NORMS_READY or-ed into dtype: that launch then skips its own
+   * pre-pass over q and k (1.7 % of the DiT-B/4 step). */
+  float* attn_norms;
+  int32_t attn_heads, attn_tok;
 } dcb_gemm_desc;
 
 int dcb_gemm(const dcb_gemm_desc* d, dcb_stream stream);
@@ -192,8 +201,10 @@ int dcb_layernorm(int dtype, const void* x, int64_t rows, int C, const float* ga
  * q/k/v: [B, Ntok, heads, d] views with row stride ld (elements); out [B, Ntok, heads*d] row stride out_ld */
 int dcb_attention(int dtype, const void* q, const void* k, const void* v, int ld, int B, int Ntok, int heads, int d,
                   float scale, void* out, int out_ld, dcb_stream stream);
-/* same with a [2 + B*heads*2] fp32 workspace: lets the tcgen05 kernel (d = 64) take its single-pass path, which uses
- * max|q| max|k| per (batch, head) as the softmax reference instead of a running maximum (exact; falls back by itself) */
+/* same with a [2 + B*heads*2] fp32 workspace: lets the tcgen05 kernel (d = 64) take its single-pass path, which bounds
+ * every score by max|q| max|k| per (batch, head) and so needs no running maximum (exact; falls back by itself).
+ * dtype | DCB_ATTN_NORMS_READY: the workspace already holds this launch's maxima (dcb_gemm_desc.attn_norms). */
+#define DCB_ATTN_NORMS_READY 0x200
 int dcb_attention_ws(int dtype, const void* q, const void* k, const void* v, int ld, int B, int Ntok, int heads, int d,
                      float scale, void* out, int out_ld, float* ws, dcb_stream stream);
 

@@ -244,10 +244,10 @@ def test_c_abi_exports_every_declared_symbol():
     lib = _lib.lib()  # dlopen + bind every prototype (no compute without a GPU)
     for name in declared:
         assert hasattr(lib, name)
-    assert lib.dcb_version() == 110 and lib.dcb_launch_count() == 0
+    assert lib.dcb_version() == 111 and lib.dcb_launch_count() == 0
     import ctypes
     assert ctypes.sizeof(_lib.Seg) == 48 == lib.dcb_struct_size(0)
-    assert ctypes.sizeof(_lib.GemmDesc) == 792 == lib.dcb_struct_size(1)
+    assert ctypes.sizeof(_lib.GemmDesc) == 808 == lib.dcb_struct_size(1)
 
 
 def test_product_has_no_cpu_path():

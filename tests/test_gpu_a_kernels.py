@@ -276,6 +276,31 @@ def test_attention_tcgen05_head64(dev, B, heads, N, qscale):
     assert rel_err(out, simt) < 1e-2
 
 
+@pytest.mark.parametrize("B,heads,N", [(5, 12, 1024), (1, 4, 1024), (2, 12, 4096)])
+def test_attention_norm_prepass_folded_into_the_qkv_projection(dev, B, heads, N):
+    """dcb_gemm_desc.attn_norms: the projection that writes q and k leaves max |q_i|^2 / max |k_j|^2 per (sample, head) --
+    from the CTA-pair kernel's epilogue registers (first and last case: >= 148 tiles) or from the row pass the library
+    runs by itself for every other kernel (middle case) -- and dcb_attention_ws(NORMS_READY) gives bit for bit the result
+    of the launch that computes them itself."""
+    from dcb200 import engine as E
+    torch.manual_seed(B * N)
+    ctx = _ctx(dev, "bf16")
+    D = heads * 64
+    x = torch.randn(B * N, D, device=dev).to(torch.bfloat16)
+    w = (torch.randn(3 * D, D, device=dev) * D ** -0.5).to(torch.bfloat16)
+    b = torch.randn(3 * D, device=dev)
+    ws = E.attn_norms_ws(ctx, B, heads)
+    ws.fill_(7.0)                                   # the call zeroes it
+    qkv = E.linear(ctx, x, w, 3 * D, bias=b, attn_norms=(ws, heads, N))
+    assert torch.equal(qkv, E.linear(ctx, x, w, 3 * D, bias=b))
+    qk = qkv[:, : 2 * D].float().reshape(B, N, 2, heads, 64)
+    want = qk.pow(2).sum(-1).amax(1).permute(0, 2, 1)            # [B, heads, {q, k}]
+    got = ws[2:].reshape(B, heads, 2)
+    assert torch.allclose(got, want, rtol=1e-2), (got - want).abs().max()
+    a = E.attention(ctx, qkv, B, N, heads, 64, norms_ready=ws)
+    assert torch.equal(a, E.attention(ctx, qkv, B, N, heads, 64))
+
+
 @pytest.mark.parametrize("d", [32, 96, 128])
 @pytest.mark.parametrize("B,heads,N,qscale", [(2, 3, 128, 3.0), (2, 5, 300, 3.0), (1, 4, 1024, 3.0), (1, 2, 4096, 1.0),
                                                (3, 1, 1000, 6.0), (1, 2, 512, 0.0)])
@@ -347,6 +372,27 @@ def test_attention_tcgen05_fast_path_decided_per_head(dev):
     alone0 = E.attention(_ctx(dev, "bf16"), qb[:N].contiguous(), 1, N, heads, d)
     alone2 = E.attention(_ctx(dev, "bf16"), qb[2 * N:].contiguous(), 1, N, heads, d)
     assert torch.equal(out[:N], alone0) and torch.equal(out[2 * N:], alone2)
+
+
+def test_attention_fallback_kernel_strides_over_samples(dev):
+    """as the fallback of the single-pass kernel the running-maximum kernel is launched with 8 CTAs per (query tile, head)
+    that stride over the samples and re-initialise their barriers per sample: with 20 samples, three of which (3, 11, 19 --
+    the same CTA) and one more (6) have logits beyond the single-pass bound in some heads, every sample still equals its
+    own single-sample launch bit for bit and torch SDPA within tolerance."""
+    from dcb200 import engine as E
+    torch.manual_seed(1)
+    B, heads, N, d = 20, 2, 1024, 64
+    qkv = torch.randn(B * N, 3 * heads * d, device=dev)
+    for smp, hd in ((3, 0), (11, 1), (19, 0), (19, 1), (6, 1)):
+        qkv[smp * N:(smp + 1) * N, hd * d:(hd + 1) * d] *= 14.0
+    qb = qkv.to(torch.bfloat16)
+    q, k, v = (t.float().reshape(B, N, heads, d).transpose(1, 2) for t in qb.chunk(3, -1))
+    ref = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B * N, heads * d)
+    out = E.attention(_ctx(dev, "bf16"), qb, B, N, heads, d)
+    assert torch.isfinite(out).all() and rel_err(out.float(), ref) < 1e-2
+    for smp in (0, 3, 6, 11, 19):
+        alone = E.attention(_ctx(dev, "bf16"), qb[smp * N:(smp + 1) * N].contiguous(), 1, N, heads, d)
+        assert torch.equal(out[smp * N:(smp + 1) * N], alone), smp
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
