@@ -190,7 +190,14 @@ int launch_gemm_tc3(const GemmDev& g, cudaStream_t st, int uniform) {
   int rc;
   if ((rc = encode_2d(&mapA, s.src, M, s.C, s.C, 128))) return rc;
   if ((rc = encode_2d(&mapB, g.W, e.N, g.K, g.K, 128))) return rc;
-  p.ngroups = (e.act != DCB_ACT_NONE && g.K <= 1024) ? 4 : 2;
+#ifndef DCB_TC3_RULE
+#define DCB_TC3_RULE 2
+#endif
+  // four 64-column epilogue groups (each issues its residual prefetch BEFORE it waits for the accumulator, and none has a
+  // second half whose prefetch would be exposed) when the main loop is short and the epilogue is not a plain store
+  const bool heavy = e.act != DCB_ACT_NONE || (DCB_TC3_RULE >= 1 && (e.residual != nullptr || e.gate != nullptr)) ||
+                     (DCB_TC3_RULE >= 2 && e.attn_norms != nullptr);
+  p.ngroups = (heavy && g.K <= 1024) ? 4 : 2;
   int stages = (TC_SMEM_LIMIT - 1024 - 512 - p.ngroups * TC_EPI_HALF_BYTES) / T3_STAGE_BYTES;
   if (stages > T3_MAX_STAGES) stages = T3_MAX_STAGES;
   if (stages > p.nkb) stages = p.nkb < 2 ? 2 : p.nkb;

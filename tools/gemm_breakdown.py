@@ -14,7 +14,7 @@ if len(sys.argv) > 3:
     cfg.dcb_max_batch = int(sys.argv[3])
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
-dc = dcb200.DiffusionClassifier(dcb200.UNetCondition2D(**arch), cfg).to(dev).eval()
+dc = dcb200.DiffusionClassifier((dcb200.DiT if wl == "dit" else dcb200.UNetCondition2D)(**arch), cfg).to(dev).eval()
 S, C = arch["sample_size"], arch["in_channels"]
 x = (torch.rand(images, C, S, S) * 2 - 1).to(dev)
 for _ in range(2):
