@@ -81,30 +81,6 @@ __device__ __forceinline__ float ex2f(float x) {
   return y;
 }
 
-// packed fp32 pairs (sm_100 add / fma .f32x2: two lanes of arithmetic per issue slot)
-__device__ __forceinline__ uint64_t f2_pack(float a, float b) {
-  uint64_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
-  return r;
-}
-__device__ __forceinline__ void f2_unpack(uint64_t v, float& a, float& b) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
-}
-__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
-  uint64_t r;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
-__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
-  uint64_t r;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
-__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
-  uint64_t r;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-  return r;
-}
 __device__ __forceinline__ void add_f32x2(float& a0, float& a1, float b0, float b1) {   // {a0, a1} += {b0, b1}
   f2_unpack(f2_add(f2_pack(a0, a1), f2_pack(b0, b1)), a0, a1);
 }

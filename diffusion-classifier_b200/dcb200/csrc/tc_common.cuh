@@ -701,10 +701,11 @@ __device__ __forceinline__ void staged_epilogue_half(const EpiGeom& gq, const Ep
           if (ocol0 + h0 + c + i < e.n_out) bz[i] += rv[i];
       }
 #pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(ra[i]) + bz[i];
+      for (int i = 0; i < 16; i += 2)
+        f2_unpack(f2_add(f2_pack(__uint_as_float(ra[i]), __uint_as_float(ra[i + 1])), f2_pack(bz[i], bz[i + 1])), v[i], v[i + 1]);
       if (e.act == DCB_ACT_SILU || e.act == DCB_ACT_GELU_TANH) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = apply_act_fast(e.act, v[i]);
+        for (int i = 0; i < 16; i += 2) act_fast_pair(e.act, v[i], v[i + 1]);
       }
       if (e.gate) {
         if (gq.uniform) {
@@ -732,7 +733,7 @@ __device__ __forceinline__ void staged_epilogue_half(const EpiGeom& gq, const Ep
       }
       if (e.act_post != DCB_ACT_NONE) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = apply_act_fast(e.act_post, v[i]);
+        for (int i = 0; i < 16; i += 2) act_fast_pair(e.act_post, v[i], v[i + 1]);
       }
       if (e.attn_norms != nullptr) {
 #pragma unroll
