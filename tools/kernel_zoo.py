@@ -106,6 +106,14 @@ case("gemm_tc3 (CTA pairs, cta_group::2): DiT QKV [131072 x 768] -> 2304", "flop
      lambda: E.linear(ctx, xd, wq, 2304))
 wf1 = bf(3072, 768) * 0.03
 bf1 = torch.randn(3072, device=dev)
+nws = E.attn_norms_ws(ctx, 32, 12)
+case("gemm_tc3 (four epilogue groups) + attention norms in the epilogue: DiT QKV [131072 x 768] -> 2304", "flops",
+     2.0 * 32 * 4096 * 2304 * 768, lambda: E.linear(ctx, xd, wq, 2304, attn_norms=(nws, 12, 4096)))
+wo = bf(768, 768) * 0.03
+gate_o = torch.randn(32, 768, device=dev)
+case("gemm_tc3 (four epilogue groups): DiT attention out-projection, gate x out + residual [131072 x 768] -> 768", "flops",
+     2.0 * 32 * 4096 * 768 * 768, lambda: E.linear(ctx, xd, wo, 768, gate=gate_o, gate_ld=768, rows_per_group=4096,
+                                                   residual=xd, res_ld=768))
 case("gemm_tc3 (CTA pairs, four epilogue groups): DiT FF1 + GELU [131072 x 768] -> 3072", "flops", 2.0 * 32 * 4096 * 3072 * 768,
      lambda: E.linear(ctx, xd, wf1, 3072, bias=bf1, act=L.ACT_GELU_TANH))
 xo = bf(NB * 128 * 128, 128)
@@ -119,6 +127,18 @@ case("gemm_tc2 x-halo + fused eps-MSE: conv_out 128->3 @128^2 x200 + mse_finaliz
 qkv = bf(8 * 4096, 2304)
 case("attention DiT-B/4: attn_norms + flash_attn_tc_fast (+ flash_attn_tc exits): 8 x 12 heads x 4096 x 64", "flops",
      4.0 * 8 * 12 * 4096 * 4096 * 64, lambda: E.attention(ctx, qkv, 8, 4096, 12, 64))
+qkvs = qkv * 0.35     # |q| |k| inside the single-pass kernel's bound, as after DiT's LayerNorm
+case("attention DiT-B/4 as the DiT blocks call it (|q||k| inside the bound, query pre-scaled): norm pass + single-pass kernel, 8 x 12 heads x 4096 x 64", "flops",
+     4.0 * 8 * 12 * 4096 * 4096 * 64, lambda: E.attention(ctx, qkvs, 8, 4096, 12, 64, scale=1.0 / 1.4426950408889634))
+qkv96 = bf(8 * 4096, 3 * 8 * 96)
+case("attention head dim 96: flash_attn_tc_kernel<96> 8 x 8 heads x 4096 x 96", "flops", 4.0 * 8 * 8 * 4096 * 4096 * 96,
+     lambda: E.attention(ctx, qkv96, 8, 4096, 8, 96))
+qkv128 = bf(8 * 4096, 3 * 8 * 128)
+case("attention head dim 128: flash_attn_tc_kernel<128> 8 x 8 heads x 4096 x 128", "flops", 4.0 * 8 * 8 * 4096 * 4096 * 128,
+     lambda: E.attention(ctx, qkv128, 8, 4096, 8, 128))
+qkv32 = bf(8 * 4096, 3 * 8 * 32)
+case("attention head dim 32: flash_attn_tc_kernel<32> 8 x 8 heads x 4096 x 32", "flops", 4.0 * 8 * 8 * 4096 * 4096 * 32,
+     lambda: E.attention(ctx, qkv32, 8, 4096, 8, 32))
 qkv2 = bf(NB * 256, 1536)
 case("attention U-Net 16^2 level: flash_attn_tc 200 x 8 heads x 256 x 64", "flops", 4.0 * NB * 8 * 256 * 256 * 64,
      lambda: E.attention(ctx, qkv2, NB, 256, 8, 64))
