@@ -774,7 +774,7 @@ __device__ __forceinline__ void staged_epilogue_half(const EpiGeom& gq, const Ep
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
       const int m_any = __shfl_sync(0xffffffffu, m, 0);
-      if (lane == 0) {
+      if (lane == 0 && row_ok) {   // rows % 128 == 0: a warp's rows exist together or not at all (odd tile count of a CTA pair)
         const int col = ocol0 + h0, which = col >= e.attn_heads * 64 ? 1 : 0;
         const int head = (col >> 6) - which * e.attn_heads;
         atomicMax(reinterpret_cast<int*>(e.attn_norms) + 2 + ((m_any / e.attn_tok) * e.attn_heads + head) * 2 + which,

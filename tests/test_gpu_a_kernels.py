@@ -276,7 +276,7 @@ def test_attention_tcgen05_head64(dev, B, heads, N, qscale):
     assert rel_err(out, simt) < 1e-2
 
 
-@pytest.mark.parametrize("B,heads,N", [(5, 12, 1024), (1, 4, 1024), (2, 12, 4096)])
+@pytest.mark.parametrize("B,heads,N", [(5, 12, 1024), (1, 4, 1024), (2, 12, 4096), (5, 12, 1152)])
 def test_attention_norm_prepass_folded_into_the_qkv_projection(dev, B, heads, N):
     """dcb_gemm_desc.attn_norms: the projection that writes q and k leaves max |q_i|^2 / max |k_j|^2 per (sample, head) --
     from the CTA-pair kernel's epilogue registers (first and last case: >= 148 tiles) or from the row pass the library
