@@ -28,6 +28,7 @@ constexpr int T3_STAGE_BYTES = 2 * TC_A_BYTES;     // A [128 x 64] + W half [128
 
 struct T3Params {
   int M, nkb, m_pairs, n_tiles, total_tiles, stages, uniform, c_off;
+  int geglu;        // GEGLU epilogue: group g owns output columns [64 g, + 64) of the tile's 128
   int ngroups;      // epilogue groups per CTA: 2 (128 columns each) or 4 (64 columns each: layers whose epilogue -- an
                     // activation over 128 x 256 outputs per CTA -- is longer than a K <= 1024 main loop)
   uint32_t idesc;
@@ -127,7 +128,7 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     // ===================== epilogue (both CTAs): group g drains columns [w g, + w) of this CTA's 128 rows, w = 256 / ngroups ==========
     const int q = warp & 3;
     const int grp = (warp - 2) >> 2;
-    const int gw = 256 / p.ngroups;
+    const int gw = p.geglu ? 64 : 256 / p.ngroups;
     const int tiles_x = (p.M + 127) / 128;
     EpiGeom gq{tiles_x, 1, 128, 1, 1, p.M, 1, 1, p.uniform};
     int as = 0;
@@ -171,8 +172,12 @@ int launch_gemm_tc3(const GemmDev& g, cudaStream_t st, int uniform) {
   const EpiDev& e = g.epi;
   const SegDev& s = g.seg[0];
   if (g.nseg != 1 || g.OH != 1 || g.NB != 1 || s.H != 1 || s.stride != 1 || s.dx != 0 || s.dy != 0 || s.nb_div > 1 ||
-      e.N % 256 != 0 || g.K % TC_BK != 0 || e.act == DCB_ACT_GEGLU || e.gn_part != nullptr || e.mse_part != nullptr ||
-      e.up_phase != 0 || s.W != g.OW)
+      e.N % 256 != 0 || g.K % TC_BK != 0 || e.gn_part != nullptr || e.mse_part != nullptr || e.up_phase != 0 || s.W != g.OW)
+    return DCB_EUNSUPPORTED;
+  // GEGLU: [128 value | 128 gate] weight rows per tile, two epilogue groups of 64 OUTPUT columns; plain form only
+  const bool geglu = e.act == DCB_ACT_GEGLU;
+  if (geglu && (e.rowvec != nullptr || e.gate != nullptr || e.residual != nullptr || e.act_post != DCB_ACT_NONE ||
+                e.attn_norms != nullptr))
     return DCB_EUNSUPPORTED;
   const int M = g.OW;
   T3Params p;
@@ -197,7 +202,8 @@ int launch_gemm_tc3(const GemmDev& g, cudaStream_t st, int uniform) {
   // second half whose prefetch would be exposed) when the main loop is short and the epilogue is not a plain store
   const bool heavy = e.act != DCB_ACT_NONE || (DCB_TC3_RULE >= 1 && (e.residual != nullptr || e.gate != nullptr)) ||
                      (DCB_TC3_RULE >= 2 && e.attn_norms != nullptr);
-  p.ngroups = (heavy && g.K <= 1024) ? 4 : 2;
+  p.ngroups = (heavy && g.K <= 1024 && !geglu) ? 4 : 2;
+  p.geglu = geglu ? 1 : 0;
   int stages = (TC_SMEM_LIMIT - 1024 - 512 - p.ngroups * TC_EPI_HALF_BYTES) / T3_STAGE_BYTES;
   if (stages > T3_MAX_STAGES) stages = T3_MAX_STAGES;
   if (stages > p.nkb) stages = p.nkb < 2 ? 2 : p.nkb;

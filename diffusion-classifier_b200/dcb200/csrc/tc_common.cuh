@@ -645,15 +645,20 @@ __device__ __forceinline__ void staged_epilogue_half(const EpiGeom& gq, const Ep
   float* s_gate = s_bias + 256 + 128;                          // [128]
   int* s_m = reinterpret_cast<int*>(s_gate + 128) + parity * 128;
   int* s_res = reinterpret_cast<int*>(s_gate + 128) + 256 + parity * 128;
-  const int wrow0 = tn * BN;
+  // GEGLU (gemm_tc3 only; BN == 64): this call owns output columns [tn * 64, + 64); their value accumulators start at
+  // taddr, their gate accumulators 128 TMEM columns further, and the packed weight rows are [128 value | 128 gate] per
+  // 128 outputs.  Same arithmetic as staged_epilogue: (a + b_a) * gelu_erf_fast(g + b_g).
+  const bool geglu = e.act == DCB_ACT_GEGLU;
   const int ncols_out = BN;
   const int ocol0 = tn * BN;
+  const int wrow0 = geglu ? (ocol0 >> 7) * 256 + (ocol0 & 127) : tn * BN;
   const int up_a = (e.up_phase - 1) >> 1, up_b = (e.up_phase - 1) & 1;
   const int m_out = e.up_phase ? ((nb * 2 * gq.OH + 2 * y + up_a) * (2 * gq.OW) + 2 * x + up_b) : m;
   s_m[r] = row_ok ? m_out : -1;
   if (e.residual) s_res[r] = row_ok ? (e.res_idx ? e.res_idx[m] : (e.res_mod > 0 ? m % e.res_mod : m)) : -1;
   const bool rv_folded = gq.uniform && e.rowvec != nullptr;
   for (int c = et; c < BN; c += 128) s_bias[c] = (e.bias && wrow0 + c < e.N) ? e.bias[wrow0 + c] : 0.f;
+  if (geglu && et < BN) s_bias[128 + et] = e.bias ? e.bias[wrow0 + 128 + et] : 0.f;
   if (gq.uniform && (e.rowvec || e.gate) && et < ncols_out) {
     const int m0 = (tb * gq.bn) * e.rows_per_sample + (ty * gq.bh) * gq.OW + tx * gq.bw;
     const int grp0 = m0 / e.rows_per_group;
@@ -742,7 +747,25 @@ __device__ __forceinline__ void staged_epilogue_half(const EpiGeom& gq, const Ep
       *s0 = pack_bf16x8(v);
       *s1 = pack_bf16x8(v + 8);
     };
-    {
+    if (geglu) {
+      for (int c = 0; c < 64; c += 16) {
+        uint32_t ra[16], rg[16];
+        tmem_ld16_nowait(taddr + (uint32_t)c, ra);
+        tmem_ld16_nowait(taddr + (uint32_t)(128 + c), rg);
+        tmem_ld_wait_dep(ra);
+        float v[16], bz[16], bg[16];
+        lds16f(smem_u32(s_bias + c), bz);
+        lds16f(smem_u32(s_bias + 128 + c), bg);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float a_ = __uint_as_float(ra[i]) + bz[i];
+          a_ *= gelu_erf_fast_f(__uint_as_float(rg[i]) + bg[i]);
+          v[i] = a_;
+        }
+        *reinterpret_cast<uint4*>(stg8 + r * 128 + ((((c >> 3)) ^ (r & 7)) << 4)) = pack_bf16x8(v);
+        *reinterpret_cast<uint4*>(stg8 + r * 128 + ((((c >> 3) + 1) ^ (r & 7)) << 4)) = pack_bf16x8(v + 8);
+      }
+    } else {
       const int ncol_h = min(64, ncols_out - h0);
       uint32_t ra[16], rb[16];
       tmem_ld16_nowait(taddr + (uint32_t)h0, ra);

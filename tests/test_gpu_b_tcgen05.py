@@ -565,6 +565,8 @@ def test_gn_fused_into_conv_operand_is_bit_identical(dev, NB, H, W, C0, C1, div1
     (20480, 768, 3072, "gelu"),          # DiT FF1 (GELU-tanh epilogue)
     (20480, 3072, 768, "gate_res"),      # DiT FF2: adaLN gate + residual, K = 3072 (48 K blocks)
     (51200, 512, 512, "rowvec_idx_c_off"),   # U-Net attention out-projection: gathered row vector, K range inside a wider tensor
+    (51200, 512, 4096, "geglu"),         # U-Net feed-forward: GEGLU, [128 value | 128 gate] weight rows per tile -> 2048 outputs
+    (20480, 768, 768, "gate_res"),       # DiT attention out-projection (four epilogue groups: K <= 1024 with gate + residual)
 ])
 def test_tc3_cta_pair_linear(dev, M, K, N, extra):
     """gemm_tc3_kernel (tcgen05 cta_group::2: a pair of CTAs computes a 256 x 256 tile, each loading its own A rows and half
@@ -589,6 +591,10 @@ def test_tc3_cta_pair_linear(dev, M, K, N, extra):
     if extra == "gelu":
         kw["act"] = L.ACT_GELU_TANH
         ref = F.gelu(ref, approximate="tanh")
+    if extra == "geglu":          # packed rows: per 128 outputs [128 value rows | 128 gate rows]
+        kw["act"] = L.ACT_GEGLU
+        r4 = ref.reshape(M, N // 256, 2, 128)
+        ref = (r4[:, :, 0] * F.gelu(r4[:, :, 1])).reshape(M, N // 2)
     if extra == "gate_res":
         gate = torch.randn(ngrp, N, device=dev)
         res = _bf(M, N, dev=dev)
