@@ -286,6 +286,32 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc_off(uint32_t smem_add
 }
 
 // 16 consecutive floats from shared memory (16-byte aligned address)
+// explicit shared-space accesses for the staged epilogues: through C++ pointers derived from the dynamic shared memory
+// base the compiler emits GENERIC loads / stores (LD.E / ST.E plus a 64-bit address per access: ncu source view of
+// gemm_tc2x, one 534-instruction copy-out block = 39 % of the epilogue warps' instructions)
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts128f(uint32_t a, float x, float y, float z, float w) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+__device__ __forceinline__ int lds32(uint32_t a) {
+  int v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts32(uint32_t a, int v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts32f(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ float2 lds64f(uint32_t a) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a) : "memory");
+  return v;
+}
 __device__ __forceinline__ void lds16f(uint32_t addr, float* f) {
 #pragma unroll
   for (int i = 0; i < 4; ++i)
@@ -641,10 +667,13 @@ __device__ __forceinline__ void staged_epilogue_half(const EpiGeom& gq, const Ep
   const int x = tx * gq.bw + xl, y = ty * gq.bh + yl, nb = tb * gq.bn + nl;
   const bool row_ok = x < gq.OW && y < gq.OH && nb < gq.NB;
   const int m = nb * e.rows_per_sample + y * gq.OW + x;
-  float* s_bias = reinterpret_cast<float*>(stg8 + 128 * 128);  // [256]
-  float* s_gate = s_bias + 256 + 128;                          // [128]
-  int* s_m = reinterpret_cast<int*>(s_gate + 128) + parity * 128;
-  int* s_res = reinterpret_cast<int*>(s_gate + 128) + 256 + parity * 128;
+  // shared-space byte addresses (see lds128): staging tile [128 rows x 128 B], bias [256] fp32, gate [128], row ids [2][128],
+  // residual row ids [2][128]
+  const uint32_t stg = smem_u32(stg8);
+  const uint32_t s_bias = stg + 128 * 128;
+  const uint32_t s_gate = s_bias + (256 + 128) * 4;
+  const uint32_t s_m = s_gate + 128 * 4 + parity * 128 * 4;
+  const uint32_t s_res = s_gate + 128 * 4 + 256 * 4 + parity * 128 * 4;
   // GEGLU (gemm_tc3 only; BN == 64): this call owns output columns [tn * 64, + 64); their value accumulators start at
   // taddr, their gate accumulators 128 TMEM columns further, and the packed weight rows are [128 value | 128 gate] per
   // 128 outputs.  Same arithmetic as staged_epilogue: (a + b_a) * gelu_erf_fast(g + b_g).
@@ -654,17 +683,23 @@ __device__ __forceinline__ void staged_epilogue_half(const EpiGeom& gq, const Ep
   const int wrow0 = geglu ? (ocol0 >> 7) * 256 + (ocol0 & 127) : tn * BN;
   const int up_a = (e.up_phase - 1) >> 1, up_b = (e.up_phase - 1) & 1;
   const int m_out = e.up_phase ? ((nb * 2 * gq.OH + 2 * y + up_a) * (2 * gq.OW) + 2 * x + up_b) : m;
-  s_m[r] = row_ok ? m_out : -1;
-  if (e.residual) s_res[r] = row_ok ? (e.res_idx ? e.res_idx[m] : (e.res_mod > 0 ? m % e.res_mod : m)) : -1;
+  sts32(s_m + r * 4, row_ok ? m_out : -1);
+  if (e.residual) sts32(s_res + r * 4, row_ok ? (e.res_idx ? e.res_idx[m] : (e.res_mod > 0 ? m % e.res_mod : m)) : -1);
   const bool rv_folded = gq.uniform && e.rowvec != nullptr;
-  for (int c = et; c < BN; c += 128) s_bias[c] = (e.bias && wrow0 + c < e.N) ? e.bias[wrow0 + c] : 0.f;
-  if (geglu && et < BN) s_bias[128 + et] = e.bias ? e.bias[wrow0 + 128 + et] : 0.f;
+  float my_bias = 0.f;     // s_bias[et] as this thread wrote it (BN <= 128: one entry per thread)
+  for (int c = et; c < BN; c += 128) {
+    my_bias = (e.bias && wrow0 + c < e.N) ? e.bias[wrow0 + c] : 0.f;
+    sts32f(s_bias + c * 4, my_bias);
+  }
+  if (geglu && et < BN) sts32f(s_bias + (128 + et) * 4, e.bias ? e.bias[wrow0 + 128 + et] : 0.f);
   if (gq.uniform && (e.rowvec || e.gate) && et < ncols_out) {
     const int m0 = (tb * gq.bn) * e.rows_per_sample + (ty * gq.bh) * gq.OW + tx * gq.bw;
     const int grp0 = m0 / e.rows_per_group;
     const bool ok = ocol0 + et < e.n_out;
-    if (e.rowvec) s_bias[et] += ok ? e.rowvec[(int64_t)(e.rowvec_idx ? e.rowvec_idx[grp0] : grp0) * e.rowvec_ld + ocol0 + et] : 0.f;
-    if (e.gate) s_gate[et] = ok ? e.gate[(int64_t)grp0 * e.gate_ld + ocol0 + et] : 0.f;
+    if (e.rowvec)
+      sts32f(s_bias + et * 4,
+             my_bias + (ok ? e.rowvec[(int64_t)(e.rowvec_idx ? e.rowvec_idx[grp0] : grp0) * e.rowvec_ld + ocol0 + et] : 0.f));
+    if (e.gate) sts32f(s_gate + et * 4, ok ? e.gate[(int64_t)grp0 * e.gate_ld + ocol0 + et] : 0.f);
   }
   epi_bar(bar_id);  // ids / constants visible; the previous tile's copy-out is complete
   const int cc = et & 7, rr0 = et >> 3;     // coalesced role: 16-byte chunk cc of rows rr0, rr0 + 16, ...
@@ -678,9 +713,9 @@ __device__ __forceinline__ void staged_epilogue_half(const EpiGeom& gq, const Ep
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int row = rr0 + 16 * i;
-        const int rrow = s_res[row];
+        const int rrow = lds32(s_res + row * 4);
         if (rrow >= 0)
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(stg8 + row * 128 + ((cc ^ (row & 7)) << 4))),
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(stg + row * 128 + ((cc ^ (row & 7)) << 4)),
                        "l"(rbase + (int64_t)rrow * e.res_ld)
                        : "memory");
       }
@@ -698,7 +733,7 @@ __device__ __forceinline__ void staged_epilogue_half(const EpiGeom& gq, const Ep
     float ss = 0.f;     // |row|^2 over this 64-column half: one attention head of q or k (EpiDev::attn_norms)
     auto process = [&](int c, const uint32_t (&ra)[16]) {     // c: column inside this half
       float v[16], bz[16];
-      lds16f(smem_u32(s_bias + h0 + c), bz);
+      lds16f(s_bias + (h0 + c) * 4, bz);
       if (e.rowvec && !rv_folded && row_ok) {
         const float* rv = e.rowvec + (int64_t)(e.rowvec_idx ? e.rowvec_idx[grp] : grp) * e.rowvec_ld + ocol0 + h0 + c;
 #pragma unroll
@@ -715,7 +750,7 @@ __device__ __forceinline__ void staged_epilogue_half(const EpiGeom& gq, const Ep
       if (e.gate) {
         if (gq.uniform) {
           float gvv[16];
-          lds16f(smem_u32(s_gate + h0 + c), gvv);
+          lds16f(s_gate + (h0 + c) * 4, gvv);
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] *= gvv[i];
         } else if (row_ok) {
@@ -725,14 +760,14 @@ __device__ __forceinline__ void staged_epilogue_half(const EpiGeom& gq, const Ep
             if (ocol0 + h0 + c + i < e.n_out) v[i] *= gt[i];
         }
       }
-      uint4* s0 = reinterpret_cast<uint4*>(stg8 + r * 128 + ((((c >> 3)) ^ (r & 7)) << 4));
-      uint4* s1 = reinterpret_cast<uint4*>(stg8 + r * 128 + ((((c >> 3) + 1) ^ (r & 7)) << 4));
+      const uint32_t s0 = stg + r * 128 + ((((c >> 3)) ^ (r & 7)) << 4);
+      const uint32_t s1 = stg + r * 128 + ((((c >> 3) + 1) ^ (r & 7)) << 4);
       if (e.residual && row_ok) {
         float f[8];
-        unpack_bf16x8(*s0, f);
+        unpack_bf16x8(lds128(s0), f);
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] += f[i];
-        unpack_bf16x8(*s1, f);
+        unpack_bf16x8(lds128(s1), f);
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[8 + i] += f[i];
       }
@@ -744,8 +779,8 @@ __device__ __forceinline__ void staged_epilogue_half(const EpiGeom& gq, const Ep
 #pragma unroll
         for (int i = 0; i < 16; ++i) ss = fmaf(v[i], v[i], ss);
       }
-      *s0 = pack_bf16x8(v);
-      *s1 = pack_bf16x8(v + 8);
+      sts128(s0, pack_bf16x8(v));
+      sts128(s1, pack_bf16x8(v + 8));
     };
     if (geglu) {
       for (int c = 0; c < 64; c += 16) {
@@ -754,16 +789,16 @@ __device__ __forceinline__ void staged_epilogue_half(const EpiGeom& gq, const Ep
         tmem_ld16_nowait(taddr + (uint32_t)(128 + c), rg);
         tmem_ld_wait_dep(ra);
         float v[16], bz[16], bg[16];
-        lds16f(smem_u32(s_bias + c), bz);
-        lds16f(smem_u32(s_bias + 128 + c), bg);
+        lds16f(s_bias + c * 4, bz);
+        lds16f(s_bias + (128 + c) * 4, bg);
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           float a_ = __uint_as_float(ra[i]) + bz[i];
           a_ *= gelu_erf_fast_f(__uint_as_float(rg[i]) + bg[i]);
           v[i] = a_;
         }
-        *reinterpret_cast<uint4*>(stg8 + r * 128 + ((((c >> 3)) ^ (r & 7)) << 4)) = pack_bf16x8(v);
-        *reinterpret_cast<uint4*>(stg8 + r * 128 + ((((c >> 3) + 1) ^ (r & 7)) << 4)) = pack_bf16x8(v + 8);
+        sts128(stg + r * 128 + ((((c >> 3)) ^ (r & 7)) << 4), pack_bf16x8(v));
+        sts128(stg + r * 128 + ((((c >> 3) + 1) ^ (r & 7)) << 4), pack_bf16x8(v + 8));
       }
     } else {
       const int ncol_h = min(64, ncols_out - h0);
@@ -814,9 +849,9 @@ __device__ __forceinline__ void staged_epilogue_half(const EpiGeom& gq, const Ep
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int row = rr0 + 16 * i;
-        const int mm = s_m[row];
+        const int mm = lds32(s_m + row * 4);
         if (mm >= 0) {
-          const uint4 val = *reinterpret_cast<const uint4*>(stg8 + row * 128 + ((cc ^ (row & 7)) << 4));
+          const uint4 val = lds128(stg + row * 128 + ((cc ^ (row & 7)) << 4));
           *reinterpret_cast<uint4*>(obase + (int64_t)mm * e.out_ld) = val;
           if (e.gn_part) {
             float f[8];
@@ -829,22 +864,22 @@ __device__ __forceinline__ void staged_epilogue_half(const EpiGeom& gq, const Ep
     }
     if (e.gn_part) {
       epi_bar(bar_id);  // every thread has read its rows out of the staging tile
-      float* red = reinterpret_cast<float*>(stg8);  // [16 row classes][64 columns][2]
+      const uint32_t red = stg;  // [16 row classes][64 columns][2] fp32
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        red[((rr0 * 64) + cc * 8 + j) * 2] = cs[j];
-        red[((rr0 * 64) + cc * 8 + j) * 2 + 1] = cq[j];
-      }
+      for (int j = 0; j < 8; j += 2)
+        sts128f(red + (((rr0 * 64) + cc * 8 + j) * 2) * 4, cs[j], cq[j], cs[j + 1], cq[j + 1]);
       epi_bar(bar_id);
       if (et < 64 && h0 + et < ncols_out && ocol0 + h0 + et < e.n_out && tb * gq.bn < gq.NB) {
         float S[4], Q4[4];
 #pragma unroll
         for (int w = 0; w < 4; ++w) {
-          const float qa = red[((2 * w) * 64 + et) * 2] + red[((2 * w + 8) * 64 + et) * 2];
-          const float qb = red[((2 * w + 1) * 64 + et) * 2] + red[((2 * w + 9) * 64 + et) * 2];
+          const float2 p0 = lds64f(red + (((2 * w) * 64 + et) * 2) * 4), p8 = lds64f(red + (((2 * w + 8) * 64 + et) * 2) * 4);
+          const float2 p1 = lds64f(red + (((2 * w + 1) * 64 + et) * 2) * 4), p9 = lds64f(red + (((2 * w + 9) * 64 + et) * 2) * 4);
+          const float qa = p0.x + p8.x;
+          const float qb = p1.x + p9.x;
           S[w] = qa + qb;
-          const float ra_ = red[((2 * w) * 64 + et) * 2 + 1] + red[((2 * w + 8) * 64 + et) * 2 + 1];
-          const float rb_ = red[((2 * w + 1) * 64 + et) * 2 + 1] + red[((2 * w + 9) * 64 + et) * 2 + 1];
+          const float ra_ = p0.y + p8.y;
+          const float rb_ = p1.y + p9.y;
           Q4[w] = ra_ + rb_;
         }
         const float s4 = (S[0] + S[1]) + (S[2] + S[3]);
