@@ -435,31 +435,39 @@ __device__ __forceinline__ void staged_epilogue(const EpiGeom& gq, const EpiDev&
   const int x = tx * gq.bw + xl, y = ty * gq.bh + yl, nb = tb * gq.bn + nl;
   const bool row_ok = x < gq.OW && y < gq.OH && nb < gq.NB;
   const int m = nb * e.rows_per_sample + y * gq.OW + x;
-    float* s_bias = reinterpret_cast<float*>(stg8 + 128 * 256);  // [256]
-    float* s_rowvec = s_bias + 256;                              // [128]
-    float* s_gate = s_rowvec + 128;                              // [128]
-    int* s_m = reinterpret_cast<int*>(s_gate + 128) + parity * 128;
-    int* s_res = reinterpret_cast<int*>(s_gate + 128) + 256 + parity * 128;
+    // shared-space byte addresses (see lds128): staging tile [128 rows x 256 B], bias [256] fp32, rowvec [128], gate [128],
+    // row ids [2][128], residual row ids [2][128]
+    const uint32_t stg = smem_u32(stg8);
+    const uint32_t s_bias = stg + 128 * 256;
+    const uint32_t s_rowvec = s_bias + 256 * 4;
+    const uint32_t s_gate = s_rowvec + 128 * 4;
+    const uint32_t s_m = s_gate + 128 * 4 + parity * 128 * 4;
+    const uint32_t s_res = s_gate + 128 * 4 + 256 * 4 + parity * 128 * 4;
             const int wrow0 = tn * BN;
     const int ncols_out = geglu ? 128 : BN;
     const int ocol0 = geglu ? tn * 128 : tn * BN;
     // output row: identity, or the (2y + a, 2x + b) position of a folded-upsample phase
     const int up_a = (e.up_phase - 1) >> 1, up_b = (e.up_phase - 1) & 1;
     const int m_out = e.up_phase ? ((nb * 2 * gq.OH + 2 * y + up_a) * (2 * gq.OW) + 2 * x + up_b) : m;
-    s_m[r] = row_ok ? m_out : -1;
-    if (e.residual) s_res[r] = row_ok ? (e.res_idx ? e.res_idx[m] : (e.res_mod > 0 ? m % e.res_mod : m)) : -1;
+    sts32(s_m + r * 4, row_ok ? m_out : -1);
+    if (e.residual) sts32(s_res + r * 4, row_ok ? (e.res_idx ? e.res_idx[m] : (e.res_mod > 0 ? m % e.res_mod : m)) : -1);
     const bool rv_folded = gq.uniform && e.rowvec != nullptr && !geglu;
-    for (int c = et; c < BN; c += 128) s_bias[c] = (e.bias && wrow0 + c < e.N) ? e.bias[wrow0 + c] : 0.f;
+    float my_bias = 0.f;     // s_bias[et] as this thread wrote it (first trip of the loop)
+    for (int c = et; c < BN; c += 128) {
+      const float bv = (e.bias && wrow0 + c < e.N) ? e.bias[wrow0 + c] : 0.f;
+      if (c == et) my_bias = bv;
+      sts32f(s_bias + c * 4, bv);
+    }
     if (gq.uniform && (e.rowvec || e.gate) && et < ncols_out) {
       const int m0 = (tb * gq.bn) * e.rows_per_sample + (ty * gq.bh) * gq.OW + tx * gq.bw;
       const int grp0 = m0 / e.rows_per_group;
       const bool ok = ocol0 + et < e.n_out;
       if (e.rowvec) {
         const float rvv = ok ? e.rowvec[(int64_t)(e.rowvec_idx ? e.rowvec_idx[grp0] : grp0) * e.rowvec_ld + ocol0 + et] : 0.f;
-        if (rv_folded) s_bias[et] += rvv;   // thread et wrote s_bias[et] just above (BN <= 128 here): acc + (bias + rowvec)
-        else s_rowvec[et] = rvv;
+        if (rv_folded) sts32f(s_bias + et * 4, my_bias + rvv);   // thread et wrote s_bias[et] just above: acc + (bias + rowvec)
+        else sts32f(s_rowvec + et * 4, rvv);
       }
-      if (e.gate) s_gate[et] = ok ? e.gate[(int64_t)grp0 * e.gate_ld + ocol0 + et] : 0.f;
+      if (e.gate) sts32f(s_gate + et * 4, ok ? e.gate[(int64_t)grp0 * e.gate_ld + ocol0 + et] : 0.f);
     }
     epi_bar(bar_id);  // ids/constants visible; everybody has finished copying the previous tile out of the staging tile
     const int cc = et & 15, rr0 = et >> 4;            // coalesced role: 16-byte chunk cc of rows rr0, rr0+8, ...
@@ -469,9 +477,9 @@ __device__ __forceinline__ void staged_epilogue(const EpiGeom& gq, const EpiDev&
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         const int row = rr0 + 8 * i;
-        const int rrow = s_res[row];
+        const int rrow = lds32(s_res + row * 4);
         if (rrow >= 0)
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(stg8 + row * 256 + ((cc ^ (row & 7)) << 4))),
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(stg + row * 256 + ((cc ^ (row & 7)) << 4)),
                        "l"(rbase + (int64_t)rrow * e.res_ld)
                        : "memory");
       }
@@ -491,8 +499,8 @@ __device__ __forceinline__ void staged_epilogue(const EpiGeom& gq, const EpiDev&
       float v[16], bz[16], bg[16];
       // tile-constant vectors through explicit 16-byte shared loads (the generic-pointer form compiles to LD.E);
       // s_bias already holds bias + rowvec when the tile has one rowvec group (rv_folded)
-      lds16f(smem_u32(s_bias + c), bz);
-      if (geglu) lds16f(smem_u32(s_bias + 128 + c), bg);
+      lds16f(s_bias + c * 4, bz);
+      if (geglu) lds16f(s_bias + (128 + c) * 4, bg);
       if (e.rowvec && !rv_folded && !geglu && row_ok) {   // row-dependent group: same (bias + rowvec) association
         const float* rv = e.rowvec + (int64_t)(e.rowvec_idx ? e.rowvec_idx[grp] : grp) * e.rowvec_ld + ocol0 + c;
 #pragma unroll
@@ -508,7 +516,7 @@ __device__ __forceinline__ void staged_epilogue(const EpiGeom& gq, const EpiDev&
       if (e.rowvec && geglu) {
         if (gq.uniform) {
           float rvv[16];
-          lds16f(smem_u32(s_rowvec + c), rvv);
+          lds16f(s_rowvec + c * 4, rvv);
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] += rvv[i];
         } else if (row_ok) {
@@ -525,7 +533,7 @@ __device__ __forceinline__ void staged_epilogue(const EpiGeom& gq, const EpiDev&
       if (e.gate) {
         if (gq.uniform) {
           float gvv[16];
-          lds16f(smem_u32(s_gate + c), gvv);
+          lds16f(s_gate + c * 4, gvv);
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] *= gvv[i];
         } else if (row_ok) {
@@ -535,14 +543,14 @@ __device__ __forceinline__ void staged_epilogue(const EpiGeom& gq, const EpiDev&
             if (ocol0 + c + i < e.n_out) v[i] *= gt[i];
         }
       }
-      uint4* s0 = reinterpret_cast<uint4*>(stg8 + r * 256 + ((((c >> 3)) ^ (r & 7)) << 4));
-      uint4* s1 = reinterpret_cast<uint4*>(stg8 + r * 256 + ((((c >> 3) + 1) ^ (r & 7)) << 4));
+      const uint32_t s0 = stg + r * 256 + ((((c >> 3)) ^ (r & 7)) << 4);
+      const uint32_t s1 = stg + r * 256 + ((((c >> 3) + 1) ^ (r & 7)) << 4);
       if (e.residual && row_ok) {
         float f[8];
-        unpack_bf16x8(*s0, f);
+        unpack_bf16x8(lds128(s0), f);
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] += f[i];
-        unpack_bf16x8(*s1, f);
+        unpack_bf16x8(lds128(s1), f);
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[8 + i] += f[i];
       }
@@ -550,8 +558,8 @@ __device__ __forceinline__ void staged_epilogue(const EpiGeom& gq, const EpiDev&
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = apply_act_fast(e.act_post, v[i]);
       }
-      *s0 = pack_bf16x8(v);
-      *s1 = pack_bf16x8(v + 8);
+      sts128(s0, pack_bf16x8(v));
+      sts128(s1, pack_bf16x8(v + 8));
     };
     if (geglu) {
       for (int c = 0; c < ncols_out; c += 16) {
@@ -593,9 +601,9 @@ __device__ __forceinline__ void staged_epilogue(const EpiGeom& gq, const EpiDev&
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         const int row = rr0 + 8 * i;
-        const int mm = s_m[row];
+        const int mm = lds32(s_m + row * 4);
         if (mm >= 0) {
-          const uint4 val = *reinterpret_cast<const uint4*>(stg8 + row * 256 + ((cc ^ (row & 7)) << 4));
+          const uint4 val = lds128(stg + row * 256 + ((cc ^ (row & 7)) << 4));
           *reinterpret_cast<uint4*>(obase + (int64_t)mm * e.out_ld) = val;
           if (e.gn_part) {
             float f[8];
@@ -622,19 +630,19 @@ __device__ __forceinline__ void staged_epilogue(const EpiGeom& gq, const EpiDev&
         cq[j] += __shfl_xor_sync(0xffffffffu, cq[j], 16);
       }
       epi_bar(bar_id);  // every thread has read its rows out of the staging tile
-      float* red = reinterpret_cast<float*>(stg8);  // [4 warps][128 columns][2]
+      const uint32_t red = stg;  // [4 warps][128 columns][2] fp32
       const int wq = et >> 5;
       if ((et & 16) == 0) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          red[(wq * 128 + cc * 8 + j) * 2] = cs[j];
-          red[(wq * 128 + cc * 8 + j) * 2 + 1] = cq[j];
-        }
+        for (int j = 0; j < 8; j += 2)
+          sts128f(red + ((wq * 128 + cc * 8 + j) * 2) * 4, cs[j], cq[j], cs[j + 1], cq[j + 1]);
       }
       epi_bar(bar_id);
       if (et < ncols_out && ocol0 + et < e.n_out && tb * gq.bn < gq.NB) {  // (tc2's odd tail sub-tile has no slot)
-        const float s4 = (red[et * 2] + red[(128 + et) * 2]) + (red[(256 + et) * 2] + red[(384 + et) * 2]);
-        const float q4 = (red[et * 2 + 1] + red[(128 + et) * 2 + 1]) + (red[(256 + et) * 2 + 1] + red[(384 + et) * 2 + 1]);
+        const float2 w0 = lds64f(red + (et * 2) * 4), w1 = lds64f(red + ((128 + et) * 2) * 4);
+        const float2 w2 = lds64f(red + ((256 + et) * 2) * 4), w3 = lds64f(red + ((384 + et) * 2) * 4);
+        const float s4 = (w0.x + w1.x) + (w2.x + w3.x);
+        const float q4 = (w0.y + w1.y) + (w2.y + w3.y);
         // phases of a folded upsample interleave their tiles per sample: [n][phase][tile of the low-resolution grid]
         const int tps = gq.tiles_x * gq.tiles_y;
         const int64_t gtile = e.up_phase ? ((int64_t)(tb * 4 + e.up_phase - 1) * tps + (tm_lin - tb * tps)) : (int64_t)tm_lin;
