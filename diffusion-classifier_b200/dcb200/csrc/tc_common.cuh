@@ -854,19 +854,38 @@ __device__ __forceinline__ void staged_epilogue_half(const EpiGeom& gq, const Ep
     for (int i = 0; i < 8; ++i) cs[i] = cq[i] = 0.f;
     if (cc_ok) {
       __nv_bfloat16* obase = (__nv_bfloat16*)e.out + ocol0 + h0 + cc * 8;
+      if (e.gn_part) {    // two loops: the (uniform) statistics test is not re-evaluated per row
+        uint64_t cs2[4], cq2[4];   // two columns per packed add / fma: same order and rounding as the scalar form
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int row = rr0 + 16 * i;
-        const int mm = lds32(s_m + row * 4);
-        if (mm >= 0) {
-          const uint4 val = lds128(stg + row * 128 + ((cc ^ (row & 7)) << 4));
-          *reinterpret_cast<uint4*>(obase + (int64_t)mm * e.out_ld) = val;
-          if (e.gn_part) {
+        for (int j = 0; j < 4; ++j) cs2[j] = cq2[j] = f2_pack(0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = rr0 + 16 * i;
+          const int mm = lds32(s_m + row * 4);
+          if (mm >= 0) {
+            const uint4 val = lds128(stg + row * 128 + ((cc ^ (row & 7)) << 4));
+            *reinterpret_cast<uint4*>(obase + (int64_t)mm * e.out_ld) = val;
             float f[8];
             unpack_bf16x8(val, f);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) { cs[j] += f[j]; cq[j] = fmaf(f[j], f[j], cq[j]); }
+            for (int j = 0; j < 4; ++j) {
+              const uint64_t f2 = f2_pack(f[2 * j], f[2 * j + 1]);
+              cs2[j] = f2_add(cs2[j], f2);
+              cq2[j] = f2_fma(f2, f2, cq2[j]);
+            }
           }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          f2_unpack(cs2[j], cs[2 * j], cs[2 * j + 1]);
+          f2_unpack(cq2[j], cq[2 * j], cq[2 * j + 1]);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = rr0 + 16 * i;
+          const int mm = lds32(s_m + row * 4);
+          if (mm >= 0) *reinterpret_cast<uint4*>(obase + (int64_t)mm * e.out_ld) = lds128(stg + row * 128 + ((cc ^ (row & 7)) << 4));
         }
       }
     }
