@@ -452,3 +452,27 @@ def test_c_abi_argument_validation_returns_codes_not_crashes():
     assert lib.dcb_pack_upsample(7, 1, 8, 8, 1, None) == -1 and "dtype" in err()
     assert lib.dcb_pack_rows(_lib.BF16, 1, 4, 2, 8, 1, 8, 0, 0, None) == -1
     assert lib.dcb_launch_count() == 0          # nothing was launched
+
+
+def test_params_version_sees_every_kind_of_weight_change():
+    """engine.params_version (the key of the packed-weight and CUDA-graph caches, evaluated at the top of every classify()
+    call) changes on an in-place update, on a replaced Parameter, on a replaced sub-module and on a moved storage -- and
+    is stable otherwise."""
+    import torch
+    import torch.nn as nn
+    from dcb200 import engine as E
+    net = nn.Sequential(nn.Linear(4, 4), nn.Sequential(nn.Linear(4, 4), nn.LayerNorm(4)))
+    v0 = E.params_version(net)
+    assert v0 == E.params_version(net) and len(v0) == 2 * len(list(net.parameters()))
+    with torch.no_grad():
+        net[1][0].bias.add_(1.0)                       # optimizer step / load_state_dict / EMA copy: in place
+    v1 = E.params_version(net)
+    assert v1 != v0
+    net[0].weight = nn.Parameter(net[0].weight.detach().clone())     # replaced Parameter (new storage)
+    v2 = E.params_version(net)
+    assert v2 != v1
+    net[1][1] = nn.LayerNorm(4)                       # replaced sub-module
+    v3 = E.params_version(net)
+    assert v3 != v2
+    net[0].weight.data = net[0].weight.data.clone()   # what Module.to() / .half() do: same Parameter, new storage
+    assert E.params_version(net) != v3
