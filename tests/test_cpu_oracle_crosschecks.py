@@ -141,3 +141,97 @@ def test_attention_oracle_equals_explicit_softmax():
     ctx = torch.randn(2, 1, 24, dtype=torch.float64)
     want1 = xatt.to_out[0](xatt.to_v(ctx)).expand(2, 9, 64)
     assert (xatt(x, ctx) - want1).abs().max() < 1e-12
+
+
+# ---- independent third-party implementations of diffusers' blocks that ship inside `transformers` -------------------------------
+# The VQ-VAE encoders of Chameleon / Emu3 carry the latent-diffusion ResnetBlock and Upsample that diffusers' ResnetBlock2D
+# and Upsample2D descend from, and Qwen2.5-Omni's token2wav DiT carries AdaLayerNormZero, the adaLN-Zero decoder layer
+# and the GELU(tanh) MLP of diffusers' BasicTransformerBlock(norm_type="ada_norm_zero").  They were written by other
+# people from the same upstream sources: executed where they lie, with the oracle's weights copied in.
+def _tf(modname, cls):
+    try:
+        mod = __import__("transformers.models." + modname, fromlist=[cls])
+        return getattr(mod, cls)
+    except Exception as e:  # pragma: no cover
+        pytest.skip(f"transformers.{modname}.{cls} not importable: {e}")
+
+
+class _Const(torch.nn.Module):
+    """stands in for a sub-module whose output the test wants to dictate"""
+
+    def __init__(self, value):
+        super().__init__()
+        self.value = value
+
+    def forward(self, *args, **kwargs):
+        return self.value
+
+
+@pytest.mark.parametrize("cin,cout", [(64, 64), (64, 128)])
+def test_resnet_block_matches_transformers_vqvae_resnet_block(cin, cout):
+    """oracle ResnetBlock2D (GroupNorm -> SiLU -> conv3x3 -> [+ time embedding] -> GroupNorm -> SiLU -> conv3x3, 1x1 shortcut
+    when the channel count changes, residual add) against ChameleonVQVAEEncoderResnetBlock with the time-embedding
+    projection zeroed (the VQ-VAE block has none)."""
+    from types import SimpleNamespace
+    from oracle import diffusers_restated as dr
+    Blk = _tf("chameleon.modeling_chameleon", "ChameleonVQVAEEncoderResnetBlock")
+    torch.manual_seed(cin + cout)
+    ours = dr.ResnetBlock2D(cin, cout, temb_channels=32, groups=32, eps=1e-6).double()
+    with torch.no_grad():
+        ours.time_emb_proj.weight.zero_()
+        ours.time_emb_proj.bias.zero_()
+        for p in (ours.norm1.weight, ours.norm1.bias, ours.norm2.weight, ours.norm2.bias):
+            p.copy_(torch.randn_like(p))
+    ref = Blk(SimpleNamespace(dropout=0.0), cin, cout).double().eval()
+    pairs = [("norm1", "norm1"), ("conv1", "conv1"), ("norm2", "norm2"), ("conv2", "conv2")]
+    if cin != cout:
+        pairs.append(("nin_shortcut", "conv_shortcut"))
+    for theirs, mine in pairs:
+        getattr(ref, theirs).load_state_dict(getattr(ours, mine).state_dict())
+    x = torch.randn(2, cin, 8, 8, dtype=torch.float64)
+    temb = torch.randn(2, 32, dtype=torch.float64)
+    assert (ours(x, temb) - ref(x.clone())).abs().max() < 1e-10
+
+
+def test_upsample_matches_transformers_vqvae_upsample():
+    """oracle Upsample2D (nearest 2x, then conv3x3 pad 1) against Emu3VQVAEEncoderConvUpsample."""
+    from oracle import diffusers_restated as dr
+    Up = _tf("emu3.modeling_emu3", "Emu3VQVAEEncoderConvUpsample")
+    torch.manual_seed(3)
+    ours, ref = dr.Upsample2D(16).double(), Up(16).double()
+    ref.conv.load_state_dict(ours.conv.state_dict())
+    x = torch.randn(2, 16, 5, 7, dtype=torch.float64)
+    assert (ours(x) - ref(x)).abs().max() < 1e-12
+
+
+def test_adaln_zero_block_matches_transformers_dit():
+    """oracle AdaLayerNormZero (SiLU -> Linear(6 dim) -> chunks IN THE ORDER shift_msa, scale_msa, gate_msa, shift_mlp,
+    scale_mlp, gate_mlp; LayerNorm without affine, eps 1e-6; x (1 + scale) + shift) and the feed-forward half of the adaLN-Zero
+    block (h + gate_mlp * MLP(LN(h) (1 + scale_mlp) + shift_mlp), MLP = Linear -> GELU(tanh) -> Linear) against
+    Qwen2.5-Omni's DiT (Qwen2_5_OmniAdaLayerNormZero, DiTMLP and the arithmetic of its decoder layer)."""
+    from oracle import diffusers_restated as dr
+    Ada = _tf("qwen2_5_omni.modeling_qwen2_5_omni", "Qwen2_5_OmniAdaLayerNormZero")
+    MLP = _tf("qwen2_5_omni.modeling_qwen2_5_omni", "DiTMLP")
+    torch.manual_seed(5)
+    dim, B, N = 48, 3, 7
+    blk = dr.BasicTransformerBlockAdaZero(dim, heads=4, dim_head=12, num_embeds=10, norm_eps=1e-6, attention_bias=True).double()
+    emb = torch.randn(B, dim, dtype=torch.float64)
+    blk.norm1.emb = _Const(emb)                                  # feed the conditioning vector directly
+    ref_ada = Ada(dim).double()
+    ref_ada.linear.load_state_dict(blk.norm1.linear.state_dict())
+    x = torch.randn(B, N, dim, dtype=torch.float64)
+    got = blk.norm1(x, None, None)
+    want = ref_ada(x, emb=emb)
+    for g, w in zip(got, want):
+        assert (g - w).abs().max() < 1e-12
+    ref_mlp = MLP(dim, mult=4).double()
+    ref_mlp.ff[0].load_state_dict(blk.ff.net[0].proj.state_dict())
+    ref_mlp.ff[3].load_state_dict(blk.ff.net[2].state_dict())
+    # the block with its attention output replaced by a known tensor: Qwen's decoder-layer arithmetic
+    a_out = torch.randn(B, N, dim, dtype=torch.float64)
+    blk.attn1 = _Const(a_out)
+    _, gate_msa, shift_mlp, scale_mlp, gate_mlp = want
+    h = x + gate_msa.unsqueeze(1) * a_out
+    norm = torch.nn.functional.layer_norm(h, (dim,), eps=1e-6) * (1 + scale_mlp[:, None]) + shift_mlp[:, None]
+    ref_out = h + gate_mlp.unsqueeze(1) * ref_mlp(norm)
+    assert (blk(x, None, None) - ref_out).abs().max() < 1e-11
