@@ -10,8 +10,10 @@ code:
   * the Haar analysis bank written from pywt's documented filter coefficients (dec_lo = [1, 1]/sqrt2,
     dec_hi = [-1, 1]/sqrt2, coefficient k = sum_j f[j] x[2k + 1 - j]) as an explicit convolution + decimation."""
 import ast
+import contextlib
 import math
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -75,9 +77,25 @@ def test_timestep_embedding_matches_tvm_port_of_diffusers(dim, flip, shift):
     assert np.abs(ref - mine).max() < 2e-6
 
 
+@contextlib.contextmanager
+def _without_test_stubs():
+    """Other tests of this suite leave spec-less stand-ins for packages this image lacks (accelerate, diffusers, ...) in
+    sys.modules; transformers probes some of them with importlib.util.find_spec, which raises on a module without a spec.
+    Import transformers' model files with those stand-ins out of the way."""
+    names = [k for k, m in sys.modules.items()
+             if k.split(".")[0] in ("accelerate", "diffusers", "comet_ml", "ema_pytorch", "pywt", "dataset")
+             and getattr(m, "__spec__", None) is None]
+    saved = {k: sys.modules.pop(k) for k in names}
+    try:
+        yield
+    finally:
+        sys.modules.update(saved)
+
+
 def test_dit_pos_embed_matches_mae_sincos_table():
     try:
-        from transformers.models.vit_mae.modeling_vit_mae import get_2d_sincos_pos_embed as mae
+        with _without_test_stubs():
+            from transformers.models.vit_mae.modeling_vit_mae import get_2d_sincos_pos_embed as mae
     except Exception:  # pragma: no cover
         pytest.skip("transformers' MAE model is not importable")
     from oracle import diffusers_restated as dr
@@ -150,7 +168,8 @@ def test_attention_oracle_equals_explicit_softmax():
 # people from the same upstream sources: executed where they lie, with the oracle's weights copied in.
 def _tf(modname, cls):
     try:
-        mod = __import__("transformers.models." + modname, fromlist=[cls])
+        with _without_test_stubs():
+            mod = __import__("transformers.models." + modname, fromlist=[cls])
         return getattr(mod, cls)
     except Exception as e:  # pragma: no cover
         pytest.skip(f"transformers.{modname}.{cls} not importable: {e}")
