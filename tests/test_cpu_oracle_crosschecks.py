@@ -254,3 +254,35 @@ def test_adaln_zero_block_matches_transformers_dit():
     norm = torch.nn.functional.layer_norm(h, (dim,), eps=1e-6) * (1 + scale_mlp[:, None]) + shift_mlp[:, None]
     ref_out = h + gate_mlp.unsqueeze(1) * ref_mlp(norm)
     assert (blk(x, None, None) - ref_out).abs().max() < 1e-11
+
+
+# ---- published parameter counts of well-known checkpoints: pin the WIRING of the restated models (every channel count of the
+# skip concatenations, the transformer blocks' inner sizes, the conditioning MLPs) independently of the reference's own configs
+def test_unet_restatement_reproduces_stable_diffusion_v1_5_parameter_count():
+    """diffusers' UNet2DConditionModel at the Stable Diffusion v1.x config (block_out_channels 320/640/1280/1280, 2 layers
+    per block, 8 heads, cross_attention_dim 768, CrossAttn x3 + Down / Up + CrossAttnUp x3) has 859 520 964 parameters
+    (the number every SD 1.x model card and `diffusers` issue quotes).  The oracle class, built on the meta device with
+    that config, must have exactly that many once the reference-specific ``encoder_hid_proj`` is taken out."""
+    from oracle import diffusers_restated as dr
+    with torch.device("meta"):
+        m = dr.UNet2DConditionModel(sample_size=64, in_channels=4, out_channels=4, block_out_channels=(320, 640, 1280, 1280),
+                                    layers_per_block=2, cross_attention_dim=768, attention_head_dim=8, encoder_hid_dim=16,
+                                    encoder_hid_dim_type="text_proj")
+    n = sum(p.numel() for p in m.parameters()) - sum(p.numel() for p in m.encoder_hid_proj.parameters())
+    assert n == 859_520_964
+
+
+def test_dit_restatement_reproduces_dit_xl_2_parameter_count():
+    """facebookresearch/DiT prints ``DiT Parameters: 675,129,632`` for DiT-XL/2 (256 x 256: 32 x 32 x 4 latents, patch 2,
+    28 layers, 16 heads x 72, learn_sigma, 1000 classes + the null class).  That count includes the frozen sincos table
+    (256 x 1152, an nn.Parameter there, a buffer in diffusers); diffusers' port additionally gives EVERY block's
+    AdaLayerNormZero its own copy of the timestep / label embedder (28 instead of 1).  Accounting for exactly those two
+    differences the oracle's DiTTransformer2DModel has the published count."""
+    from oracle import diffusers_restated as dr
+    with torch.device("meta"):
+        m = dr.DiTTransformer2DModel(num_attention_heads=16, attention_head_dim=72, in_channels=4, out_channels=8, num_layers=28,
+                                     sample_size=32, patch_size=2, num_embeds_ada_norm=1000, attention_bias=True,
+                                     norm_num_groups=32)
+    total = sum(p.numel() for p in m.parameters())
+    embedder = sum(p.numel() for p in m.transformer_blocks[0].norm1.emb.parameters())
+    assert total - 27 * embedder + 256 * 1152 == 675_129_632
