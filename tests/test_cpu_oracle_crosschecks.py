@@ -286,3 +286,16 @@ def test_dit_restatement_reproduces_dit_xl_2_parameter_count():
     total = sum(p.numel() for p in m.parameters())
     embedder = sum(p.numel() for p in m.transformer_blocks[0].norm1.emb.parameters())
     assert total - 27 * embedder + 256 * 1152 == 675_129_632
+
+
+def test_product_unet_class_has_the_same_published_parameter_count():
+    """dcb200.UNetCondition2D keeps diffusers' parameter names and shapes (reference checkpoints load into it): at the
+    Stable Diffusion v1.x config it too has 859 520 964 parameters + encoder_hid_proj."""
+    import dcb200
+    with torch.device("meta"):
+        m = dcb200.UNetCondition2D(sample_size=64, in_channels=4, out_channels=4, block_out_channels=(320, 640, 1280, 1280),
+                                   layers_per_block=2, cross_attention_dim=768, attention_head_dim=8, encoder_hid_dim=16,
+                                   encoder_hid_dim_type="text_proj",
+                                   down_block_types=("CrossAttnDownBlock2D",) * 3 + ("DownBlock2D",),
+                                   up_block_types=("UpBlock2D",) + ("CrossAttnUpBlock2D",) * 3)
+    assert sum(p.numel() for p in m.parameters()) - (16 * 768 + 768) == 859_520_964
