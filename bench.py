@@ -382,7 +382,7 @@ def run_ours(args):
         v, dt = cpu_port_run(arch, cfg, 1, n_t, threads)
         cpu = {"value": v, "unit": "evals/s", "cores": threads, "kind": "port", "seconds": dt,
                "sample": f"1 image x {n_t} timesteps x {classes} classes ({n_t * classes} evals) of the same workload, "
-                         f"fp32 oracle port (reference loop + restated diffusers U-Net) on torch CPU"}
+                         f"fp32 oracle port (reference loop + restated diffusers denoiser) on torch CPU"}
 
     eager = None
     if rank == 0 and world == 1 and not args.no_cpu:
