@@ -299,3 +299,21 @@ def test_product_unet_class_has_the_same_published_parameter_count():
                                    down_block_types=("CrossAttnDownBlock2D",) * 3 + ("DownBlock2D",),
                                    up_block_types=("UpBlock2D",) + ("CrossAttnUpBlock2D",) * 3)
     assert sum(p.numel() for p in m.parameters()) - (16 * 768 + 768) == 859_520_964
+
+
+def test_geglu_feed_forward_matches_transformers_clvp_gated_mlp():
+    """oracle GEGLU / FeedForward("geglu") -- one Linear to 2 x inner, FIRST half the value, SECOND half the gate,
+    value * gelu(gate) with the exact (erf) GELU, then Linear(inner, dim) -- against CLVP's ClvpGatedLinearUnit / ClvpEncoderMLP
+    (tortoise-tts' port of the same x-transformers / latent-diffusion GEGLU) with hidden_act = "gelu"."""
+    from types import SimpleNamespace
+    from oracle import diffusers_restated as dr
+    MLP = _tf("clvp.modeling_clvp", "ClvpEncoderMLP")
+    torch.manual_seed(11)
+    dim = 24
+    ours = dr.FeedForward(dim, "geglu").double()
+    ref = MLP(SimpleNamespace(hidden_act="gelu", hidden_size=dim, intermediate_size=4 * dim, dropout=0.0)).double().eval()
+    ref.fc1.proj.load_state_dict(ours.net[0].proj.state_dict())
+    ref.fc2.load_state_dict(ours.net[2].state_dict())
+    x = torch.randn(3, 5, dim, dtype=torch.float64)
+    assert (ours(x) - ref(x)).abs().max() < 1e-12
+    assert (ours.net[0](x) - ref.fc1(x)).abs().max() < 1e-12
